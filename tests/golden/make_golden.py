@@ -1,0 +1,176 @@
+"""Generate the golden fixtures in tests/golden/ by RUNNING THE REFERENCE's own code.
+
+Run once in the build container (needs /root/reference; the GPU box does not have it):
+
+    python tests/golden/make_golden.py
+
+What is executed (all paths relative to /root/reference/minddet/models):
+  * pointpillars/src/core/nms.py:85-112      nms_jit(dets, thresh, eps=0.0)
+  * pointpillars/src/core/nms.py:7-41        apply_nms(boxes, scores, thres, max_boxes)  (+1 areas)
+  * pointpillars/src/core/box_np_ops.py:639-679   iou_jit(boxes, query, eps=1.0)
+  * pointpillars/src/core/target_assigner.py:29-166  create_target_np(..., positive_fraction=None)
+  * pointpillars/src/core/box_np_ops.py:453-523   create_anchors_3d_stride (grid order)
+  * centerpoint/det3d_ms/ops/iou-bev-nms-org.cpp:237-283  boxes_iou_nms_cpu, compiled by
+    oracle/Makefile into oracle/_ref/nms_fast_ref.so and called through the 7-argument aot ABI.
+`mindspore` is not installed, so a stub module is injected; none of the functions above touch it
+except apply_nms's `.asnumpy()` calls, which a tiny wrapper provides.
+"""
+import ctypes
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference/minddet/models"
+
+
+def _stub_mindspore():
+    ms = types.ModuleType("mindspore")
+    ms.ops = types.ModuleType("mindspore.ops")
+    ms.nn = types.ModuleType("mindspore.nn")
+
+    class _T:  # the two MindSpore calls create_anchors_3d_stride makes, with numpy semantics
+        @staticmethod
+        def from_numpy(a):
+            return _AsNumpy(a)
+
+    ms.Tensor = _T
+    ms.ops.Tensor = _T
+    ms.ops.meshgrid = lambda *ts, indexing="xy": tuple(
+        _AsNumpy(m) for m in np.meshgrid(*[t.asnumpy() for t in ts], indexing=indexing))
+    sys.modules["mindspore"] = ms
+    sys.modules["mindspore.ops"] = ms.ops
+    sys.modules["mindspore.nn"] = ms.nn
+
+
+class _AsNumpy:
+    def __init__(self, a):
+        self.a = a
+
+    def asnumpy(self):
+        return self.a
+
+
+def rand_boxes(rng, n, img_w=1344.0, img_h=800.0, smin=8.0, smax=400.0, cluster=None):
+    if cluster is None:
+        cx = rng.uniform(0, img_w, n)
+        cy = rng.uniform(0, img_h, n)
+    else:
+        ctr = rng.uniform([0, 0], [img_w, img_h], (cluster, 2))
+        pick = rng.integers(0, cluster, n)
+        cx = ctr[pick, 0] + rng.normal(0, 12, n)
+        cy = ctr[pick, 1] + rng.normal(0, 12, n)
+    w = np.exp(rng.uniform(np.log(smin), np.log(smax), n))
+    h = np.exp(rng.uniform(np.log(smin), np.log(smax), n))
+    b = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1)
+    b[:, 0::2] = np.clip(b[:, 0::2], 0, img_w - 1)
+    b[:, 1::2] = np.clip(b[:, 1::2], 0, img_h - 1)
+    return b.astype(np.float32)
+
+
+def main():
+    _stub_mindspore()
+    sys.path.insert(0, os.path.join(REF, "pointpillars"))
+    from src.core import box_np_ops, nms as ref_nms, target_assigner
+
+    rng = np.random.default_rng(20261018)
+    out = {}
+
+    # ---- nms_jit (offset 0, inclusive >=, no union guard) ------------------------------------
+    for tag, n, cl in (("a", 300, None), ("b", 500, 12), ("c", 64, 3)):
+        boxes = rand_boxes(rng, n, cluster=cl)
+        if tag == "c":  # exact duplicates and degenerate boxes
+            boxes[10] = boxes[3]
+            boxes[20, 2] = boxes[20, 0]
+        scores = rng.permutation(n).astype(np.float32) / n
+        dets = np.concatenate([boxes, scores[:, None]], 1).astype(np.float32)
+        for thr in (0.3, 0.7):
+            keep = np.array(ref_nms.nms_jit(dets, np.float32(thr), eps=0.0), dtype=np.int64)
+            out[f"nmsjit_{tag}_{thr}_dets"] = dets
+            out[f"nmsjit_{tag}_{thr}_keep"] = keep
+
+    # ---- apply_nms (+1 areas, keeps ovr <= thr i.e. suppresses strict >) ---------------------
+    for tag, n, cl in (("a", 256, None), ("b", 400, 10)):
+        boxes = np.round(rand_boxes(rng, n, cluster=cl))
+        scores = rng.permutation(n).astype(np.float32) / n
+        for thr in (0.5, 0.7):
+            keep = ref_nms.apply_nms(_AsNumpy(boxes), _AsNumpy(scores), np.float32(thr), 10 ** 9)
+            out[f"applynms_{tag}_{thr}_boxes"] = boxes
+            out[f"applynms_{tag}_{thr}_scores"] = scores
+            out[f"applynms_{tag}_{thr}_keep"] = np.asarray(keep, np.int64)
+
+    # ---- iou_jit(eps=1) ------------------------------------------------------------------------
+    a = rand_boxes(rng, 700)
+    g = rand_boxes(rng, 23, smin=16, smax=512)
+    out["iou_boxes"] = a
+    out["iou_gts"] = g
+    out["iou_mat"] = box_np_ops.iou_jit(a, g, eps=1.0)
+
+    # ---- create_target_np (positive_fraction=None: deterministic) -------------------------------
+    def sim(anchors, gts):
+        return box_np_ops.iou_jit(anchors, gts, eps=1.0).astype(np.float32)
+
+    def enc(gts, anchors):
+        return np.zeros((anchors.shape[0], 4), np.float32)
+
+    for tag, n, ng, pos, neg in (("a", 3000, 9, 0.7, 0.3), ("b", 2000, 17, 0.5, 0.5), ("c", 1500, 5, 0.6, 0.45)):
+        anchors = np.round(rand_boxes(rng, n, smin=16, smax=300))
+        gts = np.round(rand_boxes(rng, ng, smin=24, smax=400))
+        if tag == "b":  # duplicated anchors -> ties for a gt's best anchor; one far-away gt
+            anchors[100:110] = anchors[50:60]
+            gts[3] = anchors[55]
+            gts[4] = np.array([5000, 5000, 5100, 5100], np.float32)
+        r = target_assigner.create_target_np(
+            anchors, gts, sim, enc, matched_threshold=float(pos), unmatched_threshold=float(neg),
+            positive_fraction=None, box_code_size=4)
+        gt_ids = np.full(n, -1, np.int32)
+        gt_ids[r["assigned_anchors_inds"]] = r["positive_gt_id"]
+        out[f"assign_{tag}_anchors"] = anchors
+        out[f"assign_{tag}_gts"] = gts
+        out[f"assign_{tag}_thr"] = np.array([pos, neg], np.float32)
+        out[f"assign_{tag}_labels"] = r["labels"].astype(np.int32)
+        out[f"assign_{tag}_gtids"] = gt_ids
+
+    # ---- grid order of the reference anchor generator -------------------------------------------
+    # (create_anchors_3d_range :526-568 is broken under numpy 2 -- tuple assignment -- so the
+    #  strided generator :453-523 is used; ms.ops.meshgrid is stubbed with np.meshgrid.)
+    anc = box_np_ops.create_anchors_3d_stride([1, 5, 7], sizes=(1.0, 2.0, 3.0), rotations=(0.0, 1.0),
+                                              anchor_range=[0.0, 0.0, 0.0, 6 * 8.0, 4 * 8.0, 0.0])
+    out["grid_ref"] = np.asarray(anc, np.float32)  # [1,5,7,1,2,7]: x fastest, per-cell variants innermost
+
+    # ---- compiled reference aot CPU op ----------------------------------------------------------
+    so = os.path.join(REPO, "oracle", "_ref", "nms_fast_ref.so")
+    lib = ctypes.CDLL(so)
+    n = 1000  # the reference hard-codes N=1000 (iou-bev-nms-org.cpp:244)
+    ctr = rng.uniform([0, -40], [70, 40], (40, 2))
+    pick = rng.integers(0, 40, n)
+    boxes = np.zeros((n, 7), np.float32)
+    boxes[:, 0] = ctr[pick, 0] + rng.normal(0, 1.0, n)
+    boxes[:, 1] = ctr[pick, 1] + rng.normal(0, 1.0, n)
+    boxes[:, 3] = rng.uniform(1.5, 4.5, n)
+    boxes[:, 4] = rng.uniform(1.2, 2.2, n)
+    boxes[:, 5] = 1.5
+    boxes[:, 6] = rng.uniform(-np.pi, np.pi, n)
+    boxes[-20:, 3] = 0.0  # zero-area padding rows are pre-removed (:253-255)
+    thr = np.array([0.2], np.float32)
+    keep = np.zeros(n, np.int32)
+    cnt = np.zeros(1, np.int32)
+    params = (ctypes.c_void_p * 4)(boxes.ctypes.data, thr.ctypes.data, keep.ctypes.data, cnt.ctypes.data)
+    rc = lib.boxes_iou_nms_cpu(4, params, None, None, None, None, None)
+    assert rc == 0
+    assert lib.boxes_iou_nms_cpu(3, params, None, None, None, None, None) == 1
+    out["rotnms_boxes"] = boxes
+    out["rotnms_thr"] = thr
+    out["rotnms_keep"] = keep
+    out["rotnms_count"] = cnt
+
+    path = os.path.join(HERE, "reference_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

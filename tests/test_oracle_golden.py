@@ -1,0 +1,70 @@
+"""Pin the CPU oracle against fixtures produced by RUNNING the reference's own code
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+
+import oracle as O
+
+
+def _keep_from_mask(m):
+    return np.nonzero(m)[0]
+
+
+def test_nms_mode_nms_jit_bit_exact(golden):
+    # pointpillars/src/core/nms.py:85-112: offset 0, suppress iou >= thr, no union guard.
+    for tag in "abc":
+        for thr in (0.3, 0.7):
+            dets = golden[f"nmsjit_{tag}_{thr}_dets"]
+            ref_keep = golden[f"nmsjit_{tag}_{thr}_keep"]
+            order = np.argsort(-dets[:, 4], kind="stable")  # scores are a permutation: no ties
+            mask = O.nms(dets[order], np.float32(thr), off=0.0, inclusive=True, union_eps=0.0)
+            assert np.array_equal(order[_keep_from_mask(mask)], ref_keep), (tag, thr)
+
+
+def test_nms_mode_apply_nms_bit_exact(golden):
+    # pointpillars/src/core/nms.py:7-41: +1 areas, keeps ovr <= thr (suppress strict >).
+    for tag in "ab":
+        for thr in (0.5, 0.7):
+            boxes = golden[f"applynms_{tag}_{thr}_boxes"]
+            scores = golden[f"applynms_{tag}_{thr}_scores"]
+            ref_keep = golden[f"applynms_{tag}_{thr}_keep"]
+            order = np.argsort(-scores, kind="stable")
+            mask = O.nms(boxes[order], np.float32(thr), off=1.0, inclusive=False, union_eps=0.0)
+            assert np.array_equal(order[_keep_from_mask(mask)], ref_keep), (tag, thr)
+
+
+def test_iou_plus_one_matches_iou_jit(golden):
+    # pointpillars/src/core/box_np_ops.py:639-679 with eps=1.0 (numba evaluates in float64).
+    got = O.iou_matrix(golden["iou_boxes"], golden["iou_gts"], off=1.0)
+    ref = golden["iou_mat"]
+    assert np.array_equal(got == 0, ref == 0)
+    np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-7)
+
+
+def test_assign_mode1_matches_create_target_np(golden):
+    # pointpillars/src/core/target_assigner.py:84-134 (positive_fraction=None).
+    for tag in "abc":
+        anchors, gts = golden[f"assign_{tag}_anchors"], golden[f"assign_{tag}_gts"]
+        pos, neg = golden[f"assign_{tag}_thr"]
+        labels, gtids = golden[f"assign_{tag}_labels"], golden[f"assign_{tag}_gtids"]
+        a, _, _ = O.assign(anchors, gts, pos, neg, 0.0, off=1.0, mode=1)
+        assert np.array_equal(a > 0, labels > 0), tag
+        assert np.array_equal(a == 0, labels == 0), tag
+        assert np.array_equal(a == -1, labels == -1), tag
+        fg = labels > 0
+        assert fg.sum() > 0
+        assert np.array_equal(a[fg] - 1, gtids[fg]), tag
+
+
+def test_anchor_grid_order_matches_reference_generator(golden):
+    # pointpillars/src/core/box_np_ops.py:453-523: output [D,H,W,S,R,7]; x fastest, per-cell innermost.
+    ref = golden["grid_ref"]  # (1,5,7,1,2,7), centres on an 8-px lattice
+    H, W, A = 5, 7, 2
+    base = np.array([[-1, -1, 1, 1], [-2, -2, 2, 2]], np.float32)
+    mine = O.anchor_grid(base, H, W, 8.0).reshape(H, W, A, 4)
+    cx = (mine[..., 0] + mine[..., 2]) * 0.5
+    cy = (mine[..., 1] + mine[..., 3]) * 0.5
+    np.testing.assert_allclose(cx, ref[0, :, :, 0, :, 0], atol=1e-5)
+    np.testing.assert_allclose(cy, ref[0, :, :, 0, :, 1], atol=1e-5)
+    # per-cell variants are the innermost axis in both
+    assert np.array_equal(ref[0, 2, 3, 0, :, 6], np.array([0.0, 1.0], np.float32))
+    assert np.array_equal(mine[2, 3, :, 2] - mine[2, 3, :, 0], np.array([2.0, 4.0], np.float32))
