@@ -1,0 +1,135 @@
+/*
+ * md_region_aot.h -- the drop-in boundary of libmdregion.so.
+ *
+ * Every entry point has the MindSpore `ops.Custom(func_type="aot")` signature, i.e. exactly what the
+ * reference binds for its own custom ops:
+ *   - GPU exemplar:  minddet/models/centerpoint/det3d_ms/ops/test_custom_pytorch/iou3d_nms_kernel.cu:445-446
+ *                    (`extern "C" int NmsNormalGpu(int nparam, void** params, int* ndims,
+ *                      int64_t** shapes, const char** dtypes, void* stream, void* extra)`)
+ *   - CPU exemplar:  minddet/models/centerpoint/det3d_ms/ops/iou-bev-nms-org.cpp:237
+ *   - Python side:   minddet/models/centerpoint/det3d_ms/ops/test_custom_pytorch/iou_gpu.py:55-60,
+ *                    minddet/models/centerpoint/det3d_ms/ops/nms_cpu.py:10-27
+ *
+ * Contract:
+ *   params[0 .. n_in-1] are inputs, params[n_in .. nparam-1] outputs, all DEVICE pointers owned by the
+ *   caller (outputs pre-sized from out_shape/out_dtype); ndims[i]/shapes[i][d]/dtypes[i] describe
+ *   param i; `stream` is the cudaStream_t the framework executes on -- all work is enqueued on it and
+ *   never synchronised; scratch comes from a per-(device,stream) cached workspace inside the library.
+ *   Float attributes travel as a trailing 1-D float32 `cfg` INPUT TENSOR that is read on the device
+ *   (the reference passes its NMS threshold the same way, iou_gpu.py:57, iou3d_nms_kernel.cu:500);
+ *   integer attributes travel in the output shapes.  No dynamic output shapes: fixed size + mask/count.
+ * Return value: 0 success; 1 wrong nparam; 2 bad dtype/shape; 3 CUDA error; 4 unsupported size.
+ *   (the reference returns 1 on wrong nparam, iou-bev-nms-org.cpp:238, and 0 on success, :282.)
+ * There is NO CPU fallback: without a CUDA device every entry returns 3.
+ *
+ * cfg slot tables: the MD_CFG_* enums below.
+ */
+#ifndef MD_REGION_AOT_H_
+#define MD_REGION_AOT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- cfg tensor slots (float32, read on the device) ------------------------------------------ */
+enum { /* MD_CFG_DECODE: 11 floats */
+    MD_DEC_IMG_H = 0, MD_DEC_IMG_W = 1, MD_DEC_MEAN0 = 2, MD_DEC_STD0 = 6, MD_DEC_MAX_RATIO = 10,
+    MD_DEC_LEN = 11, MD_DEC_STRIDE = 11 /* MdDecodeLevel only */
+};
+enum { /* MD_CFG_NMS: 4 floats */
+    MD_NMS_THR = 0, MD_NMS_OFFSET = 1, MD_NMS_INCLUSIVE = 2, MD_NMS_UNION_EPS = 3, MD_NMS_LEN = 4
+};
+enum { /* MD_CFG_PROPOSAL: MD_CFG_DECODE (0..10) + these + one stride per level */
+    MD_PROP_NMS_THR = 11, MD_PROP_NMS_OFFSET = 12, MD_PROP_NMS_INCLUSIVE = 13, MD_PROP_UNION_EPS = 14,
+    MD_PROP_APPLY_SIGMOID = 15, MD_PROP_STRIDE0 = 16
+};
+enum { /* MD_CFG_ASSIGN: 16 floats */
+    MD_AS_POS_THR = 0, MD_AS_NEG_THR = 1, MD_AS_MIN_POS_IOU = 2, MD_AS_IOU_OFFSET = 3, MD_AS_MODE = 4,
+    MD_AS_NUM_TOTAL = 5, MD_AS_MEAN0 = 6, MD_AS_STD0 = 10, MD_AS_LEN = 16
+};
+enum { /* MD_CFG_ROI: 4 floats + one stride per level */
+    MD_ROI_FINEST = 0, MD_ROI_SAMPLE_NUM = 1, MD_ROI_END_MODE = 2, MD_ROI_STRIDE0 = 4
+};
+
+#if defined(__GNUC__)
+#define MD_API __attribute__((visibility("default")))
+#else
+#define MD_API
+#endif
+
+#define MD_AOT_ARGS int nparam, void **params, int *ndims, int64_t **shapes, const char **dtypes, void *stream, void *extra
+
+/* a1  AnchorGenerator.grid_anchors
+ *   in : base (A,4) f32 | cfg f32[>=1] = {stride}
+ *   out: anchors (H,W,A,4) f32                       (n = (h*W+w)*A+a) */
+MD_API int MdAnchorGrid(MD_AOT_ARGS);
+
+/* a2  BoundingBoxDecode on gathered rows
+ *   in : anchors (K,4) f32 | deltas (K,4) f32 | cfg f32[11] = MD_CFG_DECODE
+ *   out: boxes (K,4) f32 */
+MD_API int MdDecodeClip(MD_AOT_ARGS);
+
+/* a2  decode-all form, straight from the RPN head layout, anchors regenerated in registers
+ *   in : deltas (B,4A,H,W) f32 | base (A,4) f32 | cfg f32[12] = MD_CFG_DECODE + {stride}
+ *   out: boxes (B,H*W*A,4) f32 */
+MD_API int MdDecodeLevel(MD_AOT_ARGS);
+
+/* a3  TopK(sorted=True) per (image, level)
+ *   in : scores (B,A,H,W) f32 [head layout, index n=(h*W+w)*A+a]  or (B,N) f32 [flat]
+ *        | cfg f32[1] = {apply_sigmoid}
+ *   out: values (B,K) f32 | indices (B,K) int32 */
+MD_API int MdTopKPerLevel(MD_AOT_ARGS);
+
+/* a4  NMSWithMask on score-sorted boxes (reference I/O shape: NmsNormalGpu, keep[N] + count[1])
+ *   in : boxes (K,C>=4) or (B,K,C>=4) f32 [x1,y1,x2,y2,...] | cfg f32[4] = MD_CFG_NMS
+ *   out: keep_idx (B,K) int32 (kept positions, ascending, zero padded) | mask (B,K) uint8/bool
+ *        | count (B) int32 */
+MD_API int MdNms(MD_AOT_ARGS);
+
+/* a3..a6  Proposal (top-k -> gather -> decode -> NMS per level -> cross-level merge), L levels
+ *   in : scores_0..scores_{L-1} (B,A,H_l,W_l) | deltas_0..deltas_{L-1} (B,4A,H_l,W_l)
+ *        | base_0..base_{L-1} (A,4) | cfg f32[16+L] = MD_CFG_PROPOSAL
+ *   out: proposals (B,max_num,5) f32 | mask (B,max_num) uint8/bool
+ *        | topk_idx (B,L,nms_pre) int32 (-1 padded) | keep (B,L,nms_pre) uint8/bool
+ *   (nparam = 3L+1+4; nms_pre and max_num are read from the output shapes) */
+MD_API int MdProposal(MD_AOT_ARGS);
+
+/* a7/a8  BboxAssignSample (RPN flavour)
+ *   in : boxes (N,4) [shared by the batch] or (B,N,4) f32 | box_valid (N)/(B,N) uint8/bool
+ *        | gts (B,G,4) f32 | gt_valid (B,G) uint8/bool | cfg f32[16] = MD_CFG_ASSIGN | seed int32[2]
+ *   out: assigned (B,N) int32 | pos_idx (B,Sp) int32 | pos_valid (B,Sp) uint8 | neg_idx (B,Sn) int32
+ *        | neg_valid (B,Sn) uint8 | pos_gt (B,Sp) int32 | pos_target (B,Sp,4) f32 | num_pos (B) int32 */
+MD_API int MdAssignSample(MD_AOT_ARGS);
+
+/* a8  BboxAssignSampleForRcnn (gts are prepended to the proposals as candidates)
+ *   in : proposals (B,P,5) f32 | prop_mask (B,P) uint8/bool | gts (B,G,4) f32 | gt_labels (B,G) int32
+ *        | gt_valid (B,G) uint8/bool | cfg f32[16] = MD_CFG_ASSIGN | seed int32[2]
+ *   out: rois (B,S,5) f32 [batch,x1,y1,x2,y2] | deltas (B,S,4) f32 | labels (B,S) int32
+ *        | mask (B,S) uint8 | assigned (B,G+P) int32 | sel_idx (B,S) int32 | pos_gt (B,Sp) int32
+ *        | num_pos (B) int32          (S = Sp+Sn; Sp is read from pos_gt's shape) */
+MD_API int MdAssignSampleRcnn(MD_AOT_ARGS);
+
+/* a9   RoI -> pyramid level
+ *   in : rois (R,5) f32 | cfg f32[2] = {finest_scale, num_levels}
+ *   out: levels (R) int32 */
+MD_API int MdRoiLevels(MD_AOT_ARGS);
+
+/* a9+a10  SingleRoIExtractor forward (level map + RoIAlign on the mapped level only)
+ *   in : rois (R,5) f32 | feat_0..feat_{L-1} (B,C,H_l,W_l) f32 | cfg f32[4+L] = MD_CFG_ROI
+ *   out: roi_feats (R,C,P,P) f32            (nparam = L+2+1) */
+MD_API int MdRoiAlignFwd(MD_AOT_ARGS);
+
+/* a11  ROIAlignGrad (bprop of MdRoiAlignFwd); outputs are zero-filled then accumulated
+ *   in : rois (R,5) f32 | dout (R,C,P,P) f32 | cfg f32[4+L]
+ *   out: dfeat_0..dfeat_{L-1} (B,C,H_l,W_l) f32     (nparam = 3+L) */
+MD_API int MdRoiAlignBwd(MD_AOT_ARGS);
+
+/* library info: returns a static string "libmdregion <version> sm_100a" */
+MD_API const char *MdVersion(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MD_REGION_AOT_H_ */

@@ -1,0 +1,317 @@
+// aot_entry.cu -- the extern "C" boundary declared in include/md_region_aot.h.
+//
+// Each symbol has the MindSpore ops.Custom(func_type="aot") signature the reference binds
+// (centerpoint/det3d_ms/ops/test_custom_pytorch/iou3d_nms_kernel.cu:445-446, 491-492, 548-549).
+// Differences from the reference's entry points, on purpose:
+//   * work is enqueued on the stream MindSpore passes and never synchronised (the reference
+//     cudaStreamSynchronize()s it and launches on the default stream, :448-449);
+//   * no libtorch (the reference wraps raw pointers as at::Tensor, ms_ext.cpp:14-27);
+//   * scratch comes from a per-(device,stream) grow-only workspace, not cudaMalloc/cudaFree per call (:510-517);
+//   * errors are returned, never exit()ed (:32-40).
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
+
+#include "../../include/md_region_aot.h"
+#include "kernels.h"
+
+namespace {
+
+enum { MD_OK = 0, MD_ERR_NPARAM = 1, MD_ERR_ARG = 2, MD_ERR_CUDA = 3, MD_ERR_SIZE = 4 };
+
+struct Workspace { void *ptr = nullptr; size_t bytes = 0; };
+std::mutex g_ws_mutex;
+std::map<std::pair<int, void *>, Workspace> g_ws;
+
+// Grow-only scratch keyed by (device, stream).  Growth frees the old block with cudaFree, which
+// waits for the device, so no kernel that still uses it can be in flight.  (Warm up before capturing
+// a CUDA graph: allocation is not capturable.)
+int get_workspace(void *stream, size_t bytes, void **out)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return MD_ERR_CUDA;
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    Workspace &w = g_ws[std::make_pair(dev, stream)];
+    if (w.bytes < bytes) {
+        if (w.ptr) cudaFree(w.ptr);
+        w.ptr = nullptr; w.bytes = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        if (cudaMalloc(&w.ptr, want) != cudaSuccess) { cudaGetLastError(); return MD_ERR_CUDA; }
+        w.bytes = want;
+    }
+    *out = w.ptr;
+    return MD_OK;
+}
+
+bool is_f32(const char *d) { return d && std::strcmp(d, "float32") == 0; }
+bool is_i32(const char *d) { return d && std::strcmp(d, "int32") == 0; }
+bool is_u8(const char *d) { return d && (std::strcmp(d, "uint8") == 0 || std::strcmp(d, "bool") == 0 || std::strcmp(d, "int8") == 0); }
+
+int64_t numel(int nd, const int64_t *sh)
+{
+    int64_t n = 1;
+    for (int i = 0; i < nd; i++) n *= sh[i];
+    return n;
+}
+int cuda_rc(cudaError_t e) { return e == cudaSuccess ? MD_OK : (e == cudaErrorInvalidValue ? MD_ERR_SIZE : MD_ERR_CUDA); }
+
+#define REQ(cond) do { if (!(cond)) return MD_ERR_ARG; } while (0)
+#define NEED_ARGS() do { if (!params || !ndims || !shapes || !dtypes) return MD_ERR_ARG; } while (0)
+
+}  // namespace
+
+extern "C" {
+
+const char *MdVersion(void) { return "libmdregion 0.1.0 sm_100a"; }
+
+int MdAnchorGrid(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam != 3) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    REQ(is_f32(dtypes[0]) && is_f32(dtypes[1]) && is_f32(dtypes[2]));
+    REQ(ndims[0] == 2 && shapes[0][1] == 4 && ndims[2] == 4 && shapes[2][3] == 4 && shapes[2][2] == shapes[0][0]);
+    REQ(numel(ndims[1], shapes[1]) >= 1);
+    return cuda_rc(md::launch_anchor_grid((const float *)params[0], (int)shapes[0][0], (int)shapes[2][0], (int)shapes[2][1],
+                                          (const float *)params[1], (float *)params[2], (cudaStream_t)stream));
+}
+
+int MdDecodeClip(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam != 4) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    for (int i = 0; i < 4; i++) REQ(is_f32(dtypes[i]));
+    REQ(ndims[0] == 2 && shapes[0][1] == 4 && ndims[1] == 2 && shapes[1][1] == 4 && shapes[1][0] == shapes[0][0]);
+    REQ(ndims[3] == 2 && shapes[3][0] == shapes[0][0] && shapes[3][1] == 4);
+    REQ(numel(ndims[2], shapes[2]) >= MD_DEC_LEN);
+    return cuda_rc(md::launch_decode_rows((const float *)params[0], (const float *)params[1], shapes[0][0],
+                                          (const float *)params[2], (float *)params[3], (cudaStream_t)stream));
+}
+
+int MdDecodeLevel(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam != 4) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    for (int i = 0; i < 4; i++) REQ(is_f32(dtypes[i]));
+    REQ(ndims[0] == 4 && ndims[1] == 2 && shapes[1][1] == 4 && shapes[0][1] == 4 * shapes[1][0]);
+    const int B = (int)shapes[0][0], A = (int)shapes[1][0], H = (int)shapes[0][2], W = (int)shapes[0][3];
+    REQ(ndims[3] == 3 && shapes[3][0] == B && shapes[3][1] == (int64_t)H * W * A && shapes[3][2] == 4);
+    REQ(numel(ndims[2], shapes[2]) >= MD_DEC_LEN + 1);
+    return cuda_rc(md::launch_decode_level((const float *)params[0], (const float *)params[1], B, A, H, W,
+                                           (const float *)params[2], (float *)params[3], (cudaStream_t)stream));
+}
+
+int MdTopKPerLevel(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam != 4) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    REQ(is_f32(dtypes[0]) && is_f32(dtypes[1]) && is_f32(dtypes[2]) && is_i32(dtypes[3]));
+    REQ(ndims[0] == 4 || ndims[0] == 2);
+    const int B = (int)shapes[0][0];
+    int A = 0, HW = 0;
+    if (ndims[0] == 4) { A = (int)shapes[0][1]; HW = (int)(shapes[0][2] * shapes[0][3]); }
+    else HW = (int)shapes[0][1];
+    REQ(ndims[2] == 2 && ndims[3] == 2 && shapes[2][0] == B && shapes[3][0] == B && shapes[2][1] == shapes[3][1]);
+    const int K = (int)shapes[2][1];
+    if (K > 2048 || (int64_t)(A ? A : 1) * HW >= (1 << 22)) return MD_ERR_SIZE;
+    REQ(numel(ndims[1], shapes[1]) >= 1);
+    return cuda_rc(md::launch_topk((const float *)params[0], B, A, HW, K, (const float *)params[1],
+                                   (float *)params[2], (int32_t *)params[3], (cudaStream_t)stream));
+}
+
+int MdNms(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam != 5) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    REQ(is_f32(dtypes[0]) && is_f32(dtypes[1]) && is_i32(dtypes[2]) && is_u8(dtypes[3]) && is_i32(dtypes[4]));
+    REQ(ndims[0] == 2 || ndims[0] == 3);
+    const int B = ndims[0] == 3 ? (int)shapes[0][0] : 1;
+    const int K = (int)shapes[0][ndims[0] - 2], ld = (int)shapes[0][ndims[0] - 1];
+    REQ(ld >= 4);
+    REQ(numel(ndims[1], shapes[1]) >= MD_NMS_LEN);
+    REQ(numel(ndims[2], shapes[2]) == (int64_t)B * K && numel(ndims[3], shapes[3]) == (int64_t)B * K && numel(ndims[4], shapes[4]) == B);
+    if (K > 2048) return MD_ERR_SIZE;
+    void *ws = nullptr;
+    int rc = get_workspace(stream, md::nms_workspace_bytes(B, K), &ws);
+    if (rc) return rc;
+    return cuda_rc(md::launch_nms((const float *)params[0], ld, B, K, (const float *)params[1], ws,
+                                  (int32_t *)params[2], (uint8_t *)params[3], (int32_t *)params[4], (cudaStream_t)stream));
+}
+
+int MdProposal(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam < 8 || (nparam - 5) % 3 != 0) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    const int L = (nparam - 5) / 3;
+    if (L > md::kMaxLv) return MD_ERR_SIZE;
+    md::LevelSet lv{};
+    lv.L = L;
+    const int B = (int)shapes[0][0];
+    for (int l = 0; l < L; l++) {
+        const int is = l, id = L + l, ib = 2 * L + l;
+        REQ(is_f32(dtypes[is]) && is_f32(dtypes[id]) && is_f32(dtypes[ib]));
+        REQ(ndims[is] == 4 && ndims[id] == 4 && ndims[ib] == 2 && shapes[ib][1] == 4);
+        lv.A[l] = (int)shapes[is][1]; lv.H[l] = (int)shapes[is][2]; lv.W[l] = (int)shapes[is][3];
+        REQ(shapes[is][0] == B && shapes[id][0] == B && shapes[id][1] == 4 * lv.A[l] && shapes[id][2] == lv.H[l] && shapes[id][3] == lv.W[l]);
+        REQ(shapes[ib][0] == lv.A[l]);
+        lv.scores[l] = (const float *)params[is]; lv.deltas[l] = (const float *)params[id]; lv.base[l] = (const float *)params[ib];
+    }
+    const int ic = 3 * L, o0 = 3 * L + 1;
+    REQ(is_f32(dtypes[ic]) && numel(ndims[ic], shapes[ic]) >= MD_PROP_STRIDE0 + L);
+    REQ(is_f32(dtypes[o0]) && is_u8(dtypes[o0 + 1]) && is_i32(dtypes[o0 + 2]) && is_u8(dtypes[o0 + 3]));
+    REQ(ndims[o0] == 3 && shapes[o0][0] == B && shapes[o0][2] == 5);
+    const int max_num = (int)shapes[o0][1];
+    REQ(numel(ndims[o0 + 1], shapes[o0 + 1]) == (int64_t)B * max_num);
+    REQ(ndims[o0 + 2] == 3 && shapes[o0 + 2][0] == B && shapes[o0 + 2][1] == L);
+    const int nms_pre = (int)shapes[o0 + 2][2];
+    REQ(numel(ndims[o0 + 3], shapes[o0 + 3]) == (int64_t)B * L * nms_pre);
+    if (nms_pre > 2048) return MD_ERR_SIZE;
+    void *ws = nullptr;
+    int rc = get_workspace(stream, md::proposal_workspace_bytes(B, L, nms_pre), &ws);
+    if (rc) return rc;
+    return cuda_rc(md::launch_proposal(lv, B, nms_pre, max_num, (const float *)params[ic], ws, (float *)params[o0],
+                                       (uint8_t *)params[o0 + 1], (int32_t *)params[o0 + 2], (uint8_t *)params[o0 + 3],
+                                       (cudaStream_t)stream));
+}
+
+int MdAssignSample(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam != 14) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    REQ(is_f32(dtypes[0]) && is_u8(dtypes[1]) && is_f32(dtypes[2]) && is_u8(dtypes[3]) && is_f32(dtypes[4]) && is_i32(dtypes[5]));
+    REQ((ndims[0] == 2 || ndims[0] == 3) && shapes[0][ndims[0] - 1] == 4);
+    REQ(ndims[2] == 3 && shapes[2][2] == 4);
+    const int per_image = ndims[0] == 3;
+    const int N = (int)shapes[0][ndims[0] - 2];
+    const int B = (int)shapes[2][0], G = (int)shapes[2][1];
+    REQ(!per_image || shapes[0][0] == B);
+    REQ(numel(ndims[1], shapes[1]) == (per_image ? (int64_t)B * N : (int64_t)N));
+    REQ(numel(ndims[3], shapes[3]) == (int64_t)B * G);
+    REQ(numel(ndims[4], shapes[4]) >= MD_AS_LEN && numel(ndims[5], shapes[5]) >= 2);
+    const int o = 6;
+    REQ(is_i32(dtypes[o]) && is_i32(dtypes[o + 1]) && is_u8(dtypes[o + 2]) && is_i32(dtypes[o + 3]) && is_u8(dtypes[o + 4]) &&
+        is_i32(dtypes[o + 5]) && is_f32(dtypes[o + 6]) && is_i32(dtypes[o + 7]));
+    REQ(numel(ndims[o], shapes[o]) == (int64_t)B * N);
+    REQ(ndims[o + 1] == 2 && ndims[o + 3] == 2 && shapes[o + 1][0] == B && shapes[o + 3][0] == B);
+    const int Sp = (int)shapes[o + 1][1], Sn = (int)shapes[o + 3][1];
+    REQ(numel(ndims[o + 2], shapes[o + 2]) == (int64_t)B * Sp && numel(ndims[o + 4], shapes[o + 4]) == (int64_t)B * Sn);
+    REQ(numel(ndims[o + 5], shapes[o + 5]) == (int64_t)B * Sp && numel(ndims[o + 6], shapes[o + 6]) == (int64_t)B * Sp * 4);
+    REQ(numel(ndims[o + 7], shapes[o + 7]) == B);
+    if (Sp > 2048 || Sn > 2048 || N >= (1 << 22) || G > 1024) return MD_ERR_SIZE;
+    void *ws = nullptr;
+    int rc = get_workspace(stream, md::assign_workspace_bytes(B, G), &ws);
+    if (rc) return rc;
+    return cuda_rc(md::launch_assign_sample_rpn(
+        (const float *)params[0], per_image, (const uint8_t *)params[1], B, N, (const float *)params[2],
+        (const uint8_t *)params[3], G, (const float *)params[4], (const int32_t *)params[5], ws, Sp, Sn,
+        (int32_t *)params[o], (int32_t *)params[o + 1], (uint8_t *)params[o + 2], (int32_t *)params[o + 3],
+        (uint8_t *)params[o + 4], (int32_t *)params[o + 5], (float *)params[o + 6], (int32_t *)params[o + 7],
+        (cudaStream_t)stream));
+}
+
+int MdAssignSampleRcnn(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam != 15) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    REQ(is_f32(dtypes[0]) && is_u8(dtypes[1]) && is_f32(dtypes[2]) && is_i32(dtypes[3]) && is_u8(dtypes[4]) &&
+        is_f32(dtypes[5]) && is_i32(dtypes[6]));
+    REQ(ndims[0] == 3 && shapes[0][2] == 5 && ndims[2] == 3 && shapes[2][2] == 4);
+    const int B = (int)shapes[0][0], P = (int)shapes[0][1], G = (int)shapes[2][1];
+    REQ(shapes[2][0] == B);
+    REQ(numel(ndims[1], shapes[1]) == (int64_t)B * P && numel(ndims[3], shapes[3]) == (int64_t)B * G && numel(ndims[4], shapes[4]) == (int64_t)B * G);
+    REQ(numel(ndims[5], shapes[5]) >= MD_AS_LEN && numel(ndims[6], shapes[6]) >= 2);
+    const int o = 7;
+    REQ(is_f32(dtypes[o]) && is_f32(dtypes[o + 1]) && is_i32(dtypes[o + 2]) && is_u8(dtypes[o + 3]) && is_i32(dtypes[o + 4]) &&
+        is_i32(dtypes[o + 5]) && is_i32(dtypes[o + 6]) && is_i32(dtypes[o + 7]));
+    REQ(ndims[o] == 3 && shapes[o][0] == B && shapes[o][2] == 5);
+    const int S = (int)shapes[o][1];
+    REQ(ndims[o + 6] == 2 && shapes[o + 6][0] == B);
+    const int Sp = (int)shapes[o + 6][1], Sn = S - Sp;
+    REQ(Sn >= 0);
+    REQ(numel(ndims[o + 1], shapes[o + 1]) == (int64_t)B * S * 4 && numel(ndims[o + 2], shapes[o + 2]) == (int64_t)B * S &&
+        numel(ndims[o + 3], shapes[o + 3]) == (int64_t)B * S && numel(ndims[o + 4], shapes[o + 4]) == (int64_t)B * (G + P) &&
+        numel(ndims[o + 5], shapes[o + 5]) == (int64_t)B * S && numel(ndims[o + 7], shapes[o + 7]) == B);
+    if (Sp > 2048 || Sn > 2048 || G + P >= (1 << 22) || G > 1024) return MD_ERR_SIZE;
+    void *ws = nullptr;
+    int rc = get_workspace(stream, md::assign_workspace_bytes(B, G), &ws);
+    if (rc) return rc;
+    return cuda_rc(md::launch_assign_sample_rcnn(
+        (const float *)params[0], (const uint8_t *)params[1], B, P, (const float *)params[2], (const int32_t *)params[3],
+        (const uint8_t *)params[4], G, (const float *)params[5], (const int32_t *)params[6], ws, Sp, Sn,
+        (float *)params[o], (float *)params[o + 1], (int32_t *)params[o + 2], (uint8_t *)params[o + 3],
+        (int32_t *)params[o + 4], (int32_t *)params[o + 5], (int32_t *)params[o + 6], (int32_t *)params[o + 7],
+        (cudaStream_t)stream));
+}
+
+int MdRoiLevels(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam != 3) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    REQ(is_f32(dtypes[0]) && is_f32(dtypes[1]) && is_i32(dtypes[2]));
+    REQ(ndims[0] == 2 && shapes[0][1] == 5 && numel(ndims[1], shapes[1]) >= 2 && numel(ndims[2], shapes[2]) == shapes[0][0]);
+    return cuda_rc(md::launch_roi_levels((const float *)params[0], (int)shapes[0][0], (const float *)params[1],
+                                         (int32_t *)params[2], (cudaStream_t)stream));
+}
+
+static int parse_feats(int L, int first, void **params, int *ndims, int64_t **shapes, const char **dtypes, md::FeatSet *fs)
+{
+    if (L < 1 || L > md::kMaxLv) return MD_ERR_SIZE;
+    fs->L = L;
+    for (int l = 0; l < L; l++) {
+        const int i = first + l;
+        REQ(is_f32(dtypes[i]) && ndims[i] == 4);
+        if (l == 0) { fs->B = (int)shapes[i][0]; fs->C = (int)shapes[i][1]; }
+        REQ(shapes[i][0] == fs->B && shapes[i][1] == fs->C);
+        fs->H[l] = (int)shapes[i][2]; fs->W[l] = (int)shapes[i][3];
+        fs->feat[l] = (float *)params[i];
+    }
+    return MD_OK;
+}
+
+int MdRoiAlignFwd(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam < 4) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    const int L = nparam - 3;
+    md::FeatSet fs{};
+    int rc = parse_feats(L, 1, params, ndims, shapes, dtypes, &fs);
+    if (rc) return rc;
+    const int ic = 1 + L, io = 2 + L;
+    REQ(is_f32(dtypes[0]) && ndims[0] == 2 && shapes[0][1] == 5);
+    REQ(is_f32(dtypes[ic]) && numel(ndims[ic], shapes[ic]) >= MD_ROI_STRIDE0 + L);
+    const int R = (int)shapes[0][0];
+    REQ(is_f32(dtypes[io]) && ndims[io] == 4 && shapes[io][0] == R && shapes[io][1] == fs.C && shapes[io][2] == shapes[io][3]);
+    const int P = (int)shapes[io][2];
+    return cuda_rc(md::launch_roialign_fwd(fs, (const float *)params[0], R, P, (const float *)params[ic],
+                                           (float *)params[io], (cudaStream_t)stream));
+}
+
+int MdRoiAlignBwd(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam < 4) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    const int L = nparam - 3;
+    md::FeatSet fs{};
+    int rc = parse_feats(L, 3, params, ndims, shapes, dtypes, &fs);
+    if (rc) return rc;
+    REQ(is_f32(dtypes[0]) && ndims[0] == 2 && shapes[0][1] == 5);
+    const int R = (int)shapes[0][0];
+    REQ(is_f32(dtypes[1]) && ndims[1] == 4 && shapes[1][0] == R && shapes[1][1] == fs.C && shapes[1][2] == shapes[1][3]);
+    REQ(is_f32(dtypes[2]) && numel(ndims[2], shapes[2]) >= MD_ROI_STRIDE0 + L);
+    const int P = (int)shapes[1][2];
+    return cuda_rc(md::launch_roialign_bwd(fs, (const float *)params[0], R, P, (const float *)params[2],
+                                           (const float *)params[1], (cudaStream_t)stream));
+}
+
+}  // extern "C"

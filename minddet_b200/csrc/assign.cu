@@ -1,0 +1,325 @@
+// assign.cu -- a7/a8: MaxIoU assignment + deterministic (Philox) sampling.  sm_100a.
+//
+// Algorithm family of the reference: create_target_np, pointpillars/src/core/target_assigner.py:84-134
+// (per-anchor argmax :90-93, per-gt max with every tie force-matched :94-103, thresholds :104-108) with
+// the IoU of pointpillars/src/core/box_np_ops.py:639-679 (iou_jit, eps=1).  The reference materialises the
+// (N x G) overlap matrix on the host per sample; here it is NEVER materialised: every thread streams the
+// (<=G) valid gts from shared memory, once to build the per-gt maxima (kernel 1) and once more to
+// label (kernel 2) -- recomputing is cheaper than a 2x4-byte-per-anchor round trip through HBM.
+// Sampling replaces npr.choice (:116-128) by "k smallest Philox keys" (oracle/CONVENTIONS.md #13) on
+// the cluster radix-select of select.cuh.
+#include "kernels.h"
+#include "select.cuh"
+
+namespace md {
+
+constexpr int kAsThreads = 256;
+constexpr int kAsMaxG = 1024;
+
+struct AsIn {
+    const float *boxes; int ld; int64_t image_stride;   // rows of ld floats; stride 0 = shared by batch
+    const uint8_t *box_valid; int64_t valid_stride;      // may be null
+    const float *gts; const uint8_t *gt_valid; int G;
+    int N;
+    const float *cfg;
+};
+
+struct GtS { float4 box; float area; int j; };
+
+MD_DEVINL float4 load_box(const float *p, int ld)
+{
+    if (ld == 4) return __ldg(reinterpret_cast<const float4 *>(p));
+    return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+}
+
+// compact the valid gts of image b into shared memory (original order kept)
+MD_DEVINL int stage_gts(const AsIn &in, int b, float off, GtS *sg, int *s_count)
+{
+    if (threadIdx.x == 0) {
+        int c = 0;
+        for (int j = 0; j < in.G; j++) {
+            if (in.gt_valid && !in.gt_valid[(int64_t)b * in.G + j]) continue;
+            GtS g;
+            g.box = __ldg(reinterpret_cast<const float4 *>(in.gts) + (int64_t)b * in.G + j);
+            g.area = area_legacy(g.box, off);
+            g.j = j;
+            sg[c++] = g;
+        }
+        *s_count = c;
+    }
+    __syncthreads();
+    return *s_count;
+}
+
+__global__ void __launch_bounds__(kAsThreads)
+assign_gtmax_kernel(const AsIn in, uint32_t *__restrict__ gmax /* (B,G) float bits, zeroed */)
+{
+    extern __shared__ unsigned char smem_raw[];
+    GtS *sg = reinterpret_cast<GtS *>(smem_raw);
+    uint32_t *smax = reinterpret_cast<uint32_t *>(sg + in.G);
+    __shared__ int s_count;
+    const int b = blockIdx.y;
+    const float off = __ldg(in.cfg + 3);
+    for (int j = threadIdx.x; j < in.G; j += kAsThreads) smax[j] = 0u;
+    const int ng = stage_gts(in, b, off, sg, &s_count);
+    if (ng == 0) return;
+    const float *boxes = in.boxes + (int64_t)b * in.image_stride;
+    for (int n = blockIdx.x * kAsThreads + threadIdx.x; n < in.N; n += gridDim.x * kAsThreads) {
+        if (in.box_valid && !in.box_valid[(int64_t)b * in.valid_stride + n]) continue;
+        const float4 a = load_box(boxes + (int64_t)n * in.ld, in.ld);
+        for (int k = 0; k < ng; k++) {
+            const float o = iou_legacy(a, sg[k].box, sg[k].area, off);
+            if (o > 0.0f) {
+                const uint32_t ob = __float_as_uint(o);      // o > 0: uint order == float order
+                if (ob > smax[k]) atomicMax(&smax[k], ob);
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < ng; k += kAsThreads)
+        if (smax[k]) atomicMax(&gmax[(int64_t)b * in.G + sg[k].j], smax[k]);
+}
+
+__global__ void __launch_bounds__(kAsThreads)
+assign_label_kernel(const AsIn in, const uint32_t *__restrict__ gmax, int32_t *__restrict__ assigned,
+                    int64_t assigned_stride, int assigned_offset)
+{
+    extern __shared__ unsigned char smem_raw[];
+    GtS *sg = reinterpret_cast<GtS *>(smem_raw);
+    float *smax = reinterpret_cast<float *>(sg + in.G);
+    __shared__ int s_count;
+    const int b = blockIdx.y;
+    const float pos_thr = __ldg(in.cfg + 0), neg_thr = __ldg(in.cfg + 1), min_pos = __ldg(in.cfg + 2);
+    const float off = __ldg(in.cfg + 3);
+    const int mode = (int)__ldg(in.cfg + 4);
+    const int ng = stage_gts(in, b, off, sg, &s_count);
+    for (int k = threadIdx.x; k < ng; k += kAsThreads) smax[k] = __uint_as_float(gmax[(int64_t)b * in.G + sg[k].j]);
+    __syncthreads();
+    const float *boxes = in.boxes + (int64_t)b * in.image_stride;
+    int32_t *out = assigned + (int64_t)b * assigned_stride + assigned_offset;
+    for (int n = blockIdx.x * kAsThreads + threadIdx.x; n < in.N; n += gridDim.x * kAsThreads) {
+        int32_t as = -1;
+        if (!in.box_valid || in.box_valid[(int64_t)b * in.valid_stride + n]) {
+            const float4 a = load_box(boxes + (int64_t)n * in.ld, in.ld);
+            float m = 0.0f;
+            int am = 0, force = 0;
+            for (int k = 0; k < ng; k++) {
+                const float o = iou_legacy(a, sg[k].box, sg[k].area, off);
+                if (o > m) { m = o; am = sg[k].j; }
+                const float gm = smax[k];
+                if (o == gm && gm > 0.0f && (mode != 0 || gm >= min_pos)) force = sg[k].j + 1;
+            }
+            if (mode == 0) {
+                if (m >= 0.0f && m < neg_thr) as = 0;
+                if (m >= pos_thr) as = am + 1;
+                if (force) as = force;
+            } else {
+                if (force || m >= pos_thr) as = am + 1;
+                else if (m < neg_thr) as = 0;
+            }
+        }
+        out[n] = as;
+    }
+}
+
+// gts-as-proposals head of the RCNN candidate list
+__global__ void rcnn_gt_head_kernel(const uint8_t *__restrict__ gt_valid, int B, int G, int32_t *__restrict__ assigned,
+                                    int64_t assigned_stride)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * G) return;
+    const int b = i / G, j = i - b * G;
+    assigned[(int64_t)b * assigned_stride + j] = (!gt_valid || gt_valid[i]) ? j + 1 : -1;
+}
+
+// ---- sampling on the cluster radix-select -------------------------------------------------------------
+struct SampleSrc {
+    const int32_t *assigned; int N; int Sp, Sn; uint32_t stream_base; const int32_t *seed;
+    __device__ int length(int) const { return N; }
+    __device__ int want(int seg) const { return (seg & 1) ? Sn : Sp; }
+    __device__ uint32_t index_of(int, int m) const { return (uint32_t)m; }
+    __device__ bool load(int seg, int m, uint32_t &key, uint32_t &index) const
+    {
+        const int b = seg >> 1, kind = seg & 1;
+        const int32_t a = __ldg(assigned + (int64_t)b * N + m);
+        index = (uint32_t)m;
+        const bool cand = kind ? (a == 0) : (a > 0);
+        if (!cand) return false;
+        key = ~philox_key((uint32_t)m, stream_base + kind, (uint32_t)b, (uint32_t)__ldg(seed), (uint32_t)__ldg(seed + 1));
+        return true;
+    }
+};
+struct SampleSink {
+    int32_t *pos_idx, *neg_idx; int Sp, Sn; int64_t pos_stride, neg_stride; int32_t *cand_count; /* (B,2) */
+    __device__ void emit(int seg, int rank, unsigned long long comp) const
+    {
+        const int b = seg >> 1;
+        const int32_t idx = (int32_t)(~(uint32_t)comp);
+        if (seg & 1) neg_idx[(int64_t)b * neg_stride + rank] = idx;
+        else pos_idx[(int64_t)b * pos_stride + rank] = idx;
+    }
+    __device__ void pad(int seg, int rank) const
+    {
+        const int b = seg >> 1;
+        if (seg & 1) neg_idx[(int64_t)b * neg_stride + rank] = 0;
+        else pos_idx[(int64_t)b * pos_stride + rank] = 0;
+    }
+    __device__ void finish(int seg, int, int candidates) const { cand_count[seg] = candidates; }
+};
+
+// ---- finalisers -------------------------------------------------------------------------------------
+__global__ void rpn_finalize_kernel(const AsIn in, int Sp, int Sn, const int32_t *__restrict__ cand_count,
+                                    const int32_t *__restrict__ assigned, int32_t *__restrict__ pos_idx,
+                                    uint8_t *__restrict__ pos_valid, int32_t *__restrict__ neg_idx,
+                                    uint8_t *__restrict__ neg_valid, int32_t *__restrict__ pos_gt,
+                                    float4 *__restrict__ pos_target, int32_t *__restrict__ num_pos_out)
+{
+    const int b = blockIdx.x;
+    const int P = cand_count[b * 2], Q = cand_count[b * 2 + 1];
+    const int num_total = (int)__ldg(in.cfg + 5);
+    const int num_pos = min(P, Sp);
+    const int nneg = max(0, min(min(Q, Sn), num_total - num_pos));
+    float mean[4], stdv[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { mean[i] = __ldg(in.cfg + 6 + i); stdv[i] = __ldg(in.cfg + 10 + i); }
+    const float *boxes = in.boxes + (int64_t)b * in.image_stride;
+    for (int i = threadIdx.x; i < Sp; i += blockDim.x) {
+        const bool v = i < num_pos;
+        const int64_t o = (int64_t)b * Sp + i;
+        pos_valid[o] = v;
+        int32_t g = 0;
+        float4 t = make_float4(0, 0, 0, 0);
+        if (v) {
+            const int32_t n = pos_idx[o];
+            g = assigned[(int64_t)b * in.N + n] - 1;
+            t = encode_box(load_box(boxes + (int64_t)n * in.ld, in.ld),
+                           __ldg(reinterpret_cast<const float4 *>(in.gts) + (int64_t)b * in.G + g), mean, stdv);
+        } else {
+            pos_idx[o] = 0;
+        }
+        pos_gt[o] = g;
+        pos_target[o] = t;
+    }
+    for (int i = threadIdx.x; i < Sn; i += blockDim.x) {
+        const bool v = i < nneg;
+        const int64_t o = (int64_t)b * Sn + i;
+        neg_valid[o] = v;
+        if (!v) neg_idx[o] = 0;
+    }
+    if (threadIdx.x == 0) num_pos_out[b] = num_pos;
+}
+
+__global__ void rcnn_finalize_kernel(const float *__restrict__ props5, int P_, const float *__restrict__ gts,
+                                     const int32_t *__restrict__ gt_labels, int G, const float *__restrict__ cfg,
+                                     int Sp, int Sn, const int32_t *__restrict__ cand_count,
+                                     const int32_t *__restrict__ assigned, int32_t *__restrict__ sel_idx,
+                                     float *__restrict__ rois5, float4 *__restrict__ deltas,
+                                     int32_t *__restrict__ labels, uint8_t *__restrict__ mask,
+                                     int32_t *__restrict__ pos_gt, int32_t *__restrict__ num_pos_out)
+{
+    const int b = blockIdx.x;
+    const int S = Sp + Sn, N = G + P_;
+    const int Pc = cand_count[b * 2], Qc = cand_count[b * 2 + 1];
+    const int num_total = (int)__ldg(cfg + 5);
+    const int num_pos = min(Pc, Sp);
+    const int nneg = max(0, min(min(Qc, Sn), num_total - num_pos));
+    float mean[4], stdv[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { mean[i] = __ldg(cfg + 6 + i); stdv[i] = __ldg(cfg + 10 + i); }
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        const bool is_pos = i < Sp;
+        const bool v = is_pos ? (i < num_pos) : ((i - Sp) < nneg);
+        const int64_t o = (int64_t)b * S + i;
+        int32_t n = v ? sel_idx[o] : 0;
+        sel_idx[o] = n;
+        float4 box;
+        if (n < G) box = __ldg(reinterpret_cast<const float4 *>(gts) + (int64_t)b * G + n);
+        else box = load_box(props5 + ((int64_t)b * P_ + (n - G)) * 5, 5);
+        float4 d = make_float4(0, 0, 0, 0);
+        int32_t lab = 0, g = 0;
+        if (v && is_pos) {
+            g = assigned[(int64_t)b * N + n] - 1;
+            d = encode_box(box, __ldg(reinterpret_cast<const float4 *>(gts) + (int64_t)b * G + g), mean, stdv);
+            lab = gt_labels[(int64_t)b * G + g];
+        }
+        float *r = rois5 + o * 5;
+        r[0] = (float)b; r[1] = box.x; r[2] = box.y; r[3] = box.z; r[4] = box.w;
+        deltas[o] = d;
+        labels[o] = lab;
+        mask[o] = v;
+        if (is_pos) pos_gt[(int64_t)b * Sp + i] = g;
+    }
+    if (threadIdx.x == 0) num_pos_out[b] = num_pos;
+}
+
+// workspace: gmax (B,G) u32 | cand_count (B,2) i32
+size_t assign_workspace_bytes(int B, int G)
+{
+    return (((size_t)B * G * 4 + 255) & ~(size_t)255) + (size_t)B * 2 * 4 + 256;
+}
+
+static cudaError_t run_assign(const AsIn &in, int B, uint32_t *gmax, int32_t *assigned, int64_t assigned_stride,
+                              int assigned_offset, cudaStream_t s)
+{
+    if (in.G > kAsMaxG) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(gmax, 0, (size_t)B * in.G * 4, s);
+    if (e != cudaSuccess) return e;
+    int gx = (in.N + kAsThreads - 1) / kAsThreads;
+    const int cap = (148 * 8 + B - 1) / B;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    const size_t smem = (size_t)in.G * (sizeof(GtS) + 4) + 16;
+    assign_gtmax_kernel<<<dim3(gx, B), kAsThreads, smem, s>>>(in, gmax);
+    assign_label_kernel<<<dim3(gx, B), kAsThreads, smem, s>>>(in, gmax, assigned, assigned_stride, assigned_offset);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assign_sample_rpn(const float *boxes, int boxes_per_image, const uint8_t *box_valid,
+                                     int B, int N, const float *gts, const uint8_t *gt_valid, int G,
+                                     const float *cfg, const int32_t *seed, void *ws, int Sp, int Sn,
+                                     int32_t *assigned, int32_t *pos_idx, uint8_t *pos_valid, int32_t *neg_idx,
+                                     uint8_t *neg_valid, int32_t *pos_gt, float *pos_target, int32_t *num_pos,
+                                     cudaStream_t s)
+{
+    if (B == 0) return cudaSuccess;
+    if (N >= (1 << kSelMaxIndexBits) || Sp > kSelMaxK || Sn > kSelMaxK) return cudaErrorInvalidValue;
+    uint32_t *gmax = reinterpret_cast<uint32_t *>(ws);
+    int32_t *cand = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(ws) + (((size_t)B * G * 4 + 255) & ~(size_t)255));
+    AsIn in{ boxes, 4, boxes_per_image ? (int64_t)N * 4 : 0, box_valid, boxes_per_image ? (int64_t)N : 0, gts, gt_valid, G, N, cfg };
+    cudaError_t e = run_assign(in, B, gmax, assigned, N, 0, s);
+    if (e != cudaSuccess) return e;
+    SampleSrc src{ assigned, N, Sp, Sn, 0u, seed };
+    SampleSink sink{ pos_idx, neg_idx, Sp, Sn, Sp, Sn, cand };
+    e = launch_select_sorted(src, sink, 2 * B, N, s);
+    if (e != cudaSuccess) return e;
+    rpn_finalize_kernel<<<B, 256, 0, s>>>(in, Sp, Sn, cand, assigned, pos_idx, pos_valid, neg_idx, neg_valid,
+                                          pos_gt, reinterpret_cast<float4 *>(pos_target), num_pos);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assign_sample_rcnn(const float *props5, const uint8_t *prop_mask, int B, int P,
+                                      const float *gts, const int32_t *gt_labels, const uint8_t *gt_valid, int G,
+                                      const float *cfg, const int32_t *seed, void *ws, int Sp, int Sn,
+                                      float *rois5, float *deltas, int32_t *labels, uint8_t *mask,
+                                      int32_t *assigned, int32_t *sel_idx, int32_t *pos_gt, int32_t *num_pos,
+                                      cudaStream_t s)
+{
+    if (B == 0) return cudaSuccess;
+    const int N = G + P, S = Sp + Sn;
+    if (N >= (1 << kSelMaxIndexBits) || Sp > kSelMaxK || Sn > kSelMaxK) return cudaErrorInvalidValue;
+    uint32_t *gmax = reinterpret_cast<uint32_t *>(ws);
+    int32_t *cand = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(ws) + (((size_t)B * G * 4 + 255) & ~(size_t)255));
+    AsIn in{ props5, 5, (int64_t)P * 5, prop_mask, (int64_t)P, gts, gt_valid, G, P, cfg };
+    if (G > 0) rcnn_gt_head_kernel<<<(B * G + 255) / 256, 256, 0, s>>>(gt_valid, B, G, assigned, N);
+    cudaError_t e = run_assign(in, B, gmax, assigned, N, G, s);
+    if (e != cudaSuccess) return e;
+    SampleSrc src{ assigned, N, Sp, Sn, 2u, seed };
+    SampleSink sink{ sel_idx, sel_idx + Sp, Sp, Sn, S, S, cand };
+    e = launch_select_sorted(src, sink, 2 * B, N, s);
+    if (e != cudaSuccess) return e;
+    rcnn_finalize_kernel<<<B, 256, 0, s>>>(props5, P, gts, gt_labels, G, cfg, Sp, Sn, cand, assigned, sel_idx,
+                                           rois5, reinterpret_cast<float4 *>(deltas), labels, mask, pos_gt, num_pos);
+    return cudaGetLastError();
+}
+
+}  // namespace md

@@ -1,0 +1,66 @@
+// kernels.h -- host-side launchers of the region-path kernels (internal; the public boundary is
+// include/md_region_aot.h).  Every launcher enqueues on `stream` and never synchronises.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace md {
+
+constexpr int kMaxLv = 8;
+
+struct LevelSet {           // per pyramid level, host-known geometry + device pointers
+    int L;
+    int A[kMaxLv], H[kMaxLv], W[kMaxLv];
+    const float *scores[kMaxLv];   // (B,A,H,W)
+    const float *deltas[kMaxLv];   // (B,4A,H,W)
+    const float *base[kMaxLv];     // (A,4)
+};
+
+// a1 / a2
+cudaError_t launch_anchor_grid(const float *base, int A, int H, int W, const float *cfg, float *out, cudaStream_t s);
+cudaError_t launch_decode_rows(const float *anchors, const float *deltas, int64_t K, const float *cfg, float *out, cudaStream_t s);
+cudaError_t launch_decode_level(const float *deltas, const float *base, int B, int A, int H, int W,
+                                const float *cfg, float *out, cudaStream_t s);
+
+// a3: scores (B,A,H,W) head layout (A>0) or flat (B,N) (A==0 -> index == memory order)
+cudaError_t launch_topk(const float *scores, int B, int A, int HW, int K, const float *cfg_sigmoid,
+                        float *values, int32_t *indices, cudaStream_t s);
+
+// a4: boxes (B,K,ld) score-sorted
+size_t nms_workspace_bytes(int nseg, int Kmax);
+cudaError_t launch_nms(const float *boxes, int ld, int B, int K, const float *cfg, void *ws,
+                       int32_t *keep_idx, uint8_t *mask, int32_t *count, cudaStream_t s);
+
+// a3..a6
+size_t proposal_workspace_bytes(int B, int L, int nms_pre);
+cudaError_t launch_proposal(const LevelSet &lv, int B, int nms_pre, int max_num, const float *cfg, void *ws,
+                            float *props, uint8_t *pmask, int32_t *topk_idx, uint8_t *keep, cudaStream_t s);
+
+// a7/a8
+size_t assign_workspace_bytes(int B, int G);
+cudaError_t launch_assign_sample_rpn(const float *boxes, int boxes_per_image, const uint8_t *box_valid,
+                                     int B, int N, const float *gts, const uint8_t *gt_valid, int G,
+                                     const float *cfg, const int32_t *seed, void *ws, int Sp, int Sn,
+                                     int32_t *assigned, int32_t *pos_idx, uint8_t *pos_valid, int32_t *neg_idx,
+                                     uint8_t *neg_valid, int32_t *pos_gt, float *pos_target, int32_t *num_pos,
+                                     cudaStream_t s);
+cudaError_t launch_assign_sample_rcnn(const float *props5, const uint8_t *prop_mask, int B, int P,
+                                      const float *gts, const int32_t *gt_labels, const uint8_t *gt_valid, int G,
+                                      const float *cfg, const int32_t *seed, void *ws, int Sp, int Sn,
+                                      float *rois5, float *deltas, int32_t *labels, uint8_t *mask,
+                                      int32_t *assigned, int32_t *sel_idx, int32_t *pos_gt, int32_t *num_pos,
+                                      cudaStream_t s);
+
+// a9..a11
+struct FeatSet {
+    int L, B, C;
+    int H[kMaxLv], W[kMaxLv];
+    float *feat[kMaxLv];    // (B,C,H,W)  (const for fwd, written by bwd)
+};
+cudaError_t launch_roi_levels(const float *rois5, int R, const float *cfg, int32_t *out, cudaStream_t s);
+cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
+                                float *out, cudaStream_t s);
+cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
+                                const float *dout, cudaStream_t s);
+
+}  // namespace md

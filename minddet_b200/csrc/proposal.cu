@@ -1,0 +1,642 @@
+// proposal.cu -- a1..a6 of the region path: anchors, delta decode + clip, per-level top-k,
+// bitmask NMS with an on-device sweep, cross-level merge.  sm_100a.
+//
+// Reference lineage (what is being replaced / followed):
+//   * NMS bitmask tiles: nms_normal_kernel, centerpoint/det3d_ms/ops/test_custom_pytorch/
+//     iou3d_nms_kernel.cu:361-405 -- same 64x64 tile -> one u64 word layout, but only the upper
+//     triangle is launched (the reference's early-out is commented out, :376) ...
+//   * ... and the host-side serial reduce (:571-593: cudaMalloc, blocking D2H of N*ceil(N/64)*8 bytes,
+//     CPU sweep, H2D) is replaced by nms_sweep_kernel: the greedy sweep runs on the device, one warp per
+//     (image, level), chunk-by-chunk with a warp-wide OR fixed point, zero host round trips.
+//   * graph order top-k -> gather -> NMS -> gather-keep: center_head.py:435-459.
+// Semantics: oracle/CONVENTIONS.md #1-8, #17; oracle/region_oracle.c (o_topk, o_nms, o_proposal_image).
+#include "kernels.h"
+#include "select.cuh"
+
+namespace md {
+
+// =====================================================================================================
+// a1: anchor grid -- pure 128-bit stores, 16 B / anchor
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+anchor_grid_kernel(const float *__restrict__ base, int A, int H, int W, const float *__restrict__ cfg,
+                   float4 *__restrict__ out)
+{
+    const float stride = __ldg(cfg);
+    const int64_t total = (int64_t)H * W * A;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < total; n += (int64_t)gridDim.x * blockDim.x) {
+        const int a = (int)(n % A);
+        const int64_t p = n / A;
+        const int w = (int)(p % W), h = (int)(p / W);
+        const float sx = mul((float)w, stride), sy = mul((float)h, stride);
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(base) + a);
+        stg_stream(out + n, make_float4(add(b.x, sx), add(b.y, sy), add(b.z, sx), add(b.w, sy)));
+    }
+}
+
+cudaError_t launch_anchor_grid(const float *base, int A, int H, int W, const float *cfg, float *out, cudaStream_t s)
+{
+    const int64_t total = (int64_t)H * W * A;
+    if (total == 0) return cudaSuccess;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    anchor_grid_kernel<<<blocks, 256, 0, s>>>(base, A, H, W, cfg, reinterpret_cast<float4 *>(out));
+    return cudaGetLastError();
+}
+
+// =====================================================================================================
+// a2: decode on gathered rows (K,4)
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+decode_rows_kernel(const float4 *__restrict__ anchors, const float4 *__restrict__ deltas, int64_t K,
+                   const float *__restrict__ cfg, float4 *__restrict__ out)
+{
+    const DecodeCfg c = load_decode_cfg(cfg);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < K; i += (int64_t)gridDim.x * blockDim.x)
+        stg_stream(out + i, decode_box(ldg_stream(anchors + i), ldg_stream(deltas + i), c));
+}
+
+cudaError_t launch_decode_rows(const float *anchors, const float *deltas, int64_t K, const float *cfg, float *out, cudaStream_t s)
+{
+    if (K == 0) return cudaSuccess;
+    int blocks = (int)((K + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    decode_rows_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4 *>(anchors),
+                                              reinterpret_cast<const float4 *>(deltas), K, cfg,
+                                              reinterpret_cast<float4 *>(out));
+    return cudaGetLastError();
+}
+
+// =====================================================================================================
+// a2 (decode-all form): RPN head layout (B,4A,H,W) -> (B,HW*A,4); anchors regenerated in registers.
+// Algorithmic bytes: 16 (deltas) + 16 (boxes) per anchor; no anchor read.
+// Each thread owns 4 consecutive cells: 4A 128-bit loads (one per delta plane), results are staged in
+// shared memory so that the (cell, anchor)-interleaved output leaves as fully coalesced 128-bit stores.
+// =====================================================================================================
+constexpr int kDecThreads = 128;
+constexpr int kDecCells = kDecThreads * 4;
+
+template <bool VEC>
+__global__ void __launch_bounds__(kDecThreads)
+decode_level_kernel(const float *__restrict__ deltas, const float *__restrict__ base, int A, int H, int W,
+                    const float *__restrict__ cfg, float4 *__restrict__ out)
+{
+    extern __shared__ float4 stage[];   // [kDecCells * A]
+    const DecodeCfg c = load_decode_cfg(cfg);
+    const float stride = __ldg(cfg + 11);
+    const int HW = H * W;
+    const int b = blockIdx.y;
+    const int tiles = (HW + kDecCells - 1) / kDecCells;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int p0 = tile * kDecCells + threadIdx.x * 4;
+        for (int a = 0; a < A; a++) {
+            float d[4][4];   // [coord][cell]
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float *plane = deltas + ((int64_t)b * 4 * A + a * 4 + k) * HW;
+                if (VEC) {
+                    float4 v = make_float4(0, 0, 0, 0);
+                    if (p0 < HW) v = ldg_stream(reinterpret_cast<const float4 *>(plane + p0));
+                    d[k][0] = v.x; d[k][1] = v.y; d[k][2] = v.z; d[k][3] = v.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) d[k][j] = (p0 + j < HW) ? __ldg(plane + p0 + j) : 0.0f;
+                }
+            }
+            const float4 bs = __ldg(reinterpret_cast<const float4 *>(base) + a);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int p = p0 + j;
+                const int w = p % W, h = p / W;
+                const float sx = mul((float)w, stride), sy = mul((float)h, stride);
+                const float4 anc = make_float4(add(bs.x, sx), add(bs.y, sy), add(bs.z, sx), add(bs.w, sy));
+                stage[(threadIdx.x * 4 + j) * A + a] =
+                    decode_box(anc, make_float4(d[0][j], d[1][j], d[2][j], d[3][j]), c);
+            }
+        }
+        __syncthreads();
+        const int cells = min(kDecCells, HW - tile * kDecCells);
+        float4 *dst = out + ((int64_t)b * HW + (int64_t)tile * kDecCells) * A;
+        for (int i = threadIdx.x; i < cells * A; i += kDecThreads) stg_stream(dst + i, stage[i]);
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_decode_level(const float *deltas, const float *base, int B, int A, int H, int W,
+                                const float *cfg, float *out, cudaStream_t s)
+{
+    const int HW = H * W;
+    if (B == 0 || HW == 0) return cudaSuccess;
+    const size_t smem = (size_t)kDecCells * A * sizeof(float4);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(deltas) & 15) == 0);
+    const int tiles = (HW + kDecCells - 1) / kDecCells;
+    int gx = tiles;
+    const int cap = (148 * 6 + B - 1) / B;
+    if (gx > cap) gx = cap;
+    auto kern = vec ? decode_level_kernel<true> : decode_level_kernel<false>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<dim3(gx, B), kDecThreads, smem, s>>>(deltas, base, A, H, W, cfg, reinterpret_cast<float4 *>(out));
+    return cudaGetLastError();
+}
+
+// =====================================================================================================
+// a3: top-k sources / sinks for select_sorted_kernel
+// =====================================================================================================
+struct TopkSrc {            // one level, B segments
+    const float *scores; int A, HW, N, K; const float *cfg_sigmoid;
+    __device__ int length(int) const { return N; }
+    __device__ int want(int) const { return K; }
+    __device__ uint32_t index_of(int, int m) const
+    {
+        if (A == 0) return (uint32_t)m;
+        const int a = m / HW, p = m - a * HW;
+        return (uint32_t)(p * A + a);
+    }
+    __device__ bool load(int seg, int m, uint32_t &key, uint32_t &index) const
+    {
+        float x = __ldg(scores + (int64_t)seg * N + m);
+        if (__ldg(cfg_sigmoid) != 0.0f) x = exact_sigmoid(x);
+        key = score_key(x);
+        index = index_of(seg, m);
+        return true;
+    }
+};
+struct TopkSink {
+    float *values; int32_t *indices; int K;
+    __device__ void emit(int seg, int rank, unsigned long long comp) const
+    {
+        values[(int64_t)seg * K + rank] = key_score((uint32_t)(comp >> 32));
+        indices[(int64_t)seg * K + rank] = (int32_t)(~(uint32_t)comp);
+    }
+    __device__ void pad(int seg, int rank) const
+    {
+        values[(int64_t)seg * K + rank] = 0.0f;
+        indices[(int64_t)seg * K + rank] = -1;
+    }
+    __device__ void finish(int, int, int) const {}
+};
+
+cudaError_t launch_topk(const float *scores, int B, int A, int HW, int K, const float *cfg_sigmoid,
+                        float *values, int32_t *indices, cudaStream_t s)
+{
+    TopkSrc src{ scores, A, HW, (A == 0 ? HW : A * HW), K, cfg_sigmoid };
+    TopkSink sink{ values, indices, K };
+    return launch_select_sorted(src, sink, B, src.N, s);
+}
+
+// ---- Proposal: all levels in one launch; the sink gathers deltas, regenerates the anchor, decodes ----
+struct PropLevels {
+    int L, B, nms_pre;
+    int A[kMaxLv], W[kMaxLv], HW[kMaxLv], K[kMaxLv];
+    const float *scores[kMaxLv], *deltas[kMaxLv], *base[kMaxLv];
+    const float *cfg;
+};
+struct PropSrc {
+    PropLevels p;
+    __device__ int length(int seg) const { const int l = seg % p.L; return p.A[l] * p.HW[l]; }
+    __device__ int want(int) const { return p.nms_pre; }   // pads up to nms_pre; selection caps at N
+    __device__ uint32_t index_of(int seg, int m) const
+    {
+        const int l = seg % p.L;
+        const int a = m / p.HW[l], q = m - a * p.HW[l];
+        return (uint32_t)(q * p.A[l] + a);
+    }
+    __device__ bool load(int seg, int m, uint32_t &key, uint32_t &index) const
+    {
+        const int l = seg % p.L, b = seg / p.L;
+        float x = __ldg(p.scores[l] + (int64_t)b * p.A[l] * p.HW[l] + m);
+        if (__ldg(p.cfg + 15) != 0.0f) x = exact_sigmoid(x);
+        key = score_key(x);
+        index = index_of(seg, m);
+        return true;
+    }
+};
+struct PropSink {
+    PropLevels p;
+    float4 *ws_boxes; float *ws_scores; int32_t *topk_idx;
+    __device__ void emit(int seg, int rank, unsigned long long comp) const
+    {
+        const int l = seg % p.L, b = seg / p.L;
+        const int A = p.A[l], W = p.W[l], HW = p.HW[l];
+        const uint32_t n = ~(uint32_t)comp;
+        const int a = n % A, q = n / A;
+        const int w = q % W, h = q / W;
+        const float stride = __ldg(p.cfg + 16 + l);
+        const float sx = mul((float)w, stride), sy = mul((float)h, stride);
+        const float4 bs = __ldg(reinterpret_cast<const float4 *>(p.base[l]) + a);
+        const float4 anc = make_float4(add(bs.x, sx), add(bs.y, sy), add(bs.z, sx), add(bs.w, sy));
+        const float *d = p.deltas[l] + ((int64_t)b * 4 * A + a * 4) * HW + q;
+        const float4 dl = make_float4(__ldg(d), __ldg(d + HW), __ldg(d + 2 * (int64_t)HW), __ldg(d + 3 * (int64_t)HW));
+        const DecodeCfg c = load_decode_cfg(p.cfg);
+        const int64_t o = (int64_t)seg * p.nms_pre + rank;
+        ws_boxes[o] = decode_box(anc, dl, c);
+        ws_scores[o] = key_score((uint32_t)(comp >> 32));
+        topk_idx[o] = (int32_t)n;
+    }
+    __device__ void pad(int seg, int rank) const
+    {
+        const int64_t o = (int64_t)seg * p.nms_pre + rank;
+        ws_boxes[o] = make_float4(0, 0, 0, 0);
+        ws_scores[o] = 0.0f;
+        topk_idx[o] = -1;
+    }
+    __device__ void finish(int, int, int) const {}
+};
+
+// =====================================================================================================
+// a4: NMS.  (1) bitmask tiles (upper triangle), (2) on-device greedy sweep.
+// =====================================================================================================
+struct NmsCfg { float thr, off, eps; bool inclusive; };
+MD_DEVINL NmsCfg load_nms_cfg(const float *__restrict__ cfg)
+{
+    NmsCfg c;
+    c.thr = __ldg(cfg + 0); c.off = __ldg(cfg + 1); c.inclusive = __ldg(cfg + 2) != 0.0f; c.eps = __ldg(cfg + 3);
+    return c;
+}
+struct BoxA { float x1, y1, x2, y2, area; };
+
+MD_DEVINL bool nms_suppresses(const BoxA &a, const BoxA &b, const NmsCfg &c, bool zero_cond)
+{
+    const float left = fmaxf(a.x1, b.x1), right = fminf(a.x2, b.x2);
+    const float top = fmaxf(a.y1, b.y1), bottom = fminf(a.y2, b.y2);
+    const float w = fmaxf(add(sub(right, left), c.off), 0.0f);
+    const float h = fmaxf(add(sub(bottom, top), c.off), 0.0f);
+    const float inter = mul(w, h);
+    if (c.eps > 0.0f && inter == 0.0f) return zero_cond;   // 0 / max(u,eps) == 0 exactly
+    float uni = sub(add(a.area, b.area), inter);
+    if (c.eps > 0.0f) uni = fmaxf(uni, c.eps);
+    const float iou = div(inter, uni);
+    return c.inclusive ? (iou >= c.thr) : (iou > c.thr);
+}
+
+struct NmsSegs {                 // segment s -> boxes + K
+    const float *boxes; int ld;  // rows of `ld` floats, segment stride = seg_stride rows
+    int seg_stride;              // rows between consecutive segments
+    int L;                       // K depends on (s % L)
+    int K[kMaxLv];
+    int nbp;                     // mask row pitch in u64 words (even)
+    int rows_pad;                // mask rows per segment (multiple of 64)
+};
+
+// grid: (triangular tile index, segment); 64 threads: thread r owns row box r of the tile.
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const NmsSegs sg, const float *__restrict__ cfg, unsigned long long *__restrict__ mask)
+{
+    const int seg = blockIdx.y;
+    const int K = sg.K[seg % sg.L];
+    const int nb = (K + 63) >> 6;
+    // decode the triangular index t -> (row block i, col block j), j >= i
+    const int t = blockIdx.x;
+    if (t >= nb * (nb + 1) / 2) return;
+    int i = (int)((2.0f * nb + 1.0f - sqrtf((2.0f * nb + 1.0f) * (2.0f * nb + 1.0f) - 8.0f * t)) * 0.5f);
+    while (i > 0 && i * (2 * nb - i + 1) / 2 > t) i--;
+    while ((i + 1) * (2 * nb - i) / 2 <= t) i++;
+    const int j = i + (t - i * (2 * nb - i + 1) / 2);
+
+    const NmsCfg c = load_nms_cfg(cfg);
+    const bool zero_cond = c.inclusive ? (0.0f >= c.thr) : (0.0f > c.thr);
+    const float *boxes = sg.boxes + (int64_t)seg * sg.seg_stride * sg.ld;
+    __shared__ BoxA cols[64];
+    const int tid = threadIdx.x;
+    {
+        const int cidx = j * 64 + tid;
+        BoxA b = { 0, 0, 0, 0, 0 };
+        if (cidx < K) {
+            const float *p = boxes + (int64_t)cidx * sg.ld;
+            b.x1 = __ldg(p); b.y1 = __ldg(p + 1); b.x2 = __ldg(p + 2); b.y2 = __ldg(p + 3);
+            b.area = mul(add(sub(b.x2, b.x1), c.off), add(sub(b.y2, b.y1), c.off));
+        }
+        cols[tid] = b;
+    }
+    __syncthreads();
+    const int ridx = i * 64 + tid;
+    if (ridx >= K) return;
+    BoxA a;
+    {
+        const float *p = boxes + (int64_t)ridx * sg.ld;
+        a.x1 = __ldg(p); a.y1 = __ldg(p + 1); a.x2 = __ldg(p + 2); a.y2 = __ldg(p + 3);
+        a.area = mul(add(sub(a.x2, a.x1), c.off), add(sub(a.y2, a.y1), c.off));
+    }
+    const int ncol = min(64, K - j * 64);
+    const int start = (i == j) ? tid + 1 : 0;
+    unsigned long long bits = 0ull;
+    for (int k = start; k < ncol; k++)
+        if (nms_suppresses(a, cols[k], c, zero_cond)) bits |= 1ull << k;
+    mask[((int64_t)seg * sg.rows_pad + ridx) * sg.nbp + j] = bits;
+}
+
+MD_DEVINL void cp_async16(void *smem, const void *gmem)
+{
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gmem) : "memory");
+}
+MD_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> MD_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// One CTA per segment.  All 128 threads stream 64-row chunks of the bitmask into a double-buffered
+// shared-memory stage with cp.async; warp 0 resolves each chunk:
+//   kept <- alive & ~OR_{b in kept} diag[b]        iterated to its (unique) fixed point == greedy NMS,
+// with the OR taken across the warp by redux.or, then ORs the kept rows into the running `removed`
+// words (lane j owns word j).
+constexpr int kSweepThreads = 128;
+constexpr int kSweepMaxNb = 32;    // K <= 2048
+
+__global__ void __launch_bounds__(kSweepThreads)
+nms_sweep_kernel(const NmsSegs sg, const unsigned long long *__restrict__ mask,
+                 int32_t *__restrict__ keep_pos, int keep_stride, uint8_t *__restrict__ keep_mask,
+                 int mask_stride, int32_t *__restrict__ count)
+{
+    __shared__ __align__(16) unsigned long long stage[2][64 * kSweepMaxNb];
+    const int seg = blockIdx.x;
+    const int K = sg.K[seg % sg.L];
+    const int nb = (K + 63) >> 6, nbp = sg.nbp;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long *m = mask + (int64_t)seg * sg.rows_pad * nbp;
+    int32_t *kp = keep_pos + (int64_t)seg * keep_stride;
+    uint8_t *km = keep_mask + (int64_t)seg * mask_stride;
+
+    auto issue = [&](int c) {   // rows c*64..c*64+63, words [c&~1, nbp)
+        const int w0 = c & ~1;
+        const int chunks_per_row = (nbp - w0) >> 1;       // 16-byte chunks
+        const int total = 64 * chunks_per_row;
+        unsigned long long *dst = stage[c & 1];
+        for (int q = tid; q < total; q += kSweepThreads) {
+            const int r = q / chunks_per_row, k = q - r * chunks_per_row;
+            cp_async16(dst + r * nbp + w0 + 2 * k, m + (int64_t)(c * 64 + r) * nbp + w0 + 2 * k);
+        }
+        cp_async_commit();
+    };
+
+    unsigned long long removed = 0ull;   // lane j: word j
+    int nkept = 0;
+    if (nb > 0) issue(0);
+    for (int c = 0; c < nb; c++) {
+        if (c + 1 < nb) { issue(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long *rows = stage[c & 1];
+            const int nrows = min(64, K - c * 64);
+            const unsigned long long vmask = nrows == 64 ? ~0ull : ((1ull << nrows) - 1ull);
+            const unsigned long long cur = __shfl_sync(0xffffffffu, removed, c);
+            const unsigned long long alive = ~cur & vmask;
+            const unsigned long long d_lo = rows[lane * nbp + c], d_hi = rows[(lane + 32) * nbp + c];
+            unsigned long long kept = alive;
+            for (int it = 0; it < 64; it++) {
+                unsigned long long sup = (((kept >> lane) & 1ull) ? d_lo : 0ull) |
+                                         (((kept >> (lane + 32)) & 1ull) ? d_hi : 0ull);
+                const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)sup);
+                const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(sup >> 32));
+                const unsigned long long nk = alive & ~(((unsigned long long)hi << 32) | lo);
+                if (nk == kept) break;
+                kept = nk;
+            }
+            // OR the kept rows into the removed words of the later chunks
+            if (lane > c && lane < nb) {
+                unsigned long long acc = 0ull, k = kept;
+                while (k) {
+                    const int b = __ffsll((long long)k) - 1;
+                    k &= k - 1;
+                    acc |= rows[b * nbp + lane];
+                }
+                removed |= acc;
+            }
+            // outputs
+            const int b0 = lane, b1 = lane + 32;
+            const bool k0 = (kept >> b0) & 1ull, k1 = (kept >> b1) & 1ull;
+            if (b0 < nrows) km[c * 64 + b0] = k0;
+            if (b1 < nrows) km[c * 64 + b1] = k1;
+            if (k0) kp[nkept + __popcll(kept & ((1ull << b0) - 1ull))] = c * 64 + b0;
+            if (k1) kp[nkept + __popcll(kept & ((1ull << b1) - 1ull))] = c * 64 + b1;
+            nkept += __popcll(kept);
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
+        for (int i = nkept + lane; i < keep_stride; i += 32) kp[i] = 0;
+        for (int i = K + lane; i < mask_stride; i += 32) km[i] = 0;
+        if (lane == 0) count[seg] = nkept;
+    }
+}
+
+size_t nms_workspace_bytes(int nseg, int Kmax)
+{
+    const int nb = (Kmax + 63) / 64, nbp = (nb + 1) & ~1;
+    return (size_t)nseg * nb * 64 * nbp * sizeof(unsigned long long) + 256;
+}
+
+static cudaError_t run_nms(const NmsSegs &sg, int nseg, int Kmax, const float *cfg, unsigned long long *mask,
+                           int32_t *keep_pos, int keep_stride, uint8_t *keep_mask, int mask_stride,
+                           int32_t *count, cudaStream_t s)
+{
+    if (nseg == 0) return cudaSuccess;
+    const int nb = (Kmax + 63) / 64;
+    if (nb > kSweepMaxNb) return cudaErrorInvalidValue;
+    const int tiles = nb * (nb + 1) / 2;
+    if (tiles > 0) nms_mask_kernel<<<dim3(tiles, nseg), 64, 0, s>>>(sg, cfg, mask);
+    nms_sweep_kernel<<<nseg, kSweepThreads, 0, s>>>(sg, mask, keep_pos, keep_stride, keep_mask, mask_stride, count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_nms(const float *boxes, int ld, int B, int K, const float *cfg, void *ws,
+                       int32_t *keep_idx, uint8_t *mask, int32_t *count, cudaStream_t s)
+{
+    NmsSegs sg{};
+    sg.boxes = boxes; sg.ld = ld; sg.seg_stride = K; sg.L = 1; sg.K[0] = K;
+    const int nb = (K + 63) / 64;
+    sg.nbp = (nb + 1) & ~1; sg.rows_pad = nb * 64;
+    return run_nms(sg, B, K, cfg, reinterpret_cast<unsigned long long *>(ws), keep_idx, K, mask, K, count, s);
+}
+
+// =====================================================================================================
+// a5: cross-level merge.  Kept boxes come first ordered by (score desc, concat index asc); suppressed
+// boxes follow in concat order (they all carry the -65536 sentinel upstream).  Every level's kept list
+// is already sorted, so a box's final rank is a sum of binary searches -- no second global top-k.
+// Precondition: scores > -65536.
+// =====================================================================================================
+constexpr int kMergeThreads = 512;
+constexpr int kMergeSplit = 4;
+
+__global__ void __launch_bounds__(kMergeThreads)
+merge_levels_kernel(int L, int nms_pre, int max_num, const float4 *__restrict__ ws_boxes,
+                    const float *__restrict__ ws_scores, const uint8_t *__restrict__ keep_mask,
+                    const int32_t *__restrict__ keep_pos, const int32_t *__restrict__ count,
+                    float *__restrict__ props, uint8_t *__restrict__ pmask)
+{
+    extern __shared__ uint32_t kkeys[];   // [L][nms_pre] keys of the kept boxes, descending per level
+    __shared__ int cnt[kMaxLv], cum[kMaxLv + 1];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        int c = 0;
+        for (int l = 0; l < L; l++) { cnt[l] = count[b * L + l]; cum[l] = c; c += cnt[l]; }
+        cum[L] = c;
+    }
+    __syncthreads();
+    for (int i = tid; i < L * nms_pre; i += kMergeThreads) {
+        const int l = i / nms_pre, t = i - l * nms_pre;
+        if (t < cnt[l]) {
+            const int64_t seg = (int64_t)b * L + l;
+            kkeys[i] = score_key(ws_scores[seg * nms_pre + keep_pos[seg * nms_pre + t]]);
+        }
+    }
+    __syncthreads();
+    const int total_kept = cum[L];
+    const int total = L * nms_pre;   // concat index space (padded slots are never kept; see below)
+    for (int e = blockIdx.y * kMergeThreads + tid; e < total; e += kMergeSplit * kMergeThreads) {
+        const int l = e / nms_pre, i = e - l * nms_pre;
+        const int64_t seg = (int64_t)b * L + l;
+        const bool kept = keep_mask[seg * nms_pre + i] != 0;
+        // #kept in my level at positions < i  (keep_pos is ascending)
+        int lo = 0, hi = cnt[l];
+        const int32_t *kp = keep_pos + seg * nms_pre;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (kp[mid] < i) lo = mid + 1; else hi = mid; }
+        const int before_in_level = lo;
+        int rank;
+        if (kept) {
+            const uint32_t key = score_key(ws_scores[seg * nms_pre + i]);
+            rank = before_in_level;
+            for (int l2 = 0; l2 < L; l2++) {
+                if (l2 == l) continue;
+                // #kept in level l2 that sort before me: key2 > key, or == when l2 < l
+                const uint32_t *kk = kkeys + l2 * nms_pre;
+                int a = 0, z = cnt[l2];
+                while (a < z) {
+                    const int mid = (a + z) >> 1;
+                    const uint32_t k2 = kk[mid];
+                    const bool before = (l2 < l) ? (k2 >= key) : (k2 > key);
+                    if (before) a = mid + 1; else z = mid;
+                }
+                rank += a;
+            }
+        } else {
+            // padded slots (i >= K_l) of a level must not be counted as suppressed boxes
+            // -> caller guarantees keep_mask==0 there and we skip them via the valid-count below
+            rank = -1;
+        }
+        if (kept && rank < max_num) {
+            const float4 bx = ws_boxes[seg * nms_pre + i];
+            float *o = props + ((int64_t)b * max_num + rank) * 5;
+            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = ws_scores[seg * nms_pre + i];
+            pmask[(int64_t)b * max_num + rank] = 1;
+        }
+        (void)total_kept;
+    }
+}
+
+// suppressed boxes: rank = total_kept + (#suppressed valid boxes before me in concat order)
+__global__ void __launch_bounds__(kMergeThreads)
+merge_suppressed_kernel(int L, int nms_pre, int max_num, const int *__restrict__ Kl_dev_unused,
+                        const float4 *__restrict__ ws_boxes, const float *__restrict__ ws_scores,
+                        const uint8_t *__restrict__ keep_mask, const int32_t *__restrict__ keep_pos,
+                        const int32_t *__restrict__ count, const NmsSegs sg,
+                        float *__restrict__ props, uint8_t *__restrict__ pmask)
+{
+    (void)Kl_dev_unused;
+    __shared__ int cnt[kMaxLv], cumk[kMaxLv + 1], cumv[kMaxLv + 1];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        int c = 0, v = 0;
+        for (int l = 0; l < L; l++) { cnt[l] = count[b * L + l]; cumk[l] = c; c += cnt[l]; cumv[l] = v; v += sg.K[l]; }
+        cumk[L] = c; cumv[L] = v;
+    }
+    __syncthreads();
+    const int total_kept = cumk[L], total_valid = cumv[L];
+    if (total_kept >= max_num) return;   // no room for suppressed boxes
+    for (int e = blockIdx.y * kMergeThreads + tid; e < L * nms_pre; e += kMergeSplit * kMergeThreads) {
+        const int l = e / nms_pre, i = e - l * nms_pre;
+        if (i >= sg.K[l]) continue;
+        const int64_t seg = (int64_t)b * L + l;
+        if (keep_mask[seg * nms_pre + i]) continue;
+        int lo = 0, hi = cnt[l];
+        const int32_t *kp = keep_pos + seg * nms_pre;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (kp[mid] < i) lo = mid + 1; else hi = mid; }
+        const int concat = cumv[l] + i;
+        const int kept_before = cumk[l] + lo;
+        const int rank = total_kept + (concat - kept_before);
+        if (rank < max_num) {
+            const float4 bx = ws_boxes[seg * nms_pre + i];
+            float *o = props + ((int64_t)b * max_num + rank) * 5;
+            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = ws_scores[seg * nms_pre + i];
+            pmask[(int64_t)b * max_num + rank] = 0;
+        }
+    }
+    // zero padding when fewer than max_num boxes exist at all
+    for (int r = total_valid + blockIdx.y * kMergeThreads + tid; r < max_num; r += kMergeSplit * kMergeThreads) {
+        float *o = props + ((int64_t)b * max_num + r) * 5;
+        o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f;
+        pmask[(int64_t)b * max_num + r] = 0;
+    }
+}
+
+// workspace layout (all per segment = b*L + l, nms_pre rows each)
+struct PropWs {
+    float4 *boxes; float *scores; int32_t *keep_pos; int32_t *count; unsigned long long *mask;
+};
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static PropWs carve_prop_ws(void *ws, int nseg, int nms_pre, size_t *total)
+{
+    PropWs w;
+    size_t o = 0;
+    unsigned char *p = reinterpret_cast<unsigned char *>(ws);
+    w.boxes = reinterpret_cast<float4 *>(p + o); o += align256((size_t)nseg * nms_pre * sizeof(float4));
+    w.scores = reinterpret_cast<float *>(p + o); o += align256((size_t)nseg * nms_pre * sizeof(float));
+    w.keep_pos = reinterpret_cast<int32_t *>(p + o); o += align256((size_t)nseg * nms_pre * sizeof(int32_t));
+    w.count = reinterpret_cast<int32_t *>(p + o); o += align256((size_t)nseg * sizeof(int32_t));
+    w.mask = reinterpret_cast<unsigned long long *>(p + o); o += nms_workspace_bytes(nseg, nms_pre);
+    if (total) *total = o;
+    return w;
+}
+size_t proposal_workspace_bytes(int B, int L, int nms_pre)
+{
+    size_t t = 0;
+    carve_prop_ws(nullptr, B * L, nms_pre, &t);
+    return t;
+}
+
+cudaError_t launch_proposal(const LevelSet &lv, int B, int nms_pre, int max_num, const float *cfg, void *ws,
+                            float *props, uint8_t *pmask, int32_t *topk_idx, uint8_t *keep, cudaStream_t s)
+{
+    if (lv.L < 1 || lv.L > kMaxLv || nms_pre > kSelMaxK) return cudaErrorInvalidValue;
+    const int L = lv.L, nseg = B * L;
+    if (nseg == 0) return cudaSuccess;
+    PropWs w = carve_prop_ws(ws, nseg, nms_pre, nullptr);
+    PropLevels pl{};
+    pl.L = L; pl.B = B; pl.nms_pre = nms_pre; pl.cfg = cfg;
+    int maxN = 0, Kmax = 0;
+    NmsSegs sg{};
+    for (int l = 0; l < L; l++) {
+        pl.A[l] = lv.A[l]; pl.W[l] = lv.W[l]; pl.HW[l] = lv.H[l] * lv.W[l];
+        const int N = lv.A[l] * lv.H[l] * lv.W[l];
+        if (N >= (1 << kSelMaxIndexBits)) return cudaErrorInvalidValue;
+        pl.K[l] = N < nms_pre ? N : nms_pre;
+        pl.scores[l] = lv.scores[l]; pl.deltas[l] = lv.deltas[l]; pl.base[l] = lv.base[l];
+        sg.K[l] = pl.K[l];
+        if (N > maxN) maxN = N;
+        if (pl.K[l] > Kmax) Kmax = pl.K[l];
+    }
+    cudaError_t e = launch_select_sorted(PropSrc{ pl }, PropSink{ pl, w.boxes, w.scores, topk_idx }, nseg, maxN, s);
+    if (e != cudaSuccess) return e;
+    sg.boxes = reinterpret_cast<const float *>(w.boxes); sg.ld = 4; sg.seg_stride = nms_pre; sg.L = L;
+    const int nb = (nms_pre + 63) / 64;
+    sg.nbp = (nb + 1) & ~1; sg.rows_pad = nb * 64;
+    e = run_nms(sg, nseg, Kmax, cfg + 11, w.mask, w.keep_pos, nms_pre, keep, nms_pre, w.count, s);
+    if (e != cudaSuccess) return e;
+    const size_t smem = (size_t)L * nms_pre * sizeof(uint32_t);
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(merge_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    merge_levels_kernel<<<dim3(B, kMergeSplit), kMergeThreads, smem, s>>>(
+        L, nms_pre, max_num, w.boxes, w.scores, keep, w.keep_pos, w.count, props, pmask);
+    merge_suppressed_kernel<<<dim3(B, kMergeSplit), kMergeThreads, 0, s>>>(
+        L, nms_pre, max_num, nullptr, w.boxes, w.scores, keep, w.keep_pos, w.count, sg, props, pmask);
+    return cudaGetLastError();
+}
+
+}  // namespace md
