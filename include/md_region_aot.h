@@ -118,13 +118,20 @@ MD_API int MdRoiLevels(MD_AOT_ARGS);
 
 /* a9+a10  SingleRoIExtractor forward (level map + RoIAlign on the mapped level only)
  *   in : rois (R,5) f32 | feat_0..feat_{L-1} (B,C,H_l,W_l) f32 | cfg f32[4+L] = MD_CFG_ROI
- *   out: roi_feats (R,C,P,P) f32            (nparam = L+2+1) */
+ *   out: roi_feats (R,C,P,P) f32            (nparam = L+2+1)
+ *   Default path: TMA-staged tiles + separable bilinear operators (rtol 1e-5 / atol 1e-6 vs the oracle). */
 MD_API int MdRoiAlignFwd(MD_AOT_ARGS);
 
 /* a11  ROIAlignGrad (bprop of MdRoiAlignFwd); outputs are zero-filled then accumulated
  *   in : rois (R,5) f32 | dout (R,C,P,P) f32 | cfg f32[4+L]
  *   out: dfeat_0..dfeat_{L-1} (B,C,H_l,W_l) f32     (nparam = 3+L) */
 MD_API int MdRoiAlignBwd(MD_AOT_ARGS);
+
+/* Bit-exact variants: same I/O, gather kernels only (forward bit-identical to the oracle's op order;
+ * used for levels/footprints the TMA path declines, and selectable by symbol because attributes cannot
+ * be read on the host from a device cfg tensor). */
+MD_API int MdRoiAlignFwdExact(MD_AOT_ARGS);
+MD_API int MdRoiAlignBwdExact(MD_AOT_ARGS);
 
 /* library info: returns a static string "libmdregion <version> sm_100a" */
 MD_API const char *MdVersion(void);

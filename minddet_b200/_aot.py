@@ -21,7 +21,8 @@ _DTYPE_NAMES = {
 }
 
 SYMBOLS = ("MdAnchorGrid", "MdDecodeClip", "MdDecodeLevel", "MdTopKPerLevel", "MdNms", "MdProposal",
-           "MdAssignSample", "MdAssignSampleRcnn", "MdRoiLevels", "MdRoiAlignFwd", "MdRoiAlignBwd")
+           "MdAssignSample", "MdAssignSampleRcnn", "MdRoiLevels", "MdRoiAlignFwd", "MdRoiAlignBwd",
+           "MdRoiAlignFwdExact", "MdRoiAlignBwdExact")
 
 ERRORS = {1: "wrong nparam", 2: "bad dtype/shape", 3: "CUDA error", 4: "unsupported size"}
 

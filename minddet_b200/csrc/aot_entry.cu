@@ -277,7 +277,7 @@ static int parse_feats(int L, int first, void **params, int *ndims, int64_t **sh
     return MD_OK;
 }
 
-int MdRoiAlignFwd(MD_AOT_ARGS)
+static int roialign_fwd_impl(int mode, MD_AOT_ARGS)
 {
     (void)extra;
     if (nparam < 4) return MD_ERR_NPARAM;
@@ -292,11 +292,14 @@ int MdRoiAlignFwd(MD_AOT_ARGS)
     const int R = (int)shapes[0][0];
     REQ(is_f32(dtypes[io]) && ndims[io] == 4 && shapes[io][0] == R && shapes[io][1] == fs.C && shapes[io][2] == shapes[io][3]);
     const int P = (int)shapes[io][2];
+    void *ws = nullptr;
+    rc = get_workspace(stream, md::roialign_workspace_bytes(R), &ws);
+    if (rc) return rc;
     return cuda_rc(md::launch_roialign_fwd(fs, (const float *)params[0], R, P, (const float *)params[ic],
-                                           (float *)params[io], (cudaStream_t)stream));
+                                           (float *)params[io], ws, mode, (cudaStream_t)stream));
 }
 
-int MdRoiAlignBwd(MD_AOT_ARGS)
+static int roialign_bwd_impl(int mode, MD_AOT_ARGS)
 {
     (void)extra;
     if (nparam < 4) return MD_ERR_NPARAM;
@@ -310,8 +313,16 @@ int MdRoiAlignBwd(MD_AOT_ARGS)
     REQ(is_f32(dtypes[1]) && ndims[1] == 4 && shapes[1][0] == R && shapes[1][1] == fs.C && shapes[1][2] == shapes[1][3]);
     REQ(is_f32(dtypes[2]) && numel(ndims[2], shapes[2]) >= MD_ROI_STRIDE0 + L);
     const int P = (int)shapes[1][2];
+    void *ws = nullptr;
+    rc = get_workspace(stream, md::roialign_workspace_bytes(R), &ws);
+    if (rc) return rc;
     return cuda_rc(md::launch_roialign_bwd(fs, (const float *)params[0], R, P, (const float *)params[2],
-                                           (const float *)params[1], (cudaStream_t)stream));
+                                           (const float *)params[1], ws, mode, (cudaStream_t)stream));
 }
+
+int MdRoiAlignFwd(MD_AOT_ARGS) { return roialign_fwd_impl(0, nparam, params, ndims, shapes, dtypes, stream, extra); }
+int MdRoiAlignBwd(MD_AOT_ARGS) { return roialign_bwd_impl(0, nparam, params, ndims, shapes, dtypes, stream, extra); }
+int MdRoiAlignFwdExact(MD_AOT_ARGS) { return roialign_fwd_impl(1, nparam, params, ndims, shapes, dtypes, stream, extra); }
+int MdRoiAlignBwdExact(MD_AOT_ARGS) { return roialign_bwd_impl(1, nparam, params, ndims, shapes, dtypes, stream, extra); }
 
 }  // extern "C"

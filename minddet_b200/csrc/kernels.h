@@ -58,9 +58,11 @@ struct FeatSet {
     float *feat[kMaxLv];    // (B,C,H,W)  (const for fwd, written by bwd)
 };
 cudaError_t launch_roi_levels(const float *rois5, int R, const float *cfg, int32_t *out, cudaStream_t s);
+size_t roialign_workspace_bytes(int R);
+// mode (cfg slot MD_ROI_MODE): 0 = TMA separable kernels (+ gather for RoIs they decline), 1 = gather only
 cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
-                                float *out, cudaStream_t s);
+                                float *out, void *ws, int mode, cudaStream_t s);
 cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
-                                const float *dout, cudaStream_t s);
+                                const float *dout, void *ws, int mode, cudaStream_t s);
 
 }  // namespace md

@@ -9,29 +9,9 @@
 // bit-identical to oracle/region_oracle.c:o_roialign_fwd.  Backward accumulates with float atomics
 // (order is not deterministic -> FP tolerance only, as north_star allows).
 #include "kernels.h"
-#include "common.cuh"
+#include "roialign_common.cuh"
 
 namespace md {
-
-constexpr int kRoiMaxTaps = 14 * 14 * 4;   // P*P*S*S upper bound handled by the tap table
-
-struct RoiFeat {
-    int L, B, C;
-    int H[kMaxLv], W[kMaxLv];
-    float *feat[kMaxLv];
-    const float *cfg;
-};
-
-MD_DEVINL int roi_level_of(const float *r /* x1,y1,x2,y2 */, float finest, int num_levels)
-{
-    const float w = add(sub(r[2], r[0]), 1.0f);
-    const float h = add(sub(r[3], r[1]), 1.0f);
-    const float s = __fsqrt_rn(mul(w, h));
-    const float t = add(div(s, finest), 1e-6f);
-    int l = (t >= 2.0f) + (t >= 4.0f) + (t >= 8.0f);
-    for (int k = 4; k < num_levels; k++) l += (t >= (float)(1 << k));
-    return min(l, num_levels - 1);
-}
 
 __global__ void roi_levels_kernel(const float *__restrict__ rois5, int R, const float *__restrict__ cfg,
                                   int32_t *__restrict__ out)
@@ -51,51 +31,6 @@ cudaError_t launch_roi_levels(const float *rois5, int R, const float *cfg, int32
     return cudaGetLastError();
 }
 
-// one bilinear sample: 4 plane offsets + 4 weights (weights 0 when the sample is out of range)
-struct __align__(16) Tap { int o1, o2, o3, o4; float w1, w2, w3, w4; };
-
-MD_DEVINL Tap make_tap(float y, float x, int H, int W)
-{
-    Tap t; t.o1 = t.o2 = t.o3 = t.o4 = 0; t.w1 = t.w2 = t.w3 = t.w4 = 0.0f;
-    if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) return t;
-    if (y <= 0.0f) y = 0.0f;
-    if (x <= 0.0f) x = 0.0f;
-    int yl = (int)y, xl = (int)x, yh, xh;
-    if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
-    if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
-    const float ly = sub(y, (float)yl), lx = sub(x, (float)xl);
-    const float hy = sub(1.0f, ly), hx = sub(1.0f, lx);
-    t.o1 = yl * W + xl; t.o2 = yl * W + xh; t.o3 = yh * W + xl; t.o4 = yh * W + xh;
-    t.w1 = mul(hy, hx); t.w2 = mul(hy, lx); t.w3 = mul(ly, hx); t.w4 = mul(ly, lx);
-    return t;
-}
-
-struct RoiGeom { int b, l, H, W; float sw, sh, bw, bh; };
-
-MD_DEVINL RoiGeom roi_geometry(const RoiFeat &f, const float *__restrict__ roi, int P)
-{
-    RoiGeom g;
-    float r[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) r[k] = __ldg(roi + 1 + k);
-    g.b = (int)__ldg(roi);
-    g.l = roi_level_of(r, __ldg(f.cfg + 0), f.L);
-    g.H = f.H[g.l]; g.W = f.W[g.l];
-    const float scale = div(1.0f, __ldg(f.cfg + 4 + g.l));
-    const float em = __ldg(f.cfg + 2);
-    g.sw = mul(r[0], scale); g.sh = mul(r[1], scale);
-    const float ew = mul(add(r[2], em), scale), eh = mul(add(r[3], em), scale);
-    const float rw = fmaxf(sub(ew, g.sw), 1.0f), rh = fmaxf(sub(eh, g.sh), 1.0f);
-    g.bw = div(rw, (float)P); g.bh = div(rh, (float)P);
-    return g;
-}
-MD_DEVINL float sample_coord(float start, float bin, int p, int i, int S)
-{
-    const float base = add(start, mul((float)p, bin));
-    const float o = div(mul(add((float)i, 0.5f), bin), (float)S);
-    return add(base, o);
-}
-
 MD_DEVINL void build_taps(const RoiGeom &g, int P, int S, Tap *taps)
 {
     const int n = P * P * S * S;
@@ -111,10 +46,11 @@ constexpr int kRoiThreads = 256;
 
 __global__ void __launch_bounds__(kRoiThreads)
 roialign_fwd_gather_kernel(const RoiFeat f, const float *__restrict__ rois5, int P, int csplit,
-                           float *__restrict__ out)
+                           float *__restrict__ out, const int32_t *__restrict__ only_flagged)
 {
     __shared__ Tap taps[kRoiMaxTaps];
     const int r = blockIdx.x;
+    if (only_flagged && !only_flagged[r]) return;   // handled by the TMA kernel
     const int S = (int)__ldg(f.cfg + 1);
     const RoiGeom g = roi_geometry(f, rois5 + (int64_t)r * 5, P);
     build_taps(g, P, S, taps);
@@ -142,10 +78,11 @@ roialign_fwd_gather_kernel(const RoiFeat f, const float *__restrict__ rois5, int
 
 __global__ void __launch_bounds__(kRoiThreads)
 roialign_bwd_gather_kernel(const RoiFeat f, const float *__restrict__ rois5, int P, int csplit,
-                           const float *__restrict__ dout)
+                           const float *__restrict__ dout, const int32_t *__restrict__ only_flagged)
 {
     __shared__ Tap taps[kRoiMaxTaps];
     const int r = blockIdx.x;
+    if (only_flagged && !only_flagged[r]) return;
     const int S = (int)__ldg(f.cfg + 1);
     const RoiGeom g = roi_geometry(f, rois5 + (int64_t)r * 5, P);
     build_taps(g, P, S, taps);
@@ -178,19 +115,33 @@ static RoiFeat to_roifeat(const FeatSet &fs, const float *cfg)
     return f;
 }
 
+cudaError_t launch_roialign_fwd_tma(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P,
+                                    float *out, int32_t *fallback_flag, cudaStream_t s, bool *launched);
+cudaError_t launch_roialign_bwd_tma(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P,
+                                    const float *dout, int32_t *fallback_flag, cudaStream_t s, bool *launched);
+
+size_t roialign_workspace_bytes(int R) { return (size_t)R * sizeof(int32_t) + 256; }
+
+// mode: 0 = TMA separable kernel + gather for the RoIs it declines (default); 1 = gather only (bit-exact fwd)
 cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
-                                float *out, cudaStream_t s)
+                                float *out, void *ws, int mode, cudaStream_t s)
 {
     if (R == 0) return cudaSuccess;
     if (P * P * 4 > kRoiMaxTaps || fs.L > kMaxLv) return cudaErrorInvalidValue;
     const RoiFeat f = to_roifeat(fs, cfg);
-    const int csplit = fs.C >= 64 ? 4 : 1;
-    roialign_fwd_gather_kernel<<<dim3(R, csplit), kRoiThreads, 0, s>>>(f, rois5, P, csplit, out);
+    int32_t *flags = reinterpret_cast<int32_t *>(ws);
+    bool tma = false;
+    if (mode == 0 && flags) {
+        cudaError_t e = launch_roialign_fwd_tma(fs, f, rois5, R, P, out, flags, s, &tma);
+        if (e != cudaSuccess) return e;
+    }
+    const int csplit = (fs.C >= 64 && !tma) ? 4 : 1;
+    roialign_fwd_gather_kernel<<<dim3(R, csplit), kRoiThreads, 0, s>>>(f, rois5, P, csplit, out, tma ? flags : nullptr);
     return cudaGetLastError();
 }
 
 cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
-                                const float *dout, cudaStream_t s)
+                                const float *dout, void *ws, int mode, cudaStream_t s)
 {
     if (P * P * 4 > kRoiMaxTaps || fs.L > kMaxLv) return cudaErrorInvalidValue;
     for (int l = 0; l < fs.L; l++) {
@@ -199,8 +150,14 @@ cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, in
     }
     if (R == 0) return cudaSuccess;
     const RoiFeat f = to_roifeat(fs, cfg);
-    const int csplit = fs.C >= 64 ? 4 : 1;
-    roialign_bwd_gather_kernel<<<dim3(R, csplit), kRoiThreads, 0, s>>>(f, rois5, P, csplit, dout);
+    int32_t *flags = reinterpret_cast<int32_t *>(ws);
+    bool tma = false;
+    if (mode == 0 && flags) {
+        cudaError_t e = launch_roialign_bwd_tma(fs, f, rois5, R, P, dout, flags, s, &tma);
+        if (e != cudaSuccess) return e;
+    }
+    const int csplit = (fs.C >= 64 && !tma) ? 4 : 1;
+    roialign_bwd_gather_kernel<<<dim3(R, csplit), kRoiThreads, 0, s>>>(f, rois5, P, csplit, dout, tma ? flags : nullptr);
     return cudaGetLastError();
 }
 

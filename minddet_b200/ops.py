@@ -247,12 +247,15 @@ class SingleRoIExtractor(_Cell):
     """a9..a12.  ``construct(rois, feat1, ..., featL)`` -> (R,C,P,P); rois (R,5) = [batch,x1,y1,x2,y2].
     Only the level each RoI maps to is read.  The bprop (ROIAlignGrad) is ``MdRoiAlignBwd``."""
 
-    def __init__(self, out_size=7, sample_num=2, featmap_strides=(4, 8, 16, 32), finest_scale=56, roi_end_mode=0):
+    def __init__(self, out_size=7, sample_num=2, featmap_strides=(4, 8, 16, 32), finest_scale=56, roi_end_mode=0,
+                 exact=False):
+        """exact=True selects the gather kernels only (forward bit-identical to the oracle's op order);
+        the default is the TMA-staged separable path (rtol 1e-5 / atol 1e-6)."""
         self.P = out_size
         self.strides = [float(s) for s in featmap_strides]
         self.cfg_values = [float(finest_scale), float(sample_num), float(roi_end_mode), 0.0] + self.strides
-        self._fwd = Custom(_so("MdRoiAlignFwd"), None, torch.float32)
-        self._bwd = Custom(_so("MdRoiAlignBwd"), None, torch.float32)
+        self._fwd = Custom(_so("MdRoiAlignFwdExact" if exact else "MdRoiAlignFwd"), None, torch.float32)
+        self._bwd = Custom(_so("MdRoiAlignBwdExact" if exact else "MdRoiAlignBwd"), None, torch.float32)
         self._lvl = Custom(_so("MdRoiLevels"), lambda r, c: (r[0],), torch.int32)
 
     def map_roi_levels(self, rois):
