@@ -1,23 +1,30 @@
-// roialign_tma.cu -- a10/a11 fast path: TMA-staged feature tiles + separable bilinear operators.
+// roialign_tma.cu -- a10/a11 fast path: per-warp ROW-STREAMING TMA rings + separable bilinear operators.
 //
-// RoIAlign (aligned=False, S x S samples averaged) is a separable linear map per (RoI, channel):
-//        Out[ph][pw] = sum_y sum_x  Ay[ph][y] * F[y][x] * Ax[pw][x]
-// where Ay[ph][.] / Ax[pw][.] accumulate the 1-D bilinear weights of the S samples of bin row ph /
-// bin column pw (validity and edge clamping are per-axis, so they separate too).  Each operator row has
-// a short contiguous support.  Per (RoI, channel chunk):
-//   forward : the footprint tile [c][y][x] is brought NCHW -> shared memory by TMA
-//             (cp.async.bulk.tensor.3d, mbarrier complete_tx, double buffered); thread (c,x) walks its
-//             column ONCE (U[ph][x] = sum_y Ay F: conflict-free, every tile element read once), then
-//             thread (c,ph,pw) contracts U with Ax and stores coalesced.
-//   backward: the transpose: T = G Ax, dTile = Ay^T T written conflict-free (no shared-memory float
-//             atomics -- they are CAS loops on sm_100a), then ONE TMA reduce-add
-//             (cp.reduce.async.bulk.tensor .add.f32) per box folds the tile into dX at L2.
-// Tiles are tight: the box starts at the footprint's x rounded down to 4 floats (TMA needs a 16-byte aligned
-// innermost coordinate) and its width is rounded up to 4 floats (one tensor map per width),
-// rows come in boxes of 8, channels in boxes of 4.  RoIs whose level pitch is not 16-byte aligned, or
-// whose footprint does not fit, take the gather kernels of roialign.cu (bit-exact path).
+// RoIAlign (aligned=False, S x S samples averaged) is separable per (RoI, channel):
+//        Out[p][q] = sum_{sy in bin p} sum_{sx in bin q}  wy(sy) . F[rows(sy)][cols(sx)] . wx(sx)
+// where every 1-D sample touches two adjacent rows / columns (validity and edge clamping are per axis).
 //
-// Forward here is NOT bit-identical to the oracle (different summation order, FMA): tolerance
+// Work decomposition (one CTA of 4 warps per RoI, warps fully decoupled -- no CTA barrier after the
+// prologue):
+//   * lane = (channel-in-group, column quad): a warp owns CPW = 32/LPC channels at a time, LPC lanes per
+//     channel, 4 feature columns per lane (LPC in {4,8,16,32} chosen from the footprint width BW <= 128).
+//   * the footprint of a channel group is streamed through a per-warp shared-memory ring of ROW BLOCKS
+//     (box = BW columns x 4 rows x CPW channels, NCHW -> smem by ONE cp.async.bulk.tensor.3d each; the
+//     box x-origin is rounded down to 4 floats because TMA needs a 16-byte aligned innermost coordinate).
+//     Blocks of consecutive channel groups follow each other in the ring, so the pipeline never drains;
+//     any footprint height works (the window slides with the samples, which are sorted in y).
+//   forward : step 1 (registers)  U[p][4 cols] += wy . row  for the 2*S*P (sample,row) pairs, 128-bit LDS
+//             step 2              U -> smem, 4 column taps per output, outputs stored fully coalesced.
+//   backward: step 1 (registers)  T[p][4 cols] = sum_q dY[p][q] . Ax[q][cols]      (dY staged by cp.async)
+//             step 2              D[row][4 cols] = sum_p Ay[p][row] . T[p]  (<= 4 non-zero bins per row),
+//             written conflict-free into the ring and folded into dX by ONE TMA reduce-add per row block
+//             (cp.reduce.async.bulk.tensor .add.f32, performed at L2; no smem or per-element atomics).
+//   Levels whose row pitch is not a multiple of 16 bytes (e.g. 25x42) cannot be described by a tensor map:
+//   the same ring is filled with 4-byte cp.async (completion through the same mbarriers), and the
+//   backward uses red.global.add.f32 per element.  RoIs the kernel declines (footprint wider than 128
+//   columns, S != 2, ...) are flagged and handled by the gather kernels of roialign.cu.
+//
+// Forward here is NOT bit-identical to the oracle (separable summation order, FMA): tolerance
 // rtol 1e-5 (north_star) + atol 1e-6 for cancellation; tests/test_gpu_parity.py states it.
 #include <cuda.h>
 
@@ -29,25 +36,22 @@
 
 namespace md {
 
-constexpr int kTmaThreads = 256;
-constexpr int kBoxRows = 8, kBoxCh = 4;
-constexpr int kMaxBW = 64, kMaxHT = 64;
-constexpr int kNumBW = kMaxBW / 4;                 // tensor maps per level
-constexpr int kTileFloats = 6144;                  // per buffer (24 KB)
-constexpr int kUFloats = 4096;                     // U / T scratch (16 KB)
-constexpr int kGFloats = 2048;                     // dY chunk (bwd)
-constexpr int kMaxP = 14;
-constexpr int kCCMax = 32;
+constexpr int kStWarps = 4;
+constexpr int kStThreads = kStWarps * 32;
+constexpr int kRingFloats = 3328;          // forward ring per warp (13 KB)
+constexpr int kMaxBW = 128;                // footprint width limit (floats)
+constexpr int kMaxSlots = 16;
+constexpr int kBwdSlots = 4;               // fixed: cp.async.bulk.wait_group needs an immediate
+constexpr int kBwdRingFloats = kBwdSlots * 512;
+constexpr int kNumBW = kMaxBW / 4;         // tensor maps per level
+constexpr int kTmaLevels = 4;
+constexpr int kMaxRowsBwd = 128;           // backward row-table capacity
 
-struct TmaMaps { CUtensorMap m[4 * kNumBW]; };      // [level][bw/4 - 1]
+struct TmaMaps { CUtensorMap m[kTmaLevels * kNumBW]; };   // [level][bw/4 - 1], box = {bw, 4, CPW(bw)}
 
-struct TmaShared {
-    unsigned long long bar[2];
-    float Ay[kMaxP][kMaxHT];
-    float Ax[kMaxP][kMaxBW];
-    int ys[kMaxP], ye[kMaxP], xs[kMaxP], xe[kMaxP];   // support [s, e) of each operator row (tile coords)
-    int x_lo, y_lo, w_fp, h_fp, fits;
-};
+struct __align__(16) SampleTap { int lo, hi; float wl, wh; };   // rows/cols relative to the footprint origin
+
+__host__ __device__ inline int lanes_per_channel(int bw) { return bw <= 16 ? 4 : (bw <= 32 ? 8 : (bw <= 64 ? 16 : 32)); }
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
 MD_DEVINL uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -82,9 +86,19 @@ MD_DEVINL void tma_reduce_add_3d(const CUtensorMap *map, int x, int y, int z, co
 }
 MD_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> MD_DEVINL void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+template <int N> MD_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
+MD_DEVINL void cp_async4(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+MD_DEVINL void cp_async_mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+MD_DEVINL void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> MD_DEVINL void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-// ---- separable operators -------------------------------------------------------------------------------
-// 1-D sample -> (low index, high index, low weight (h), high weight (l), valid); mirrors make_tap.
+// ---- 1-D sample -> (low index, high index, low weight, high weight, valid); mirrors make_tap ----------
 MD_DEVINL bool sample_1d(float v, int extent, int &lo, int &hi, float &wl, float &wh)
 {
     if (v < -1.0f || v > (float)extent) return false;
@@ -96,284 +110,440 @@ MD_DEVINL bool sample_1d(float v, int extent, int &lo, int &hi, float &wl, float
     return true;
 }
 
-// Builds Ay/Ax (scaled by 1/S each), their supports and the footprint; returns through sh.
-// Called by all threads; thread p < P builds row p of Ay, thread 32+p row p of Ax.
-MD_DEVINL void build_operators(TmaShared &sh, const RoiGeom &g, int P, int S)
-{
-    const int t = threadIdx.x;
-    for (int i = t; i < kMaxP * kMaxHT; i += blockDim.x) (&sh.Ay[0][0])[i] = 0.0f;
-    for (int i = t; i < kMaxP * kMaxBW; i += blockDim.x) (&sh.Ax[0][0])[i] = 0.0f;
-    // footprint bounds: every thread computes them redundantly (cheap, uniform)
-    int x_lo = 1 << 30, x_hi = -1, y_lo = 1 << 30, y_hi = -1;
-    for (int p = 0; p < P; p++)
-        for (int i = 0; i < S; i++) {
-            int lo, hi; float wl, wh;
-            if (sample_1d(sample_coord(g.sw, g.bw, p, i, S), g.W, lo, hi, wl, wh)) { x_lo = min(x_lo, lo); x_hi = max(x_hi, hi); }
-            if (sample_1d(sample_coord(g.sh, g.bh, p, i, S), g.H, lo, hi, wl, wh)) { y_lo = min(y_lo, lo); y_hi = max(y_hi, hi); }
-        }
-    const bool any = x_hi >= 0 && y_hi >= 0;
-    if (!any) { x_lo = y_lo = 0; x_hi = y_hi = 0; }
-    x_lo &= ~3;   // the innermost TMA coordinate must be 16-byte aligned (unaligned -> "illegal instruction", measured)
-    const int w_fp = x_hi - x_lo + 1, h_fp = y_hi - y_lo + 1;
-    const bool fits = w_fp <= kMaxBW && h_fp <= kMaxHT;
-    __syncthreads();
-    const float inv = div(1.0f, (float)S);
-    if (fits && t < P) {                       // Ay row t
-        int s = 1 << 30, e = 0;
-        for (int i = 0; i < S; i++) {
-            int lo, hi; float wl, wh;
-            if (!sample_1d(sample_coord(g.sh, g.bh, t, i, S), g.H, lo, hi, wl, wh)) continue;
-            sh.Ay[t][lo - y_lo] += wl * inv;
-            sh.Ay[t][hi - y_lo] += wh * inv;
-            s = min(s, lo - y_lo); e = max(e, hi - y_lo + 1);
-        }
-        if (e == 0) s = 0;
-        sh.ys[t] = s; sh.ye[t] = e;
-    }
-    if (fits && t >= 32 && t < 32 + P) {       // Ax row t-32
-        const int p = t - 32;
-        int s = 1 << 30, e = 0;
-        for (int i = 0; i < S; i++) {
-            int lo, hi; float wl, wh;
-            if (!sample_1d(sample_coord(g.sw, g.bw, p, i, S), g.W, lo, hi, wl, wh)) continue;
-            sh.Ax[p][lo - x_lo] += wl * inv;
-            sh.Ax[p][hi - x_lo] += wh * inv;
-            s = min(s, lo - x_lo); e = max(e, hi - x_lo + 1);
-        }
-        if (e == 0) s = 0;
-        sh.xs[p] = s; sh.xe[p] = e;
-    }
-    if (t == 0) { sh.x_lo = x_lo; sh.y_lo = y_lo; sh.w_fp = w_fp; sh.h_fp = h_fp; sh.fits = fits; }
-    __syncthreads();
-}
+// ---- per-RoI prologue: sample tables and footprint --------------------------------------------------
+template <int P>
+struct StreamShared {
+    unsigned long long full[kStWarps][kMaxSlots];
+    SampleTap ytab[2 * P], xtab[2 * P];
+    int x_lo, y_lo, bw, h_fp, any_x, any_y;
+};
 
-// rows_per_group / CC selection so that tile and scratch fit; returns false if even one bin row does not.
-struct Plan { int BW, rows, CC, ngroups; };
-MD_DEVINL bool make_plan(const TmaShared &sh, int P, int gcap_floats, Plan &pl)
+// warp 0 builds the y table, warp 1 the x table (2*P <= 32 samples per axis); weights carry the 1/S factor.
+template <int P>
+MD_DEVINL void build_tables(StreamShared<P> &sh, const RoiGeom &g)
 {
-    pl.BW = (sh.w_fp + 3) & ~3;
-    int rows = P;
-    for (;;) {
-        // tallest group with this many bin rows
-        int ht = 0;
-        for (int p0 = 0; p0 < P; p0 += rows) {
-            const int p1 = min(P, p0 + rows) - 1;
-            int y0 = 1 << 30, y1 = 0;
-            for (int p = p0; p <= p1; p++) if (sh.ye[p] > 0) { y0 = min(y0, sh.ys[p]); y1 = max(y1, sh.ye[p]); }
-            if (y1 > 0) ht = max(ht, ((y1 - y0) + kBoxRows - 1) / kBoxRows * kBoxRows);
+    constexpr int S = 2, NS = P * S;
+    static_assert(NS <= 32, "one warp builds one axis");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < 2) {
+        const bool is_y = warp == 0;
+        const int extent = is_y ? g.H : g.W;
+        int lo = 0, hi = 0;
+        float wl = 0.0f, wh = 0.0f, v = 0.0f;
+        bool ok = false;
+        if (lane < NS) {
+            v = is_y ? sample_coord(g.sh, g.bh, lane / S, lane % S, S) : sample_coord(g.sw, g.bw, lane / S, lane % S, S);
+            ok = sample_1d(v, extent, lo, hi, wl, wh);
         }
-        if (ht == 0) ht = kBoxRows;
-        int cc = min(kCCMax, kTileFloats / (pl.BW * ht));
-        cc = min(cc, kUFloats / (rows * pl.BW));
-        if (gcap_floats) cc = min(cc, gcap_floats / (rows * P));
-        cc &= ~(kBoxCh - 1);
-        if (cc >= kBoxCh) { pl.rows = rows; pl.CC = cc; pl.ngroups = (P + rows - 1) / rows; return true; }
-        if (rows == 1) return false;
-        rows = (rows + 1) / 2;
+        int mn = ok ? lo : (1 << 30), mx = ok ? hi : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        const bool any = mx >= 0;
+        if (!any) { mn = 0; mx = 0; }
+        if (!is_y) mn &= ~3;   // the innermost TMA coordinate must be 16-byte aligned
+        if (lane < NS) {
+            SampleTap t;
+            if (ok) { t.lo = lo - mn; t.hi = hi - mn; t.wl = mul(wl, 0.5f); t.wh = mul(wh, 0.5f); }
+            else { t.lo = t.hi = (v < -1.0f) ? 0 : (mx - mn); t.wl = t.wh = 0.0f; }   // keeps the table monotone
+            (is_y ? sh.ytab : sh.xtab)[lane] = t;
+        }
+        if (lane == 0) {
+            if (is_y) { sh.y_lo = mn; sh.h_fp = mx - mn + 1; sh.any_y = any; }
+            else { sh.x_lo = mn; sh.bw = (mx - mn + 1 + 3) & ~3; sh.any_x = any; }
+        }
     }
 }
 
 // =====================================================================================================
 // forward
 // =====================================================================================================
-__global__ void __launch_bounds__(kTmaThreads)
-roialign_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f, const float *__restrict__ rois5,
-                        int P, float *__restrict__ out, int32_t *__restrict__ fallback_flag)
+template <int P>
+__global__ void __launch_bounds__(kStThreads, 3)
+roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f, const int tma_mask,
+                           const float *__restrict__ rois5, float *__restrict__ out, int32_t *__restrict__ fallback_flag)
 {
+    constexpr int S = 2, NS = P * S, PP = P * P;
+    constexpr int kUFloats = P * 160;                     // max over LPC of CPW * P * (4*LPC + 4)
     extern __shared__ __align__(128) unsigned char dsm[];
-    float *tile0 = reinterpret_cast<float *>(dsm);
-    float *tile1 = tile0 + kTileFloats;
-    float *U = tile1 + kTileFloats;
-    TmaShared &sh = *reinterpret_cast<TmaShared *>(U + kUFloats);
-    const int r = blockIdx.x, tid = threadIdx.x;
-    const int S = (int)__ldg(f.cfg + 1);
+    float *ring_all = reinterpret_cast<float *>(dsm);
+    float *U_all = ring_all + kStWarps * kRingFloats;
+    StreamShared<P> &sh = *reinterpret_cast<StreamShared<P> *>(U_all + kStWarps * kUFloats);
+
+    const int r = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const RoiGeom g = roi_geometry(f, rois5 + (int64_t)r * 5, P);
-    const bool aligned = (g.W & 3) == 0;
-    Plan pl{};
-    bool ok = aligned && P <= kMaxP && g.l < 4;
-    if (ok) {
-        build_operators(sh, g, P, S);
-        ok = sh.fits && make_plan(sh, P, 0, pl);
-    }
-    if (!ok) {                                   // uniform per CTA: gather path handles this RoI
+    const int C = f.C;
+    const bool use_tma = (tma_mask >> g.l) & 1;
+    if ((int)__ldg(f.cfg + 1) != S || g.l >= kTmaLevels) {        // uniform: gather path handles this RoI
         if (tid == 0) fallback_flag[r] = 1;
         return;
     }
-    if (tid == 0) {
-        fallback_flag[r] = 0;
-        mbar_init(&sh.bar[0], 1); mbar_init(&sh.bar[1], 1);
+    if (lane == 0) {
+        for (int i = 0; i < kMaxSlots; i++) mbar_init(&sh.full[warp][i], use_tma ? 1 : 32);
         fence_barrier_init();
     }
+    build_tables<P>(sh, g);
     __syncthreads();
-    const CUtensorMap *map = &maps.m[g.l * kNumBW + (pl.BW >> 2) - 1];
-    const int PP = P * P, C = f.C;
-    const int nchunks = (C + pl.CC - 1) / pl.CC;
-    const int nstages = pl.ngroups * nchunks;
-    float *tiles[2] = { tile0, tile1 };
+    const int BW = sh.bw;
+    if (BW > kMaxBW) {
+        if (tid == 0) fallback_flag[r] = 1;
+        return;
+    }
+    if (tid == 0) fallback_flag[r] = 0;
+    float *orow = out + (int64_t)r * C * PP;
+    if (!sh.any_x || !sh.any_y) {                                   // every sample is out of range -> zeros
+        for (int i = tid; i < C * PP; i += kStThreads) orow[i] = 0.0f;
+        return;
+    }
+    const int LPC = lanes_per_channel(BW), CPW = 32 / LPC, BWU = 4 * LPC + 4;
+    const int lshift = LPC == 4 ? 2 : (LPC == 8 ? 3 : (LPC == 16 ? 4 : 5));
+    const int csub = lane >> lshift, xq = lane & (LPC - 1);
+    const bool col_ok = 4 * xq < BW;
+    const int x_lo = sh.x_lo, y_lo = sh.y_lo, h_fp = sh.h_fp;
+    const int nblk = (h_fp + 3) >> 2;
+    const int BLK = CPW * 4 * BW, SLOT = (BLK + 31) & ~31;
+    const int NB = min(kMaxSlots, kRingFloats / SLOT);
+    const int ngroups = C / CPW;                                      // host guarantees C % 8 == 0
+    const int ng_w = (ngroups - warp + kStWarps - 1) / kStWarps;      // groups warp, warp+4, ...
+    const int total = ng_w * nblk;
+    float *ring = ring_all + warp * kRingFloats;
+    float *U = U_all + warp * kUFloats;
+    unsigned long long *full = sh.full[warp];
+    const CUtensorMap *map = &maps.m[g.l * kNumBW + (BW >> 2) - 1];
+    const int H = g.H, W = g.W;
+    const float *fplane = f.feat[g.l] + (int64_t)g.b * C * H * W;
 
-    // group geometry helper (uniform)
-    auto group_rows = [&](int gi, int &p0, int &p1, int &y0, int &ht) {
-        p0 = gi * pl.rows; p1 = min(P, p0 + pl.rows);
-        int a = 1 << 30, b = 0;
-        for (int p = p0; p < p1; p++) if (sh.ye[p] > 0) { a = min(a, sh.ys[p]); b = max(b, sh.ye[p]); }
-        if (b == 0) { a = 0; b = 1; }
-        y0 = a; ht = ((b - a) + kBoxRows - 1) / kBoxRows * kBoxRows;
+    // ---- producer state: block `iss` = (group iss_g, row block iss_j) goes to slot iss_slot --------------
+    int iss = 0, iss_g = 0, iss_j = 0, iss_slot = 0;
+    auto issue_one = [&]() {
+        __syncwarp();                                   // every lane is done reading the slot's previous block
+        const int c0 = (warp + kStWarps * iss_g) * CPW;
+        float *dst = ring + iss_slot * SLOT;
+        if (use_tma) {
+            if (lane == 0) {
+                mbar_expect_tx(&full[iss_slot], (uint32_t)BLK * 4u);
+                tma_load_3d(dst, map, x_lo, y_lo + 4 * iss_j, g.b * C + c0, &full[iss_slot]);
+            }
+        } else {
+            // elements outside the map are never used with a non-zero weight (rows/cols clamp), so they stay unwritten
+            for (int e = lane; e < BLK; e += 32) {
+                const int c = e / (4 * BW), rem = e - c * (4 * BW);
+                const int rr = rem / BW, xx = rem - rr * BW;
+                const int y = y_lo + 4 * iss_j + rr, x = x_lo + xx;
+                if (y < H && x < W) cp_async4(dst + e, fplane + ((int64_t)(c0 + c) * H + y) * W + x);
+            }
+            cp_async_mbar_arrive(&full[iss_slot]);
+        }
+        iss++;
+        if (++iss_j == nblk) { iss_j = 0; iss_g++; }
+        if (++iss_slot == NB) iss_slot = 0;
     };
-    auto issue = [&](int st) {                   // thread 0 only
-        const int gi = st / nchunks, ch = st - gi * nchunks;
-        int p0, p1, y0, ht;
-        group_rows(gi, p0, p1, y0, ht);
-        const int c0 = ch * pl.CC, cc = min(pl.CC, ((C - c0) + kBoxCh - 1) / kBoxCh * kBoxCh);
-        const int nty = ht / kBoxRows, ncb = cc / kBoxCh;
-        const uint32_t box_bytes = (uint32_t)(pl.BW * kBoxRows * kBoxCh * sizeof(float));
-        unsigned long long *bar = &sh.bar[st & 1];
-        mbar_expect_tx(bar, box_bytes * nty * ncb);
-        float *dst = tiles[st & 1];
-        for (int ty = 0; ty < nty; ty++)
-            for (int cb = 0; cb < ncb; cb++)
-                tma_load_3d(dst + (ty * ncb + cb) * (pl.BW * kBoxRows * kBoxCh), map, sh.x_lo,
-                            sh.y_lo + y0 + ty * kBoxRows, g.b * C + c0 + cb * kBoxCh, bar);
+    // ---- consumer state -------------------------------------------------------------------------------
+    int wt = 0, wt_slot = 0;
+    uint32_t wt_par = 0;
+    int grp_slot = 0;                                   // slot of the current group's block 0
+
+    // Make every block <= need visible.  A slot may be refilled only when its previous block has been both
+    // waited for (its mbarrier phase observed) and consumed (every block below `freed` is dead).
+    auto advance = [&](int need, int freed) {
+        for (;;) {
+            const int lim = min(freed, wt) + NB;
+            while (iss < total && iss < lim) issue_one();
+            if (wt > need) break;
+            mbar_wait(&full[wt_slot], wt_par);
+            wt++;
+            if (++wt_slot == NB) { wt_slot = 0; wt_par ^= 1u; }
+        }
     };
 
-    if (tid == 0) issue(0);
-    uint32_t phase[2] = { 0, 0 };
-    const int BW = pl.BW, w_fp = sh.w_fp;
-    for (int st = 0; st < nstages; st++) {
-        if (tid == 0 && st + 1 < nstages) issue(st + 1);
-        const int gi = st / nchunks, ch = st - gi * nchunks;
-        int p0, p1, y0, ht;
-        group_rows(gi, p0, p1, y0, ht);
-        const int c0 = ch * pl.CC, cc = min(pl.CC, C - c0);
-        const int ncb = (min(pl.CC, ((C - c0) + kBoxCh - 1) / kBoxCh * kBoxCh)) / kBoxCh;
-        const int rows = p1 - p0;
-        mbar_wait(&sh.bar[st & 1], phase[st & 1]);
-        phase[st & 1] ^= 1;
-        const float *tile = tiles[st & 1];
-        // ---- step 1: U[c][p][x] = sum_y Ay[p][y] * F[c][y][x]  (thread per (c, x) column) ----------
-        for (int i = tid; i < cc * w_fp; i += kTmaThreads) {
-            const int c = i / w_fp, x = i - c * w_fp;
-            const int cb = c / kBoxCh, ci = c - cb * kBoxCh;
-            for (int p = p0; p < p1; p++) {
-                float acc = 0.0f;
-                for (int y = sh.ys[p]; y < sh.ye[p]; y++) {
-                    const int yy = y - y0, ty = yy / kBoxRows, yi = yy - ty * kBoxRows;
-                    acc = __fmaf_rn(sh.Ay[p][y], tile[((ty * ncb + cb) * kBoxCh + ci) * (kBoxRows * BW) + yi * BW + x], acc);
-                }
-                U[(c * rows + (p - p0)) * BW + x] = acc;
+    for (int gi = 0; gi < ng_w; gi++) {
+        const int gbase = gi * nblk;
+        const int c0 = (warp + kStWarps * gi) * CPW;
+        float u[P][4];
+#pragma unroll
+        for (int p = 0; p < P; p++) u[p][0] = u[p][1] = u[p][2] = u[p][3] = 0.0f;
+        int cur_blk = 0, cur_slot = grp_slot;
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const SampleTap t = sh.ytab[s];
+            const int blo = t.lo >> 2, bhi = t.hi >> 2;
+            while (cur_blk < blo) { cur_blk++; if (++cur_slot == NB) cur_slot = 0; }
+            advance(gbase + bhi, gbase + blo);
+            int hi_slot = cur_slot;
+            if (bhi != blo) { hi_slot = cur_slot + 1; if (hi_slot == NB) hi_slot = 0; }
+            if (col_ok) {
+                const float4 a = *reinterpret_cast<const float4 *>(ring + cur_slot * SLOT + (csub * 4 + (t.lo & 3)) * BW + 4 * xq);
+                const float4 b = *reinterpret_cast<const float4 *>(ring + hi_slot * SLOT + (csub * 4 + (t.hi & 3)) * BW + 4 * xq);
+                u[s / S][0] = __fmaf_rn(t.wl, a.x, __fmaf_rn(t.wh, b.x, u[s / S][0]));
+                u[s / S][1] = __fmaf_rn(t.wl, a.y, __fmaf_rn(t.wh, b.y, u[s / S][1]));
+                u[s / S][2] = __fmaf_rn(t.wl, a.z, __fmaf_rn(t.wh, b.z, u[s / S][2]));
+                u[s / S][3] = __fmaf_rn(t.wl, a.w, __fmaf_rn(t.wh, b.w, u[s / S][3]));
             }
         }
-        __syncthreads();
-        // ---- step 2: Out[c][p][q] = sum_x U[c][p][x] * Ax[q][x]  (coalesced store) -------------------
-        float *o = out + ((int64_t)r * C + c0) * PP + p0 * P;
-        for (int i = tid; i < cc * rows * P; i += kTmaThreads) {
-            const int c = i / (rows * P), rem = i - c * (rows * P);
-            const int p = rem / P, q = rem - p * P;
-            float acc = 0.0f;
-            const float *u = U + (c * rows + p) * BW;
-            for (int x = sh.xs[q]; x < sh.xe[q]; x++) acc = __fmaf_rn(u[x], sh.Ax[q][x], acc);
-            o[(int64_t)c * PP + p * P + q] = acc;
+        // the whole group is consumed: release its blocks, keep the producer ahead
+        grp_slot += nblk;
+        while (grp_slot >= NB) grp_slot -= NB;
+        advance(gbase + nblk - 1, gbase + nblk);
+        // ---- step 2: U -> smem, 4 column taps per output, coalesced stores ----------------------------
+        if (col_ok) {
+#pragma unroll
+            for (int p = 0; p < P; p++)
+                *reinterpret_cast<float4 *>(U + (csub * P + p) * BWU + 4 * xq) = make_float4(u[p][0], u[p][1], u[p][2], u[p][3]);
         }
-        __syncthreads();   // tile[st&1] and U are free again
+        __syncwarp();
+        float *o = orow + (int64_t)c0 * PP;
+        for (int i = lane; i < CPW * PP; i += 32) {
+            const int cs = i / PP, pq = i - cs * PP;
+            const int p = pq / P, q = pq - p * P;
+            const SampleTap t0 = sh.xtab[q * S], t1 = sh.xtab[q * S + 1];
+            const float *ur = U + (cs * P + p) * BWU;
+            float acc = mul(t0.wl, ur[t0.lo]);
+            acc = __fmaf_rn(t0.wh, ur[t0.hi], acc);
+            acc = __fmaf_rn(t1.wl, ur[t1.lo], acc);
+            acc = __fmaf_rn(t1.wh, ur[t1.hi], acc);
+            o[i] = acc;
+        }
+        __syncwarp();
     }
 }
 
 // =====================================================================================================
 // backward
 // =====================================================================================================
-__global__ void __launch_bounds__(kTmaThreads)
-roialign_bwd_tma_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f, const float *__restrict__ rois5,
-                        int P, const float *__restrict__ dout, int32_t *__restrict__ fallback_flag)
-{
-    extern __shared__ __align__(128) unsigned char dsm[];
-    float *tile0 = reinterpret_cast<float *>(dsm);
-    float *tile1 = tile0 + kTileFloats;
-    float *T = tile1 + kTileFloats;                 // [c][p][x]
-    float *G = T + kUFloats;                        // [c][p][q] chunk of dY
-    TmaShared &sh = *reinterpret_cast<TmaShared *>(G + kGFloats);
-    const int r = blockIdx.x, tid = threadIdx.x;
-    const int S = (int)__ldg(f.cfg + 1);
-    const RoiGeom g = roi_geometry(f, rois5 + (int64_t)r * 5, P);
-    const bool aligned = (g.W & 3) == 0;
-    Plan pl{};
-    bool ok = aligned && P <= kMaxP && g.l < 4;
-    if (ok) {
-        build_operators(sh, g, P, S);
-        ok = sh.fits && make_plan(sh, P, kGFloats, pl);
+template <int P>
+struct BwdShared {
+    StreamShared<P> st;
+    float4 row_w[kMaxRowsBwd];         // weights of bins row_p .. row_p+3
+    int row_p[kMaxRowsBwd];            // first contributing bin of each footprint row
+    float ay_dense[16][8];             // rows x bins, only when some row has more than 4 contributing bins
+    int dense;
+};
+
+// d += w * T[PA + K] when that bin exists (compile-time guard keeps the register index static)
+#define MD_ACC(K, WV)                                                          \
+    if (PA + K < P) {                                                          \
+        d0 = __fmaf_rn(WV, T[PA + K < P ? PA + K : 0][0], d0);                 \
+        d1 = __fmaf_rn(WV, T[PA + K < P ? PA + K : 0][1], d1);                 \
+        d2 = __fmaf_rn(WV, T[PA + K < P ? PA + K : 0][2], d2);                 \
+        d3 = __fmaf_rn(WV, T[PA + K < P ? PA + K : 0][3], d3);                 \
     }
-    if (!ok) {
+template <int P, int PA>
+MD_DEVINL void row_from_bins(const float (&T)[P][4], const float4 w, float &d0, float &d1, float &d2, float &d3)
+{
+    d0 = mul(w.x, T[PA][0]); d1 = mul(w.x, T[PA][1]); d2 = mul(w.x, T[PA][2]); d3 = mul(w.x, T[PA][3]);
+    MD_ACC(1, w.y)
+    MD_ACC(2, w.z)
+    MD_ACC(3, w.w)
+}
+#undef MD_ACC
+
+template <int P>
+__global__ void __launch_bounds__(kStThreads, 4)
+roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f, const int tma_mask,
+                           const float *__restrict__ rois5, const float *__restrict__ dout,
+                           int32_t *__restrict__ fallback_flag)
+{
+    static_assert(P == 7, "backward stream kernel is specialised for 7x7");
+    constexpr int S = 2, NS = P * S, PP = P * P;
+    constexpr int kGFloats = 8 * P * 8;                   // CPW(max 8) x P x 8 (q padded to 8)
+    constexpr int kAxFloats = P * 132;                    // Ax dense [q][<=128 + 4]
+    extern __shared__ __align__(128) unsigned char dsm[];
+    float *ring_all = reinterpret_cast<float *>(dsm);
+    float *G_all = ring_all + kStWarps * kBwdRingFloats; // [warp][2][kGFloats]
+    float *AxD = G_all + kStWarps * 2 * kGFloats;        // [q][BWA]
+    BwdShared<P> &bs = *reinterpret_cast<BwdShared<P> *>(AxD + kAxFloats);
+    StreamShared<P> &sh = bs.st;
+
+    const int r = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const RoiGeom g = roi_geometry(f, rois5 + (int64_t)r * 5, P);
+    const int C = f.C;
+    const bool use_tma = (tma_mask >> g.l) & 1;
+    if ((int)__ldg(f.cfg + 1) != S || g.l >= kTmaLevels) {
         if (tid == 0) fallback_flag[r] = 1;
         return;
     }
-    if (tid == 0) fallback_flag[r] = 0;
-    const CUtensorMap *map = &maps.m[g.l * kNumBW + (pl.BW >> 2) - 1];
-    const int PP = P * P, C = f.C;
-    const int nchunks = (C + pl.CC - 1) / pl.CC;
-    const int nstages = pl.ngroups * nchunks;
-    float *tiles[2] = { tile0, tile1 };
-    const int BW = pl.BW;
-
-    for (int st = 0; st < nstages; st++) {
-        const int gi = st / nchunks, ch = st - gi * nchunks;
-        const int p0 = gi * pl.rows, p1 = min(P, p0 + pl.rows), rows = p1 - p0;
-        int a = 1 << 30, b = 0;
-        for (int p = p0; p < p1; p++) if (sh.ye[p] > 0) { a = min(a, sh.ys[p]); b = max(b, sh.ye[p]); }
-        if (b == 0) { a = 0; b = 1; }
-        const int y0 = a, ht = ((b - a) + kBoxRows - 1) / kBoxRows * kBoxRows;
-        const int c0 = ch * pl.CC, cc = min(pl.CC, C - c0);
-        const int ccb = (cc + kBoxCh - 1) / kBoxCh * kBoxCh, ncb = ccb / kBoxCh, nty = ht / kBoxRows;
-        float *tile = tiles[st & 1];
-        // ---- load the dY chunk (contiguous per channel) ------------------------------------------------
-        const float *gsrc = dout + ((int64_t)r * C + c0) * PP + p0 * P;
-        for (int i = tid; i < cc * rows * P; i += kTmaThreads) {
-            const int c = i / (rows * P), rem = i - c * (rows * P);
-            G[i] = __ldg(gsrc + (int64_t)c * PP + rem);
+    build_tables<P>(sh, g);
+    if (tid == 0) bs.dense = 0;
+    __syncthreads();
+    const int BW = sh.bw, h_fp = sh.h_fp;
+    if (BW > kMaxBW || h_fp > kMaxRowsBwd) {
+        if (tid == 0) fallback_flag[r] = 1;
+        return;
+    }
+    if (!sh.any_x || !sh.any_y) {                                   // no sample in range -> no gradient
+        if (tid == 0) fallback_flag[r] = 0;
+        return;
+    }
+    const int BWA = BW + 4;
+    // ---- dense Ax[q][x] (x relative to x_lo) and the per-row bin lists --------------------------------
+    for (int i = tid; i < P * BWA; i += kStThreads) AxD[i] = 0.0f;
+    __syncthreads();
+    if (tid < P) {
+        const SampleTap t0 = sh.xtab[tid * S], t1 = sh.xtab[tid * S + 1];
+        float *a = AxD + tid * BWA;
+        a[t0.lo] += t0.wl; a[t0.hi] += t0.wh; a[t1.lo] += t1.wl; a[t1.hi] += t1.wh;
+    }
+    for (int y = tid; y < h_fp; y += kStThreads) {
+        float w[P];
+#pragma unroll
+        for (int p = 0; p < P; p++) w[p] = 0.0f;
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const SampleTap t = sh.ytab[s];
+            if (t.lo == y) w[s / S] += t.wl;
+            if (t.hi == y) w[s / S] += t.wh;
         }
-        __syncthreads();
-        // ---- T[c][p][x] = sum_q G[c][p][q] * Ax[q][x] ----------------------------------------------------
-        for (int i = tid; i < cc * rows * BW; i += kTmaThreads) {
-            const int c = i / (rows * BW), rem = i - c * (rows * BW);
-            const int p = rem / BW, x = rem - p * BW;
-            float acc = 0.0f;
-            const float *gp = G + (c * rows + p) * P;
-            for (int q = 0; q < P; q++)
-                if (x >= sh.xs[q] && x < sh.xe[q]) acc = __fmaf_rn(gp[q], sh.Ax[q][x], acc);
-            T[i] = acc;
+        int pa = P, pz = -1;
+#pragma unroll
+        for (int p = P - 1; p >= 0; p--) if (w[p] != 0.0f) pa = p;
+#pragma unroll
+        for (int p = 0; p < P; p++) if (w[p] != 0.0f) pz = p;
+        if (pz < 0) pa = pz = 0;                                     // row without contribution
+        float4 ww = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            if (p == pa) ww.x = w[p];
+            if (p == pa + 1) ww.y = w[p];
+            if (p == pa + 2) ww.z = w[p];
+            if (p == pa + 3) ww.w = w[p];
         }
-        // the TMA reduce that read this tile buffer two stages ago must have finished reading it
-        if (tid == 0) bulk_wait_read<1>();
-        __syncthreads();
-        // ---- dTile[c][y][x] = sum_p Ay[p][y] * T[c][p][x]  (every tile element written, zeros included) --
-        for (int i = tid; i < ccb * ht * BW; i += kTmaThreads) {
-            const int c = i / (ht * BW), rem = i - c * (ht * BW);
-            const int yy = rem / BW, x = rem - yy * BW;
-            float acc = 0.0f;
-            if (c < cc) {
-                const int y = yy + y0;
-                for (int p = p0; p < p1; p++)
-                    if (y >= sh.ys[p] && y < sh.ye[p]) acc = __fmaf_rn(sh.Ay[p][y], T[(c * rows + (p - p0)) * BW + x], acc);
-            }
-            const int cb = c / kBoxCh, ci = c - cb * kBoxCh, ty = yy / kBoxRows, yi = yy - ty * kBoxRows;
-            tile[((ty * ncb + cb) * kBoxCh + ci) * (kBoxRows * BW) + yi * BW + x] = acc;
-        }
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            for (int ty = 0; ty < nty; ty++)
-                for (int cb = 0; cb < ncb; cb++) {
-                    // channels beyond C would fold zeros into the next image: skip boxes that start past C
-                    if (c0 + cb * kBoxCh >= C) continue;
-                    tma_reduce_add_3d(map, sh.x_lo, sh.y_lo + y0 + ty * kBoxRows, g.b * C + c0 + cb * kBoxCh,
-                                      tile + (ty * ncb + cb) * (BW * kBoxRows * kBoxCh));
-                }
-            bulk_commit();
+        bs.row_p[y] = pa;
+        bs.row_w[y] = ww;
+        if (pz - pa > 3) bs.dense = 1;                               // benign race: every writer stores 1
+        if (y < 16) {
+#pragma unroll
+            for (int p = 0; p < 8; p++) bs.ay_dense[y][p] = p < P ? w[p] : 0.0f;
         }
     }
-    if (tid == 0) bulk_wait_read<0>();
     __syncthreads();
+    const bool dense = bs.dense != 0;
+    if (tid == 0) fallback_flag[r] = (dense && h_fp > 16) ? 1 : 0;
+    if (dense && h_fp > 16) return;                                   // cannot happen for bins < 1 row; be safe
+
+    const int LPC = lanes_per_channel(BW), CPW = 32 / LPC;
+    const int lshift = LPC == 4 ? 2 : (LPC == 8 ? 3 : (LPC == 16 ? 4 : 5));
+    const int csub = lane >> lshift, xq = lane & (LPC - 1);
+    const bool col_ok = 4 * xq < BW;
+    const int x_lo = sh.x_lo, y_lo = sh.y_lo;
+    const int nblk = (h_fp + 3) >> 2;
+    const int BLK = CPW * 4 * BW, SLOT = (BLK + 31) & ~31;
+    const int ngroups = C / CPW;
+    const int ng_w = (ngroups - warp + kStWarps - 1) / kStWarps;
+    float *ring = ring_all + warp * kBwdRingFloats;
+    float *Gs = G_all + warp * 2 * kGFloats;
+    const CUtensorMap *map = &maps.m[g.l * kNumBW + (BW >> 2) - 1];
+    const int H = g.H, W = g.W;
+    float *dplane = f.feat[g.l] + (int64_t)g.b * C * H * W;
+    const float *grow = dout + (int64_t)r * C * PP;
+
+    float ax[P][4];
+#pragma unroll
+    for (int q = 0; q < P; q++) {
+        const float4 v = col_ok ? *reinterpret_cast<const float4 *>(AxD + q * BWA + 4 * xq) : make_float4(0, 0, 0, 0);
+        ax[q][0] = v.x; ax[q][1] = v.y; ax[q][2] = v.z; ax[q][3] = v.w;
+    }
+
+    auto stage_g = [&](int gi) {                          // dY of group gi -> Gs[gi & 1][cs][p][8]
+        const int c0 = (warp + kStWarps * gi) * CPW;
+        float *dst = Gs + (gi & 1) * kGFloats;
+        const float *src = grow + (int64_t)c0 * PP;
+        for (int e = lane; e < CPW * PP; e += 32) {
+            const int cs = e / PP, pq = e - cs * PP;
+            const int p = pq / P, q = pq - p * P;
+            cp_async4(dst + (cs * P + p) * 8 + q, src + e);
+        }
+        cp_async_commit_group();
+    };
+
+    int slot = 0;
+    if (ng_w > 0) stage_g(0);
+    for (int gi = 0; gi < ng_w; gi++) {
+        const int c0 = (warp + kStWarps * gi) * CPW;
+        if (gi + 1 < ng_w) { stage_g(gi + 1); cp_async_wait_group<1>(); } else { cp_async_wait_group<0>(); }
+        __syncwarp();
+        // ---- step 1: T[p][4 cols] = sum_q dY[p][q] * Ax[q][cols] -----------------------------------------
+        float T[P][4];
+        {
+            const float *gs = Gs + (gi & 1) * kGFloats + csub * P * 8;
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const float4 g0 = *reinterpret_cast<const float4 *>(gs + p * 8);
+                const float4 g1 = *reinterpret_cast<const float4 *>(gs + p * 8 + 4);
+                const float gq[7] = { g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z };
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    float acc = mul(gq[0], ax[0][k]);
+#pragma unroll
+                    for (int q = 1; q < P; q++) acc = __fmaf_rn(gq[q], ax[q][k], acc);
+                    T[p][k] = acc;
+                }
+            }
+        }
+        // ---- step 2: D[row][4 cols] = sum_p Ay[p][row] * T[p], one TMA reduce-add per 4-row block ---------
+        for (int j = 0; j < nblk; j++) {
+            float *dst = ring + slot * SLOT;
+            if (use_tma) {
+                if (lane == 0) bulk_wait_read<kBwdSlots - 1>();      // the reduce that last read this slot is done
+                __syncwarp();
+            }
+#pragma unroll
+            for (int rr = 0; rr < 4; rr++) {
+                const int y = 4 * j + rr;
+                float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+                if (y < h_fp) {
+                    if (!dense) {
+                        const int pa = bs.row_p[y];
+                        const float4 w = bs.row_w[y];
+                        switch (pa) {
+                            case 0: row_from_bins<P, 0>(T, w, d0, d1, d2, d3); break;
+                            case 1: row_from_bins<P, 1>(T, w, d0, d1, d2, d3); break;
+                            case 2: row_from_bins<P, 2>(T, w, d0, d1, d2, d3); break;
+                            case 3: row_from_bins<P, 3>(T, w, d0, d1, d2, d3); break;
+                            case 4: row_from_bins<P, 4>(T, w, d0, d1, d2, d3); break;
+                            case 5: row_from_bins<P, 5>(T, w, d0, d1, d2, d3); break;
+                            default: row_from_bins<P, 6>(T, w, d0, d1, d2, d3); break;
+                        }
+                    } else {
+                        const float4 w0 = *reinterpret_cast<const float4 *>(&bs.ay_dense[y][0]);
+                        const float4 w1 = *reinterpret_cast<const float4 *>(&bs.ay_dense[y][4]);
+                        const float wp[7] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z };
+#pragma unroll
+                        for (int p = 0; p < P; p++) {
+                            d0 = __fmaf_rn(wp[p], T[p][0], d0); d1 = __fmaf_rn(wp[p], T[p][1], d1);
+                            d2 = __fmaf_rn(wp[p], T[p][2], d2); d3 = __fmaf_rn(wp[p], T[p][3], d3);
+                        }
+                    }
+                }
+                if (use_tma) {
+                    if (col_ok) *reinterpret_cast<float4 *>(dst + (csub * 4 + rr) * BW + 4 * xq) = make_float4(d0, d1, d2, d3);
+                } else if (col_ok && y < h_fp && y_lo + y < H) {
+                    const int xa = x_lo + 4 * xq;
+                    float *dp = dplane + ((int64_t)(c0 + csub) * H + (y_lo + y)) * W + xa;
+                    if (xa < W && d0 != 0.0f) atomicAdd(dp, d0);
+                    if (xa + 1 < W && d1 != 0.0f) atomicAdd(dp + 1, d1);
+                    if (xa + 2 < W && d2 != 0.0f) atomicAdd(dp + 2, d2);
+                    if (xa + 3 < W && d3 != 0.0f) atomicAdd(dp + 3, d3);
+                }
+            }
+            if (use_tma) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_reduce_add_3d(map, x_lo, y_lo + 4 * j, g.b * C + c0, dst);
+                    bulk_commit();
+                }
+                if (++slot == kBwdSlots) slot = 0;
+            }
+        }
+        __syncwarp();                                     // Gs[gi & 1] may be overwritten by stage_g(gi + 2)
+    }
+    if (use_tma && lane == 0) bulk_wait_all<0>();
 }
 
 // =====================================================================================================
-// host: tensor maps (one per (level, box width)); cached per (pointer, dims)
+// host: tensor maps (one per (level, box width)); small LRU keyed by (pointers, dims)
 // =====================================================================================================
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -393,74 +563,109 @@ static EncodeTiledFn get_encode()
     return fn;
 }
 
-struct MapCache { void *ptr[4]; int H[4], W[4], BC; int L; TmaMaps maps; bool valid; };
-static MapCache g_cache[2];          // [0] forward (features), [1] backward (gradients)
+struct MapCache {
+    void *ptr[kTmaLevels]; int H[kTmaLevels], W[kTmaLevels], BC, L, mask; TmaMaps maps; bool valid; unsigned long long stamp;
+};
+constexpr int kCacheEntries = 4;
+static MapCache g_cache[kCacheEntries];
+static unsigned long long g_stamp = 0;
 static std::mutex g_cache_mutex;
 
-// returns false when no level is TMA-eligible or the driver entry point is missing
-static bool build_maps(const FeatSet &fs, int which, TmaMaps *out)
+// Returns the TMA-eligible level mask (0 when the driver entry point is missing: cp.async path for all).
+static int build_maps(const FeatSet &fs, TmaMaps *out)
 {
     EncodeTiledFn enc = get_encode();
-    if (!enc || fs.L > 4) return false;
     std::lock_guard<std::mutex> lock(g_cache_mutex);
-    MapCache &c = g_cache[which];
-    bool same = c.valid && c.L == fs.L && c.BC == fs.B * fs.C;
-    for (int l = 0; same && l < fs.L; l++) same = c.ptr[l] == fs.feat[l] && c.H[l] == fs.H[l] && c.W[l] == fs.W[l];
-    if (!same) {
+    const int L = fs.L < kTmaLevels ? fs.L : kTmaLevels;
+    MapCache *hit = nullptr, *victim = &g_cache[0];
+    for (int e = 0; e < kCacheEntries; e++) {
+        MapCache &c = g_cache[e];
+        bool same = c.valid && c.L == L && c.BC == fs.B * fs.C;
+        for (int l = 0; same && l < L; l++) same = c.ptr[l] == fs.feat[l] && c.H[l] == fs.H[l] && c.W[l] == fs.W[l];
+        if (same) { hit = &c; break; }
+        if (!c.valid) { if (victim->valid) victim = &c; }
+        else if (victim->valid && c.stamp < victim->stamp) victim = &c;
+    }
+    if (!hit) {
+        MapCache &c = *victim;
         std::memset(&c.maps, 0, sizeof(c.maps));
-        for (int l = 0; l < fs.L; l++) {
+        c.mask = 0;
+        for (int l = 0; l < L; l++) {
             c.ptr[l] = fs.feat[l]; c.H[l] = fs.H[l]; c.W[l] = fs.W[l];
-            if ((fs.W[l] & 3) || (reinterpret_cast<uintptr_t>(fs.feat[l]) & 15)) continue;   // gather path for this level
-            for (int k = 0; k < kNumBW; k++) {
+            if (!enc || (fs.W[l] & 3) || (reinterpret_cast<uintptr_t>(fs.feat[l]) & 15)) continue;   // cp.async path
+            bool ok = true;
+            for (int k = 0; k < kNumBW && ok; k++) {
+                const int bw = 4 * (k + 1);
                 const cuuint64_t dims[3] = { (cuuint64_t)fs.W[l], (cuuint64_t)fs.H[l], (cuuint64_t)fs.B * fs.C };
                 const cuuint64_t strides[2] = { (cuuint64_t)fs.W[l] * 4, (cuuint64_t)fs.W[l] * fs.H[l] * 4 };
-                const cuuint32_t box[3] = { (cuuint32_t)(4 * (k + 1)), kBoxRows, kBoxCh };
+                const cuuint32_t box[3] = { (cuuint32_t)bw, 4u, (cuuint32_t)(32 / lanes_per_channel(bw)) };
                 const cuuint32_t estr[3] = { 1, 1, 1 };
-                CUresult rc = enc(&c.maps.m[l * kNumBW + k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, fs.feat[l], dims, strides,
-                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                if (rc != CUDA_SUCCESS) { c.valid = false; return false; }
+                ok = enc(&c.maps.m[l * kNumBW + k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, fs.feat[l], dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
             }
+            if (ok) c.mask |= 1 << l;
         }
-        c.L = fs.L; c.BC = fs.B * fs.C; c.valid = true;
+        c.L = L; c.BC = fs.B * fs.C; c.valid = true;
+        hit = &c;
     }
-    *out = c.maps;
-    return true;
+    hit->stamp = ++g_stamp;
+    *out = hit->maps;
+    return hit->mask;
 }
 
-static size_t fwd_smem() { return (size_t)(2 * kTileFloats + kUFloats) * sizeof(float) + sizeof(TmaShared) + 128; }
-static size_t bwd_smem() { return (size_t)(2 * kTileFloats + kUFloats + kGFloats) * sizeof(float) + sizeof(TmaShared) + 128; }
+template <int P> static size_t fwd_smem()
+{
+    return (size_t)(kStWarps * kRingFloats + kStWarps * P * 160) * sizeof(float) + sizeof(StreamShared<P>) + 128;
+}
+template <int P> static size_t bwd_smem()
+{
+    return (size_t)(kStWarps * kBwdRingFloats + kStWarps * 2 * 8 * P * 8 + P * 132) * sizeof(float) + sizeof(BwdShared<P>) + 128;
+}
+
+template <int P>
+static cudaError_t launch_fwd(const TmaMaps &maps, const RoiFeat &f, int mask, const float *rois5, int R, float *out,
+                              int32_t *flag, cudaStream_t s)
+{
+    static bool configured = false;
+    auto kern = roialign_fwd_stream_kernel<P>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<P>());
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<R, kStThreads, fwd_smem<P>(), s>>>(maps, f, mask, rois5, out, flag);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_roialign_fwd_tma(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P,
                                     float *out, int32_t *fallback_flag, cudaStream_t s, bool *launched)
 {
     *launched = false;
+    if ((fs.C & 7) || (P != 7 && P != 14)) return cudaSuccess;        // gather path
     TmaMaps maps;
-    if (!build_maps(fs, 0, &maps)) return cudaSuccess;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(roialign_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem());
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    roialign_fwd_tma_kernel<<<R, kTmaThreads, fwd_smem(), s>>>(maps, f, rois5, P, out, fallback_flag);
-    *launched = true;
-    return cudaGetLastError();
+    const int mask = build_maps(fs, &maps);
+    cudaError_t e = P == 7 ? launch_fwd<7>(maps, f, mask, rois5, R, out, fallback_flag, s)
+                           : launch_fwd<14>(maps, f, mask, rois5, R, out, fallback_flag, s);
+    *launched = e == cudaSuccess;
+    return e;
 }
 
 cudaError_t launch_roialign_bwd_tma(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P,
                                     const float *dout, int32_t *fallback_flag, cudaStream_t s, bool *launched)
 {
     *launched = false;
+    if ((fs.C & 7) || P != 7) return cudaSuccess;
     TmaMaps maps;
-    if (!build_maps(fs, 1, &maps)) return cudaSuccess;
+    const int mask = build_maps(fs, &maps);
     static bool configured = false;
+    auto kern = roialign_bwd_stream_kernel<7>;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(roialign_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem());
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<7>());
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    roialign_bwd_tma_kernel<<<R, kTmaThreads, bwd_smem(), s>>>(maps, f, rois5, P, dout, fallback_flag);
+    kern<<<R, kStThreads, bwd_smem<7>(), s>>>(maps, f, mask, rois5, dout, fallback_flag);
     *launched = true;
     return cudaGetLastError();
 }
