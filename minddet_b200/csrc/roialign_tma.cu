@@ -28,6 +28,7 @@
 // rtol 1e-5 (north_star) + atol 1e-6 for cancellation; tests/test_gpu_parity.py states it.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -114,7 +115,7 @@ MD_DEVINL bool sample_1d(float v, int extent, int &lo, int &hi, float &wl, float
 template <int P>
 struct StreamShared {
     unsigned long long full[kStWarps][kMaxSlots];
-    SampleTap ytab[2 * P], xtab[2 * P];
+    SampleTap ytab[2 * P], xtab[2 * P], yoff[2 * P];
     int x_lo, y_lo, bw, h_fp, any_x, any_y;
 };
 
@@ -160,24 +161,44 @@ MD_DEVINL void build_tables(StreamShared<P> &sh, const RoiGeom &g)
 // =====================================================================================================
 // forward
 // =====================================================================================================
+// CTA -> (RoI, channel chunk).  Blocks are ordered (segment of `seg` consecutive RoIs, chunk, RoI in segment)
+// so that the CTAs resident at any time read the SAME channel planes of (normally) one image: every
+// feature byte is then fetched from HBM once and re-used out of L2 by all RoIs that overlap it.
+struct WorkItem { int r, chunk; };
+MD_DEVINL WorkItem work_item(int bid, int R, int seg, int nchunk)
+{
+    const int per_seg = seg * nchunk;
+    const int sidx = bid / per_seg, base = sidx * seg;
+    const int seg_len = min(seg, R - base);
+    const int rem = bid - sidx * per_seg;
+    WorkItem w;
+    w.chunk = rem / seg_len;
+    w.r = base + (rem - w.chunk * seg_len);
+    return w;
+}
+
 template <int P>
 __global__ void __launch_bounds__(kStThreads, 3)
 roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f, const int tma_mask,
-                           const float *__restrict__ rois5, float *__restrict__ out, int32_t *__restrict__ fallback_flag)
+                           const float *__restrict__ rois5, const int R, const int seg, const int nchunk,
+                           float *__restrict__ out, int32_t *__restrict__ fallback_flag)
 {
     constexpr int S = 2, NS = P * S, PP = P * P;
     constexpr int kUFloats = P * 160;                     // max over LPC of CPW * P * (4*LPC + 4)
+    constexpr int ROUNDS = (PP + 31) / 32;
     extern __shared__ __align__(128) unsigned char dsm[];
     float *ring_all = reinterpret_cast<float *>(dsm);
     float *U_all = ring_all + kStWarps * kRingFloats;
     StreamShared<P> &sh = *reinterpret_cast<StreamShared<P> *>(U_all + kStWarps * kUFloats);
 
-    const int r = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const WorkItem wi = work_item(blockIdx.x, R, seg, nchunk);
+    const int r = wi.r, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const RoiGeom g = roi_geometry(f, rois5 + (int64_t)r * 5, P);
-    const int C = f.C;
+    const int C = f.C, CH = C / nchunk, cbase = wi.chunk * CH;
     const bool use_tma = (tma_mask >> g.l) & 1;
+    const bool flag_writer = tid == 0 && wi.chunk == 0;
     if ((int)__ldg(f.cfg + 1) != S || g.l >= kTmaLevels) {        // uniform: gather path handles this RoI
-        if (tid == 0) fallback_flag[r] = 1;
+        if (flag_writer) fallback_flag[r] = 1;
         return;
     }
     if (lane == 0) {
@@ -188,13 +209,13 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
     __syncthreads();
     const int BW = sh.bw;
     if (BW > kMaxBW) {
-        if (tid == 0) fallback_flag[r] = 1;
+        if (flag_writer) fallback_flag[r] = 1;
         return;
     }
-    if (tid == 0) fallback_flag[r] = 0;
-    float *orow = out + (int64_t)r * C * PP;
+    if (flag_writer) fallback_flag[r] = 0;
+    float *orow = out + ((int64_t)r * C + cbase) * PP;
     if (!sh.any_x || !sh.any_y) {                                   // every sample is out of range -> zeros
-        for (int i = tid; i < C * PP; i += kStThreads) orow[i] = 0.0f;
+        for (int i = tid; i < CH * PP; i += kStThreads) orow[i] = 0.0f;
         return;
     }
     const int LPC = lanes_per_channel(BW), CPW = 32 / LPC, BWU = 4 * LPC + 4;
@@ -204,47 +225,145 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
     const int x_lo = sh.x_lo, y_lo = sh.y_lo, h_fp = sh.h_fp;
     const int nblk = (h_fp + 3) >> 2;
     const int BLK = CPW * 4 * BW, SLOT = (BLK + 31) & ~31;
-    const int NB = min(kMaxSlots, kRingFloats / SLOT);
-    const int ngroups = C / CPW;                                      // host guarantees C % 8 == 0
+    const int ngroups = CH / CPW;                                     // host guarantees CH % 8 == 0
     const int ng_w = (ngroups - warp + kStWarps - 1) / kStWarps;      // groups warp, warp+4, ...
-    const int total = ng_w * nblk;
     float *ring = ring_all + warp * kRingFloats;
     float *U = U_all + warp * kUFloats;
     unsigned long long *full = sh.full[warp];
     const CUtensorMap *map = &maps.m[g.l * kNumBW + (BW >> 2) - 1];
     const int H = g.H, W = g.W;
-    const float *fplane = f.feat[g.l] + (int64_t)g.b * C * H * W;
+    const float *fplane = f.feat[g.l] + ((int64_t)g.b * C + cbase) * H * W;
+    const int zbase = g.b * C + cbase;
+    const int lane_off = csub * 4 * BW + 4 * xq;          // this lane's float offset inside a row block
 
-    // ---- producer state: block `iss` = (group iss_g, row block iss_j) goes to slot iss_slot --------------
-    int iss = 0, iss_g = 0, iss_j = 0, iss_slot = 0;
-    auto issue_one = [&]() {
-        __syncwarp();                                   // every lane is done reading the slot's previous block
-        const int c0 = (warp + kStWarps * iss_g) * CPW;
-        float *dst = ring + iss_slot * SLOT;
+    // one row block (BW x 4 rows x CPW channels) of channel group `grp` -> dst, completion on `bar`
+    auto load_block = [&](float *dst, int grp, int j, unsigned long long *bar) {
+        const int c0 = (warp + kStWarps * grp) * CPW;
         if (use_tma) {
-            if (lane == 0) {
-                mbar_expect_tx(&full[iss_slot], (uint32_t)BLK * 4u);
-                tma_load_3d(dst, map, x_lo, y_lo + 4 * iss_j, g.b * C + c0, &full[iss_slot]);
-            }
+            if (lane == 0) tma_load_3d(dst, map, x_lo, y_lo + 4 * j, zbase + c0, bar);
         } else {
-            // elements outside the map are never used with a non-zero weight (rows/cols clamp), so they stay unwritten
+            // elements outside the map are never used with a non-zero weight (rows/cols clamp): left unwritten
             for (int e = lane; e < BLK; e += 32) {
                 const int c = e / (4 * BW), rem = e - c * (4 * BW);
                 const int rr = rem / BW, xx = rem - rr * BW;
-                const int y = y_lo + 4 * iss_j + rr, x = x_lo + xx;
+                const int y = y_lo + 4 * j + rr, x = x_lo + xx;
                 if (y < H && x < W) cp_async4(dst + e, fplane + ((int64_t)(c0 + c) * H + y) * W + x);
             }
-            cp_async_mbar_arrive(&full[iss_slot]);
         }
+    };
+
+    // ---- step 2 taps of this lane's outputs pq = lane + 32k (registers when there are at most 2 rounds) ----
+    int ta[ROUNDS <= 2 ? ROUNDS : 1][4];
+    float tw[ROUNDS <= 2 ? ROUNDS : 1][4];
+    if (ROUNDS <= 2) {
+#pragma unroll
+        for (int k = 0; k < (ROUNDS <= 2 ? ROUNDS : 1); k++) {
+            const int pq = min(lane + 32 * k, PP - 1), p = pq / P, q = pq - p * P;
+            const SampleTap t0 = sh.xtab[q * S], t1 = sh.xtab[q * S + 1];
+            ta[k][0] = p * BWU + t0.lo; ta[k][1] = p * BWU + t0.hi; ta[k][2] = p * BWU + t1.lo; ta[k][3] = p * BWU + t1.hi;
+            tw[k][0] = t0.wl; tw[k][1] = t0.wh; tw[k][2] = t1.wl; tw[k][3] = t1.wh;
+        }
+    }
+    auto step2 = [&](const float (&u)[P][4], int grp) {
+        if (col_ok) {
+#pragma unroll
+            for (int p = 0; p < P; p++)
+                *reinterpret_cast<float4 *>(U + (csub * P + p) * BWU + 4 * xq) = make_float4(u[p][0], u[p][1], u[p][2], u[p][3]);
+        }
+        __syncwarp();
+        float *o = orow + (int64_t)(warp + kStWarps * grp) * CPW * PP;
+        if (ROUNDS <= 2) {
+            const float *uc = U;
+            for (int cs = 0; cs < CPW; cs++, uc += P * BWU, o += PP) {
+#pragma unroll
+                for (int k = 0; k < (ROUNDS <= 2 ? ROUNDS : 1); k++) {
+                    float acc = mul(tw[k][0], uc[ta[k][0]]);
+                    acc = __fmaf_rn(tw[k][1], uc[ta[k][1]], acc);
+                    acc = __fmaf_rn(tw[k][2], uc[ta[k][2]], acc);
+                    acc = __fmaf_rn(tw[k][3], uc[ta[k][3]], acc);
+                    if (lane + 32 * k < PP) o[lane + 32 * k] = acc;
+                }
+            }
+        } else {
+            for (int i = lane; i < CPW * PP; i += 32) {
+                const int cs = i / PP, pq = i - cs * PP;
+                const int p = pq / P, q = pq - p * P;
+                const SampleTap t0 = sh.xtab[q * S], t1 = sh.xtab[q * S + 1];
+                const float *ur = U + (cs * P + p) * BWU;
+                float acc = mul(t0.wl, ur[t0.lo]);
+                acc = __fmaf_rn(t0.wh, ur[t0.hi], acc);
+                acc = __fmaf_rn(t1.wl, ur[t1.lo], acc);
+                acc = __fmaf_rn(t1.wh, ur[t1.hi], acc);
+                o[i] = acc;
+            }
+        }
+        __syncwarp();
+    };
+
+    const int TILE = nblk * SLOT;
+    if (2 * TILE <= kRingFloats) {
+        // =============== tile mode: the whole footprint of a channel group is one pipeline stage ===============
+        const int NST = min(4, kRingFloats / TILE);
+        // per-sample float offsets inside a tile (row block, row in block); same for every group
+        SampleTap *yoff = sh.yoff;
+        if (warp == 0 && lane < NS) {
+            const SampleTap t = sh.ytab[lane];
+            SampleTap o;
+            o.lo = (t.lo >> 2) * SLOT + (t.lo & 3) * BW; o.hi = (t.hi >> 2) * SLOT + (t.hi & 3) * BW; o.wl = t.wl; o.wh = t.wh;
+            yoff[lane] = o;
+        }
+        __syncthreads();
+        auto issue_tile = [&](int grp) {
+            const int st = grp % NST;
+            if (use_tma && lane == 0) mbar_expect_tx(&full[st], (uint32_t)(nblk * BLK) * 4u);
+            for (int j = 0; j < nblk; j++) load_block(ring + st * TILE + j * SLOT, grp, j, &full[st]);
+            if (!use_tma) cp_async_mbar_arrive(&full[st]);
+        };
+        for (int gi = 0; gi < NST && gi < ng_w; gi++) issue_tile(gi);
+        int st = 0;
+        uint32_t par = 0;
+        for (int gi = 0; gi < ng_w; gi++) {
+            mbar_wait(&full[st], par);
+            const float *tile = ring + st * TILE + lane_off;
+            float u[P][4];
+#pragma unroll
+            for (int p = 0; p < P; p++) u[p][0] = u[p][1] = u[p][2] = u[p][3] = 0.0f;
+            if (col_ok) {
+#pragma unroll
+                for (int s = 0; s < NS; s++) {
+                    const SampleTap t = yoff[s];
+                    const float4 a = *reinterpret_cast<const float4 *>(tile + t.lo);
+                    const float4 b = *reinterpret_cast<const float4 *>(tile + t.hi);
+                    u[s / S][0] = __fmaf_rn(t.wl, a.x, __fmaf_rn(t.wh, b.x, u[s / S][0]));
+                    u[s / S][1] = __fmaf_rn(t.wl, a.y, __fmaf_rn(t.wh, b.y, u[s / S][1]));
+                    u[s / S][2] = __fmaf_rn(t.wl, a.z, __fmaf_rn(t.wh, b.z, u[s / S][2]));
+                    u[s / S][3] = __fmaf_rn(t.wl, a.w, __fmaf_rn(t.wh, b.w, u[s / S][3]));
+                }
+            }
+            __syncwarp();                                   // every lane is done reading this stage
+            if (gi + NST < ng_w) issue_tile(gi + NST);
+            step2(u, gi);
+            if (++st == NST) { st = 0; par ^= 1u; }
+        }
+        return;
+    }
+
+    // =============== stream mode: row blocks slide through the ring (any footprint height) ===============
+    const int NB = min(kMaxSlots, kRingFloats / SLOT);
+    const int total = ng_w * nblk;
+    int iss = 0, iss_g = 0, iss_j = 0, iss_slot = 0;
+    auto issue_one = [&]() {
+        __syncwarp();                                   // every lane is done reading the slot's previous block
+        if (use_tma && lane == 0) mbar_expect_tx(&full[iss_slot], (uint32_t)BLK * 4u);
+        load_block(ring + iss_slot * SLOT, iss_g, iss_j, &full[iss_slot]);
+        if (!use_tma) cp_async_mbar_arrive(&full[iss_slot]);
         iss++;
         if (++iss_j == nblk) { iss_j = 0; iss_g++; }
         if (++iss_slot == NB) iss_slot = 0;
     };
-    // ---- consumer state -------------------------------------------------------------------------------
     int wt = 0, wt_slot = 0;
     uint32_t wt_par = 0;
     int grp_slot = 0;                                   // slot of the current group's block 0
-
     // Make every block <= need visible.  A slot may be refilled only when its previous block has been both
     // waited for (its mbarrier phase observed) and consumed (every block below `freed` is dead).
     auto advance = [&](int need, int freed) {
@@ -257,55 +376,41 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
             if (++wt_slot == NB) { wt_slot = 0; wt_par ^= 1u; }
         }
     };
-
     for (int gi = 0; gi < ng_w; gi++) {
         const int gbase = gi * nblk;
-        const int c0 = (warp + kStWarps * gi) * CPW;
         float u[P][4];
 #pragma unroll
         for (int p = 0; p < P; p++) u[p][0] = u[p][1] = u[p][2] = u[p][3] = 0.0f;
         int cur_blk = 0, cur_slot = grp_slot;
+#pragma unroll 1
+        for (int p = 0; p < P; p++) {
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll
-        for (int s = 0; s < NS; s++) {
-            const SampleTap t = sh.ytab[s];
-            const int blo = t.lo >> 2, bhi = t.hi >> 2;
-            while (cur_blk < blo) { cur_blk++; if (++cur_slot == NB) cur_slot = 0; }
-            advance(gbase + bhi, gbase + blo);
-            int hi_slot = cur_slot;
-            if (bhi != blo) { hi_slot = cur_slot + 1; if (hi_slot == NB) hi_slot = 0; }
-            if (col_ok) {
-                const float4 a = *reinterpret_cast<const float4 *>(ring + cur_slot * SLOT + (csub * 4 + (t.lo & 3)) * BW + 4 * xq);
-                const float4 b = *reinterpret_cast<const float4 *>(ring + hi_slot * SLOT + (csub * 4 + (t.hi & 3)) * BW + 4 * xq);
-                u[s / S][0] = __fmaf_rn(t.wl, a.x, __fmaf_rn(t.wh, b.x, u[s / S][0]));
-                u[s / S][1] = __fmaf_rn(t.wl, a.y, __fmaf_rn(t.wh, b.y, u[s / S][1]));
-                u[s / S][2] = __fmaf_rn(t.wl, a.z, __fmaf_rn(t.wh, b.z, u[s / S][2]));
-                u[s / S][3] = __fmaf_rn(t.wl, a.w, __fmaf_rn(t.wh, b.w, u[s / S][3]));
+            for (int i = 0; i < S; i++) {
+                const SampleTap t = sh.ytab[p * S + i];
+                const int blo = t.lo >> 2, bhi = t.hi >> 2;
+                while (cur_blk < blo) { cur_blk++; if (++cur_slot == NB) cur_slot = 0; }
+                advance(gbase + bhi, gbase + blo);
+                int hi_slot = cur_slot;
+                if (bhi != blo) { hi_slot = cur_slot + 1; if (hi_slot == NB) hi_slot = 0; }
+                if (col_ok) {
+                    const float4 a = *reinterpret_cast<const float4 *>(ring + cur_slot * SLOT + (t.lo & 3) * BW + lane_off);
+                    const float4 b = *reinterpret_cast<const float4 *>(ring + hi_slot * SLOT + (t.hi & 3) * BW + lane_off);
+                    a0 = __fmaf_rn(t.wl, a.x, __fmaf_rn(t.wh, b.x, a0));
+                    a1 = __fmaf_rn(t.wl, a.y, __fmaf_rn(t.wh, b.y, a1));
+                    a2 = __fmaf_rn(t.wl, a.z, __fmaf_rn(t.wh, b.z, a2));
+                    a3 = __fmaf_rn(t.wl, a.w, __fmaf_rn(t.wh, b.w, a3));
+                }
             }
+            // static register index without unrolling the bookkeeping P times
+#pragma unroll
+            for (int pp = 0; pp < P; pp++)
+                if (pp == p) { u[pp][0] = a0; u[pp][1] = a1; u[pp][2] = a2; u[pp][3] = a3; }
         }
-        // the whole group is consumed: release its blocks, keep the producer ahead
         grp_slot += nblk;
         while (grp_slot >= NB) grp_slot -= NB;
-        advance(gbase + nblk - 1, gbase + nblk);
-        // ---- step 2: U -> smem, 4 column taps per output, coalesced stores ----------------------------
-        if (col_ok) {
-#pragma unroll
-            for (int p = 0; p < P; p++)
-                *reinterpret_cast<float4 *>(U + (csub * P + p) * BWU + 4 * xq) = make_float4(u[p][0], u[p][1], u[p][2], u[p][3]);
-        }
-        __syncwarp();
-        float *o = orow + (int64_t)c0 * PP;
-        for (int i = lane; i < CPW * PP; i += 32) {
-            const int cs = i / PP, pq = i - cs * PP;
-            const int p = pq / P, q = pq - p * P;
-            const SampleTap t0 = sh.xtab[q * S], t1 = sh.xtab[q * S + 1];
-            const float *ur = U + (cs * P + p) * BWU;
-            float acc = mul(t0.wl, ur[t0.lo]);
-            acc = __fmaf_rn(t0.wh, ur[t0.hi], acc);
-            acc = __fmaf_rn(t1.wl, ur[t1.lo], acc);
-            acc = __fmaf_rn(t1.wh, ur[t1.hi], acc);
-            o[i] = acc;
-        }
-        __syncwarp();
+        advance(gbase + nblk - 1, gbase + nblk);           // the whole group is consumed: keep the producer ahead
+        step2(u, gi);
     }
 }
 
@@ -342,8 +447,8 @@ MD_DEVINL void row_from_bins(const float (&T)[P][4], const float4 w, float &d0, 
 template <int P>
 __global__ void __launch_bounds__(kStThreads, 4)
 roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f, const int tma_mask,
-                           const float *__restrict__ rois5, const float *__restrict__ dout,
-                           int32_t *__restrict__ fallback_flag)
+                           const float *__restrict__ rois5, const int R, const int seg, const int nchunk,
+                           const float *__restrict__ dout, int32_t *__restrict__ fallback_flag)
 {
     static_assert(P == 7, "backward stream kernel is specialised for 7x7");
     constexpr int S = 2, NS = P * S, PP = P * P;
@@ -356,12 +461,14 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
     BwdShared<P> &bs = *reinterpret_cast<BwdShared<P> *>(AxD + kAxFloats);
     StreamShared<P> &sh = bs.st;
 
-    const int r = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const WorkItem wi = work_item(blockIdx.x, R, seg, nchunk);
+    const int r = wi.r, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const RoiGeom g = roi_geometry(f, rois5 + (int64_t)r * 5, P);
-    const int C = f.C;
+    const int C = f.C, CH = C / nchunk, cbase = wi.chunk * CH;
     const bool use_tma = (tma_mask >> g.l) & 1;
+    const bool flag_writer = tid == 0 && wi.chunk == 0;
     if ((int)__ldg(f.cfg + 1) != S || g.l >= kTmaLevels) {
-        if (tid == 0) fallback_flag[r] = 1;
+        if (flag_writer) fallback_flag[r] = 1;
         return;
     }
     build_tables<P>(sh, g);
@@ -369,11 +476,11 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
     __syncthreads();
     const int BW = sh.bw, h_fp = sh.h_fp;
     if (BW > kMaxBW || h_fp > kMaxRowsBwd) {
-        if (tid == 0) fallback_flag[r] = 1;
+        if (flag_writer) fallback_flag[r] = 1;
         return;
     }
     if (!sh.any_x || !sh.any_y) {                                   // no sample in range -> no gradient
-        if (tid == 0) fallback_flag[r] = 0;
+        if (flag_writer) fallback_flag[r] = 0;
         return;
     }
     const int BWA = BW + 4;
@@ -419,7 +526,7 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
     }
     __syncthreads();
     const bool dense = bs.dense != 0;
-    if (tid == 0) fallback_flag[r] = (dense && h_fp > 16) ? 1 : 0;
+    if (flag_writer) fallback_flag[r] = (dense && h_fp > 16) ? 1 : 0;
     if (dense && h_fp > 16) return;                                   // cannot happen for bins < 1 row; be safe
 
     const int LPC = lanes_per_channel(BW), CPW = 32 / LPC;
@@ -429,14 +536,15 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
     const int x_lo = sh.x_lo, y_lo = sh.y_lo;
     const int nblk = (h_fp + 3) >> 2;
     const int BLK = CPW * 4 * BW, SLOT = (BLK + 31) & ~31;
-    const int ngroups = C / CPW;
+    const int ngroups = CH / CPW;
     const int ng_w = (ngroups - warp + kStWarps - 1) / kStWarps;
     float *ring = ring_all + warp * kBwdRingFloats;
     float *Gs = G_all + warp * 2 * kGFloats;
     const CUtensorMap *map = &maps.m[g.l * kNumBW + (BW >> 2) - 1];
     const int H = g.H, W = g.W;
-    float *dplane = f.feat[g.l] + (int64_t)g.b * C * H * W;
-    const float *grow = dout + (int64_t)r * C * PP;
+    float *dplane = f.feat[g.l] + ((int64_t)g.b * C + cbase) * H * W;
+    const float *grow = dout + ((int64_t)r * C + cbase) * PP;
+    const int zbase = g.b * C + cbase;
 
     float ax[P][4];
 #pragma unroll
@@ -531,7 +639,7 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_reduce_add_3d(map, x_lo, y_lo + 4 * j, g.b * C + c0, dst);
+                    tma_reduce_add_3d(map, x_lo, y_lo + 4 * j, zbase + c0, dst);
                     bulk_commit();
                 }
                 if (++slot == kBwdSlots) slot = 0;
@@ -614,6 +722,18 @@ static int build_maps(const FeatSet &fs, TmaMaps *out)
     return hit->mask;
 }
 
+// channel chunks per RoI: 128 channels per CTA when C allows it (working set of one (image, chunk) sweep
+// = 128 planes of every level ~ 46 MB at config 2, inside the 126 MB L2; measured best of 32/64/128/256)
+constexpr int kSegRois = 512;
+static int chunks_for(int C)
+{
+    const char *e = getenv("MD_ROI_CHUNK");
+    const int want = e ? atoi(e) : 128;
+    int n = C / want;
+    while (n > 1 && (C % n != 0 || (C / n) % 8 != 0)) n--;
+    return n < 1 ? 1 : n;
+}
+
 template <int P> static size_t fwd_smem()
 {
     return (size_t)(kStWarps * kRingFloats + kStWarps * P * 160) * sizeof(float) + sizeof(StreamShared<P>) + 128;
@@ -634,7 +754,8 @@ static cudaError_t launch_fwd(const TmaMaps &maps, const RoiFeat &f, int mask, c
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<R, kStThreads, fwd_smem<P>(), s>>>(maps, f, mask, rois5, out, flag);
+    const int nchunk = chunks_for(f.C);
+    kern<<<R * nchunk, kStThreads, fwd_smem<P>(), s>>>(maps, f, mask, rois5, R, kSegRois, nchunk, out, flag);
     return cudaGetLastError();
 }
 
@@ -665,7 +786,8 @@ cudaError_t launch_roialign_bwd_tma(const FeatSet &fs, const RoiFeat &f, const f
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<R, kStThreads, bwd_smem<7>(), s>>>(maps, f, mask, rois5, dout, fallback_flag);
+    const int nchunk = chunks_for(f.C);
+    kern<<<R * nchunk, kStThreads, bwd_smem<7>(), s>>>(maps, f, mask, rois5, R, kSegRois, nchunk, dout, fallback_flag);
     *launched = true;
     return cudaGetLastError();
 }
