@@ -39,7 +39,7 @@ namespace md {
 
 constexpr int kStWarps = 4;
 constexpr int kStThreads = kStWarps * 32;
-constexpr int kRingFloats = 3328;          // forward ring per warp (13 KB)
+constexpr int kRingFloats = 4608;          // forward ring per warp (18 KB; a consumed stage doubles as the U buffer)
 constexpr int kMaxBW = 128;                // footprint width limit (floats)
 constexpr int kMaxSlots = 16;
 constexpr int kBwdSlots = 4;               // fixed: cp.async.bulk.wait_group needs an immediate
@@ -177,6 +177,31 @@ MD_DEVINL WorkItem work_item(int bid, int R, int seg, int nchunk)
     return w;
 }
 
+// step 2 of the forward: U[cs][p][BWU] (smem) -> Out[cs][p][q].  lane = (channel-in-round, q); the lane's four
+// column taps stay in registers, rows advance by an immediate (BWU is a template parameter).
+template <int P, int BWU>
+MD_DEVINL void fwd_step2(const float *U, int CPW, const SampleTap t0, const SampleTap t1, float *o, int lane)
+{
+    constexpr int CSG = 32 / P, PP = P * P;                 // channels per round
+    const int csl = lane / P, q = lane - csl * P;
+    if (csl >= CSG) return;
+    for (int cb = 0; cb < CPW; cb += CSG) {
+        const int cs = cb + csl;
+        if (cs < CPW) {
+            const float *uc = U + cs * P * BWU;
+            float *oc = o + cs * PP + q;
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                float acc = mul(t0.wl, uc[p * BWU + t0.lo]);
+                acc = __fmaf_rn(t0.wh, uc[p * BWU + t0.hi], acc);
+                acc = __fmaf_rn(t1.wl, uc[p * BWU + t1.lo], acc);
+                acc = __fmaf_rn(t1.wh, uc[p * BWU + t1.hi], acc);
+                oc[p * P] = acc;
+            }
+        }
+    }
+}
+
 template <int P>
 __global__ void __launch_bounds__(kStThreads, 3)
 roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f, const int tma_mask,
@@ -185,11 +210,9 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
 {
     constexpr int S = 2, NS = P * S, PP = P * P;
     constexpr int kUFloats = P * 160;                     // max over LPC of CPW * P * (4*LPC + 4)
-    constexpr int ROUNDS = (PP + 31) / 32;
     extern __shared__ __align__(128) unsigned char dsm[];
     float *ring_all = reinterpret_cast<float *>(dsm);
-    float *U_all = ring_all + kStWarps * kRingFloats;
-    StreamShared<P> &sh = *reinterpret_cast<StreamShared<P> *>(U_all + kStWarps * kUFloats);
+    StreamShared<P> &sh = *reinterpret_cast<StreamShared<P> *>(ring_all + kStWarps * kRingFloats);
 
     const WorkItem wi = work_item(blockIdx.x, R, seg, nchunk);
     const int r = wi.r, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -228,7 +251,6 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
     const int ngroups = CH / CPW;                                     // host guarantees CH % 8 == 0
     const int ng_w = (ngroups - warp + kStWarps - 1) / kStWarps;      // groups warp, warp+4, ...
     float *ring = ring_all + warp * kRingFloats;
-    float *U = U_all + warp * kUFloats;
     unsigned long long *full = sh.full[warp];
     const CUtensorMap *map = &maps.m[g.l * kNumBW + (BW >> 2) - 1];
     const int H = g.H, W = g.W;
@@ -252,19 +274,10 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
         }
     };
 
-    // ---- step 2 taps of this lane's outputs pq = lane + 32k (registers when there are at most 2 rounds) ----
-    int ta[ROUNDS <= 2 ? ROUNDS : 1][4];
-    float tw[ROUNDS <= 2 ? ROUNDS : 1][4];
-    if (ROUNDS <= 2) {
-#pragma unroll
-        for (int k = 0; k < (ROUNDS <= 2 ? ROUNDS : 1); k++) {
-            const int pq = min(lane + 32 * k, PP - 1), p = pq / P, q = pq - p * P;
-            const SampleTap t0 = sh.xtab[q * S], t1 = sh.xtab[q * S + 1];
-            ta[k][0] = p * BWU + t0.lo; ta[k][1] = p * BWU + t0.hi; ta[k][2] = p * BWU + t1.lo; ta[k][3] = p * BWU + t1.hi;
-            tw[k][0] = t0.wl; tw[k][1] = t0.wh; tw[k][2] = t1.wl; tw[k][3] = t1.wh;
-        }
-    }
-    auto step2 = [&](const float (&u)[P][4], int grp) {
+    // ---- step 2: the lane's output column q and its four taps -------------------------------------------
+    const int q2 = lane % P;
+    const SampleTap xt0 = sh.xtab[q2 * S], xt1 = sh.xtab[q2 * S + 1];
+    auto step2 = [&](float *U, const float (&u)[P][4], int grp) {
         if (col_ok) {
 #pragma unroll
             for (int p = 0; p < P; p++)
@@ -272,38 +285,20 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
         }
         __syncwarp();
         float *o = orow + (int64_t)(warp + kStWarps * grp) * CPW * PP;
-        if (ROUNDS <= 2) {
-            const float *uc = U;
-            for (int cs = 0; cs < CPW; cs++, uc += P * BWU, o += PP) {
-#pragma unroll
-                for (int k = 0; k < (ROUNDS <= 2 ? ROUNDS : 1); k++) {
-                    float acc = mul(tw[k][0], uc[ta[k][0]]);
-                    acc = __fmaf_rn(tw[k][1], uc[ta[k][1]], acc);
-                    acc = __fmaf_rn(tw[k][2], uc[ta[k][2]], acc);
-                    acc = __fmaf_rn(tw[k][3], uc[ta[k][3]], acc);
-                    if (lane + 32 * k < PP) o[lane + 32 * k] = acc;
-                }
-            }
-        } else {
-            for (int i = lane; i < CPW * PP; i += 32) {
-                const int cs = i / PP, pq = i - cs * PP;
-                const int p = pq / P, q = pq - p * P;
-                const SampleTap t0 = sh.xtab[q * S], t1 = sh.xtab[q * S + 1];
-                const float *ur = U + (cs * P + p) * BWU;
-                float acc = mul(t0.wl, ur[t0.lo]);
-                acc = __fmaf_rn(t0.wh, ur[t0.hi], acc);
-                acc = __fmaf_rn(t1.wl, ur[t1.lo], acc);
-                acc = __fmaf_rn(t1.wh, ur[t1.hi], acc);
-                o[i] = acc;
-            }
+        switch (LPC) {
+            case 4: fwd_step2<P, 20>(U, CPW, xt0, xt1, o, lane); break;
+            case 8: fwd_step2<P, 36>(U, CPW, xt0, xt1, o, lane); break;
+            case 16: fwd_step2<P, 68>(U, CPW, xt0, xt1, o, lane); break;
+            default: fwd_step2<P, 132>(U, CPW, xt0, xt1, o, lane); break;
         }
         __syncwarp();
     };
 
     const int TILE = nblk * SLOT;
-    if (2 * TILE <= kRingFloats) {
+    const int SP = (max(TILE, CPW * P * BWU) + 31) & ~31;   // stage pitch: a consumed stage doubles as the U buffer
+    if (2 * SP <= kRingFloats) {
         // =============== tile mode: the whole footprint of a channel group is one pipeline stage ===============
-        const int NST = min(4, kRingFloats / TILE);
+        const int NST = min(4, kRingFloats / SP);
         // per-sample float offsets inside a tile (row block, row in block); same for every group
         SampleTap *yoff = sh.yoff;
         if (warp == 0 && lane < NS) {
@@ -313,18 +308,18 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
             yoff[lane] = o;
         }
         __syncthreads();
-        auto issue_tile = [&](int grp) {
-            const int st = grp % NST;
+        auto issue_tile = [&](int grp, int st) {
             if (use_tma && lane == 0) mbar_expect_tx(&full[st], (uint32_t)(nblk * BLK) * 4u);
-            for (int j = 0; j < nblk; j++) load_block(ring + st * TILE + j * SLOT, grp, j, &full[st]);
+            for (int j = 0; j < nblk; j++) load_block(ring + st * SP + j * SLOT, grp, j, &full[st]);
             if (!use_tma) cp_async_mbar_arrive(&full[st]);
         };
-        for (int gi = 0; gi < NST && gi < ng_w; gi++) issue_tile(gi);
+        for (int gi = 0; gi < NST && gi < ng_w; gi++) issue_tile(gi, gi);
         int st = 0;
         uint32_t par = 0;
         for (int gi = 0; gi < ng_w; gi++) {
             mbar_wait(&full[st], par);
-            const float *tile = ring + st * TILE + lane_off;
+            float *stage = ring + st * SP;
+            const float *tile = stage + lane_off;
             float u[P][4];
 #pragma unroll
             for (int p = 0; p < P; p++) u[p][0] = u[p][1] = u[p][2] = u[p][3] = 0.0f;
@@ -341,15 +336,16 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
                 }
             }
             __syncwarp();                                   // every lane is done reading this stage
-            if (gi + NST < ng_w) issue_tile(gi + NST);
-            step2(u, gi);
+            step2(stage, u, gi);                            // the consumed stage is the U buffer
+            if (gi + NST < ng_w) issue_tile(gi + NST, st);
             if (++st == NST) { st = 0; par ^= 1u; }
         }
         return;
     }
 
     // =============== stream mode: row blocks slide through the ring (any footprint height) ===============
-    const int NB = min(kMaxSlots, kRingFloats / SLOT);
+    float *Ubuf = ring + kRingFloats - kUFloats;
+    const int NB = min(kMaxSlots, (kRingFloats - kUFloats) / SLOT);
     const int total = ng_w * nblk;
     int iss = 0, iss_g = 0, iss_j = 0, iss_slot = 0;
     auto issue_one = [&]() {
@@ -410,7 +406,7 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
         grp_slot += nblk;
         while (grp_slot >= NB) grp_slot -= NB;
         advance(gbase + nblk - 1, gbase + nblk);           // the whole group is consumed: keep the producer ahead
-        step2(u, gi);
+        step2(Ubuf, u, gi);
     }
 }
 
@@ -683,6 +679,9 @@ static std::mutex g_cache_mutex;
 static int build_maps(const FeatSet &fs, TmaMaps *out)
 {
     EncodeTiledFn enc = get_encode();
+    const char *pe = getenv("MD_ROI_L2PROMO");
+    const int pv = pe ? atoi(pe) : 128;
+    const CUtensorMapL2promotion l2promo = pv == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (pv == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (pv == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
     std::lock_guard<std::mutex> lock(g_cache_mutex);
     const int L = fs.L < kTmaLevels ? fs.L : kTmaLevels;
     MapCache *hit = nullptr, *victim = &g_cache[0];
@@ -709,7 +708,7 @@ static int build_maps(const FeatSet &fs, TmaMaps *out)
                 const cuuint32_t box[3] = { (cuuint32_t)bw, 4u, (cuuint32_t)(32 / lanes_per_channel(bw)) };
                 const cuuint32_t estr[3] = { 1, 1, 1 };
                 ok = enc(&c.maps.m[l * kNumBW + k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, fs.feat[l], dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2promo,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
             }
             if (ok) c.mask |= 1 << l;
@@ -736,7 +735,7 @@ static int chunks_for(int C)
 
 template <int P> static size_t fwd_smem()
 {
-    return (size_t)(kStWarps * kRingFloats + kStWarps * P * 160) * sizeof(float) + sizeof(StreamShared<P>) + 128;
+    return (size_t)(kStWarps * kRingFloats) * sizeof(float) + sizeof(StreamShared<P>) + 128;
 }
 template <int P> static size_t bwd_smem()
 {
