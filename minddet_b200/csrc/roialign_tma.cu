@@ -417,8 +417,10 @@ template <int P>
 struct BwdShared {
     StreamShared<P> st;
     float4 row_w[kMaxRowsBwd];         // weights of bins row_p .. row_p+3
-    int row_p[kMaxRowsBwd];            // first contributing bin of each footprint row
+    int row_p[kMaxRowsBwd];            // first contributing bin of each footprint row (-1: none)
+    int row_p2[kMaxRowsBwd];           // same with empty rows filled in
     float ay_dense[16][8];             // rows x bins, only when some row has more than 4 contributing bins
+    int rs[P + 1];                     // rows [rs[p], rs[p+1]) have first contributing bin p (row_p is non-decreasing)
     int dense;
 };
 
@@ -503,7 +505,7 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
         for (int p = P - 1; p >= 0; p--) if (w[p] != 0.0f) pa = p;
 #pragma unroll
         for (int p = 0; p < P; p++) if (w[p] != 0.0f) pz = p;
-        if (pz < 0) pa = pz = 0;                                     // row without contribution
+        if (pz < 0) { pa = -1; pz = -1; }                            // row without contribution (fixed up below)
         float4 ww = make_float4(0, 0, 0, 0);
 #pragma unroll
         for (int p = 0; p < P; p++) {
@@ -519,6 +521,19 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
 #pragma unroll
             for (int p = 0; p < 8; p++) bs.ay_dense[y][p] = p < P ? w[p] : 0.0f;
         }
+    }
+    if (tid <= P) bs.rs[tid] = h_fp;
+    __syncthreads();
+    // empty rows inherit the previous row's first bin (weights are zero), which keeps row_p non-decreasing;
+    // rs[p] = first row whose first bin is >= p
+    for (int y = tid; y < h_fp; y += kStThreads) {
+        int pa = bs.row_p[y], yy = y;
+        while (pa < 0 && yy > 0) pa = bs.row_p[--yy];
+        if (pa < 0) pa = 0;
+        int prev = -1, yp = y - 1;
+        if (yp >= 0) { prev = bs.row_p[yp]; while (prev < 0 && yp > 0) prev = bs.row_p[--yp]; if (prev < 0) prev = 0; }
+        for (int q = prev + 1; q <= pa; q++) bs.rs[q] = y;
+        bs.row_p2[y] = pa;
     }
     __syncthreads();
     const bool dense = bs.dense != 0;
@@ -542,6 +557,8 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
     const float *grow = dout + ((int64_t)r * C + cbase) * PP;
     const int zbase = g.b * C + cbase;
 
+    const int lane_off = csub * 4 * BW + 4 * xq;
+
     float ax[P][4];
 #pragma unroll
     for (int q = 0; q < P; q++) {
@@ -553,11 +570,7 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
         const int c0 = (warp + kStWarps * gi) * CPW;
         float *dst = Gs + (gi & 1) * kGFloats;
         const float *src = grow + (int64_t)c0 * PP;
-        for (int e = lane; e < CPW * PP; e += 32) {
-            const int cs = e / PP, pq = e - cs * PP;
-            const int p = pq / P, q = pq - p * P;
-            cp_async4(dst + (cs * P + p) * 8 + q, src + e);
-        }
+        for (int e = lane; e < CPW * PP; e += 32) cp_async4(dst + e + e / P, src + e);   // rows of P padded to 8
         cp_async_commit_group();
     };
 
@@ -585,60 +598,59 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
                 }
             }
         }
-        // ---- step 2: D[row][4 cols] = sum_p Ay[p][row] * T[p], one TMA reduce-add per 4-row block ---------
-        for (int j = 0; j < nblk; j++) {
-            float *dst = ring + slot * SLOT;
+        // ---- step 2: D[row][4 cols] = sum_p Ay[p][row] * T[p].  Rows are walked bin by bin (row_p is
+        //      non-decreasing, so the register index of T stays static and no per-row dispatch is needed).
+        //      TMA levels: rows go conflict-free into a ring slot; every completed 4-row block is folded into
+        //      dX by ONE TMA reduce-add (at most kBwdSlots in flight).  Other levels: red.global per element. ----
+        auto emit_row = [&](int y, float d0, float d1, float d2, float d3) {
             if (use_tma) {
-                if (lane == 0) bulk_wait_read<kBwdSlots - 1>();      // the reduce that last read this slot is done
-                __syncwarp();
-            }
-#pragma unroll
-            for (int rr = 0; rr < 4; rr++) {
-                const int y = 4 * j + rr;
-                float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
-                if (y < h_fp) {
-                    if (!dense) {
-                        const int pa = bs.row_p[y];
-                        const float4 w = bs.row_w[y];
-                        switch (pa) {
-                            case 0: row_from_bins<P, 0>(T, w, d0, d1, d2, d3); break;
-                            case 1: row_from_bins<P, 1>(T, w, d0, d1, d2, d3); break;
-                            case 2: row_from_bins<P, 2>(T, w, d0, d1, d2, d3); break;
-                            case 3: row_from_bins<P, 3>(T, w, d0, d1, d2, d3); break;
-                            case 4: row_from_bins<P, 4>(T, w, d0, d1, d2, d3); break;
-                            case 5: row_from_bins<P, 5>(T, w, d0, d1, d2, d3); break;
-                            default: row_from_bins<P, 6>(T, w, d0, d1, d2, d3); break;
-                        }
-                    } else {
-                        const float4 w0 = *reinterpret_cast<const float4 *>(&bs.ay_dense[y][0]);
-                        const float4 w1 = *reinterpret_cast<const float4 *>(&bs.ay_dense[y][4]);
-                        const float wp[7] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z };
-#pragma unroll
-                        for (int p = 0; p < P; p++) {
-                            d0 = __fmaf_rn(wp[p], T[p][0], d0); d1 = __fmaf_rn(wp[p], T[p][1], d1);
-                            d2 = __fmaf_rn(wp[p], T[p][2], d2); d3 = __fmaf_rn(wp[p], T[p][3], d3);
-                        }
+                float *dst = ring + slot * SLOT + lane_off;
+                if (col_ok) *reinterpret_cast<float4 *>(dst + (y & 3) * BW) = make_float4(d0, d1, d2, d3);
+                if ((y & 3) == 3 || y == h_fp - 1) {
+                    for (int z = (y & 3) + 1; z < 4; z++)
+                        if (col_ok) *reinterpret_cast<float4 *>(dst + z * BW) = make_float4(0, 0, 0, 0);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (++slot == kBwdSlots) slot = 0;
+                    if (lane == 0) {
+                        tma_reduce_add_3d(map, x_lo, y_lo + (y & ~3), zbase + c0, dst - lane_off);
+                        bulk_commit();
+                        bulk_wait_read<kBwdSlots - 1>();             // the reduce that last read the NEXT slot is done
                     }
+                    __syncwarp();
                 }
-                if (use_tma) {
-                    if (col_ok) *reinterpret_cast<float4 *>(dst + (csub * 4 + rr) * BW + 4 * xq) = make_float4(d0, d1, d2, d3);
-                } else if (col_ok && y < h_fp && y_lo + y < H) {
-                    const int xa = x_lo + 4 * xq;
-                    float *dp = dplane + ((int64_t)(c0 + csub) * H + (y_lo + y)) * W + xa;
-                    if (xa < W && d0 != 0.0f) atomicAdd(dp, d0);
-                    if (xa + 1 < W && d1 != 0.0f) atomicAdd(dp + 1, d1);
-                    if (xa + 2 < W && d2 != 0.0f) atomicAdd(dp + 2, d2);
-                    if (xa + 3 < W && d3 != 0.0f) atomicAdd(dp + 3, d3);
-                }
+            } else if (col_ok && y_lo + y < H) {
+                const int xa = x_lo + 4 * xq;
+                float *dp = dplane + ((int64_t)(c0 + csub) * H + (y_lo + y)) * W + xa;
+                if (xa < W && d0 != 0.0f) atomicAdd(dp, d0);
+                if (xa + 1 < W && d1 != 0.0f) atomicAdd(dp + 1, d1);
+                if (xa + 2 < W && d2 != 0.0f) atomicAdd(dp + 2, d2);
+                if (xa + 3 < W && d3 != 0.0f) atomicAdd(dp + 3, d3);
             }
-            if (use_tma) {
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_reduce_add_3d(map, x_lo, y_lo + 4 * j, zbase + c0, dst);
-                    bulk_commit();
+        };
+        if (!dense) {
+            int y = 0;
+#define MD_BIN(PA)                                                                                   \
+    for (const int ye = bs.rs[PA + 1]; y < ye; y++) {                                                \
+        const float4 w = bs.row_w[y];                                                                \
+        float d0, d1, d2, d3;                                                                        \
+        row_from_bins<P, PA>(T, w, d0, d1, d2, d3);                                                  \
+        emit_row(y, d0, d1, d2, d3);                                                                 \
+    }
+            MD_BIN(0) MD_BIN(1) MD_BIN(2) MD_BIN(3) MD_BIN(4) MD_BIN(5) MD_BIN(6)
+#undef MD_BIN
+        } else {
+            for (int y = 0; y < h_fp; y++) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(&bs.ay_dense[y][0]);
+                const float4 w1 = *reinterpret_cast<const float4 *>(&bs.ay_dense[y][4]);
+                const float wp[7] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z };
+                float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    d0 = __fmaf_rn(wp[p], T[p][0], d0); d1 = __fmaf_rn(wp[p], T[p][1], d1);
+                    d2 = __fmaf_rn(wp[p], T[p][2], d2); d3 = __fmaf_rn(wp[p], T[p][3], d3);
                 }
-                if (++slot == kBwdSlots) slot = 0;
+                emit_row(y, d0, d1, d2, d3);
             }
         }
         __syncwarp();                                     // Gs[gi & 1] may be overwritten by stage_g(gi + 2)
