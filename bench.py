@@ -29,6 +29,8 @@ if ROOT not in sys.path:
 METRIC = "Faster R-CNN RPN+RoI region path throughput"
 UNIT = "img/s"
 BATCH = 8
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the stream kernels (ncu --set full, profiles/r1_roialign_ncu.md)
+NCU_TRAFFIC = {"roialign_fwd": 855e6, "roialign_bwd": 1277e6}
 WORKLOAD = ("configs[1]: Faster R-CNN R50-FPN region path, batch 8/GPU, 800x1344, 5 levels (268569 anchors), "
             "2000 pre-NMS/level, NMS 0.7, max_num 2000, G<=128 gts, 512 sampled RoIs, 256-ch 7x7 RoIAlign fwd+bwd")
 
@@ -121,13 +123,13 @@ def run_reference(args):
                             inp["gt_valid"].numpy().astype(np.uint8), cfg, dout=inp["dout"].numpy(), nthreads=cores)
         return time.perf_counter() - t0
 
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(min(args.warmup, 2)):
         one()
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 20))
     dt = sum(one() for _ in range(steps)) / steps
     val = nimg / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": min(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": f"{nimg} images per step"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
@@ -166,7 +168,7 @@ def run_b200(args):
     host = pipeline.make_inputs(BATCH, seed=0xD37 + rank, pin=True)
     h2d_bytes = pipeline.input_bytes(host)
     side = torch.cuda.Stream()
-    gather_buf = torch.empty(world * BATCH, 100, 5, device="cuda") if world > 1 else None
+    from minddet_b200 import shard
 
     def step(inp, timers=None):
         def mark(name):
@@ -187,9 +189,6 @@ def run_b200(args):
         mark("roialign_fwd")
         dfe = rp.extractor._backward(rois, inp["dout"], [tuple(f.shape) for f in inp["feats"]])
         mark("roialign_bwd")
-        if world > 1:   # the path's only collective: all-gather of the final detections (top-100 proposals / image)
-            dist.all_gather_into_tensor(gather_buf, props[:, :100].contiguous())
-            mark("allgather")
         return dict(props=props, pmask=pmask, rpn=rpn, rcnn=rcnn, rois=rois, roi_feats=roi_feats, dfeats=dfe)
 
     with torch.cuda.stream(side):
@@ -207,11 +206,10 @@ def run_b200(args):
             for (n0, e0), (n1, e1) in zip(tm[:-1], tm[1:]):
                 stage_ms.setdefault(n1, []).append(e0.elapsed_time(e1))
         stage_ms = {k: float(np.median(v)) for k, v in stage_ms.items()}
-        dominant = max((k for k in stage_ms if k.startswith("roialign")), key=lambda k: stage_ms[k])
 
         # CUDA graph of the whole step (launch-bound otherwise: 16 kernels + 5 memsets behind 7 ctypes calls)
         graph = None
-        if not args.no_graph and world == 1:
+        if not args.no_graph:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
                 out = step(dev)
@@ -221,8 +219,12 @@ def run_b200(args):
         def run_step():
             if graph is not None:
                 graph.replay()
-                return out
-            return step(dev)
+                o = out
+            else:
+                o = step(dev)
+            if world > 1:   # the path's only collective: all-gather of the final detections (top-100 proposals / image)
+                o["gathered"] = shard.gather_detections(o["props"][:, :100].contiguous(), world * BATCH)
+            return o
 
         # ---- timed region: device-resident inputs (731 MB of features per step >> 126 MB L2) ----------
         sampler = ClockSampler(local)
@@ -240,40 +242,78 @@ def run_b200(args):
             dist.barrier()
         ms = e0.elapsed_time(e1) / K
 
-        # dominant-kernel duration, live with CUDA events on the launching stream (eager, same kernels)
-        dom = []
+        # per-stage durations, live with CUDA events on the launching stream (eager, same kernels), K passes
+        per = {}
         for _ in range(K):
             tm = []
             step(dev, tm)
             side.synchronize()
-            names = [n for n, _ in tm]
-            i = names.index(dominant)
-            dom.append(tm[i - 1][1].elapsed_time(tm[i][1]))
-        dom_ms = float(np.mean(dom))
+            for (n0, ev0), (n1, ev1) in zip(tm[:-1], tm[1:]):
+                per.setdefault(n1, []).append(ev0.elapsed_time(ev1))
+        live_ms = {k: float(np.mean(v)) for k, v in per.items()}
 
-        # ---- e2e: pinned host -> device copies of every input + D2H of the compact results, every step --
-        def e2e_step():
-            for k, v in host.items():
-                if isinstance(v, list):
-                    for d, h in zip(dev[k], v):
-                        d.copy_(h, non_blocking=True)
-                else:
-                    dev[k].copy_(v, non_blocking=True)
-            o = run_step()
-            res = [o["rcnn"]["rois"], o["rcnn"]["labels"], o["rcnn"]["deltas"], o["rcnn"]["mask"], o["rpn"]["pos_idx"],
-                   o["rpn"]["neg_idx"], o["rpn"]["pos_target"], o["props"][:, :100],
-                   o["roi_feats"].sum().reshape(1), torch.stack([d.sum() for d in o["dfeats"]])]
-            got = [r.cpu() for r in res]
-            return sum(g.numel() * g.element_size() for g in got)
-
-        d2h_bytes = e2e_step()
+        # ---- e2e: every step copies ALL inputs pinned host -> device and reads the step's compact results back.
+        # Two device input sets + a copy stream: the H2D of step i+1 overlaps the kernels of step i (a user
+        # feeding the op from host memory would do the same); each set has its own captured graph. ------------
+        cs = torch.cuda.Stream()
+        dev2 = pipeline.to_device(host)
         side.synchronize()
+        sets, outs, graphs = [dev, dev2], [out, None], [graph, None]
+        if graph is not None:
+            for _ in range(2):
+                step(dev2)
+            side.synchronize()
+            graphs[1] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graphs[1], stream=side):
+                outs[1] = step(dev2)
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        pinned = [None, None]
+
+        def results_of(o):
+            return [o["rcnn"]["rois"], o["rcnn"]["labels"], o["rcnn"]["deltas"], o["rcnn"]["mask"], o["rpn"]["pos_idx"],
+                    o["rpn"]["neg_idx"], o["rpn"]["pos_target"], o["props"][:, :100].contiguous(),
+                    o["roi_feats"][:4].contiguous()] + [d[0, 0, 0, :8].contiguous() for d in o["dfeats"]]
+
+        def e2e_step(i):
+            b = i & 1
+            if i >= 2:
+                cs.wait_event(done[b])                  # the kernels that read this input set have finished
+            with torch.cuda.stream(cs):
+                for k, v in host.items():
+                    if isinstance(v, list):
+                        for d, h in zip(sets[b][k], v):
+                            d.copy_(h, non_blocking=True)
+                    else:
+                        sets[b][k].copy_(v, non_blocking=True)
+                copied[b].record(cs)
+            side.wait_event(copied[b])
+            if graphs[b] is not None:
+                graphs[b].replay()
+                o = outs[b]
+            else:
+                o = step(sets[b])
+            if world > 1:
+                o["gathered"] = shard.gather_detections(o["props"][:, :100].contiguous(), world * BATCH)
+            res = results_of(o)
+            if pinned[b] is None:
+                pinned[b] = [torch.empty(r.shape, dtype=r.dtype, pin_memory=True) for r in res]
+            for dst, r in zip(pinned[b], res):
+                dst.copy_(r, non_blocking=True)
+            done[b].record(side)
+            if i >= 1:
+                done[1 - b].synchronize()               # host consumes the previous step's results
+            return sum(r.numel() * r.element_size() for r in res)
+
+        d2h_bytes = e2e_step(0)
+        e2e_step(1)
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(K):
-            e2e_step()
+        for i in range(K):
+            e2e_step(i + 2)
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / K
         sampler.stop_flag = True
@@ -289,18 +329,35 @@ def run_b200(args):
         return
 
     value = world * BATCH / (ms * 1e-3)
-    # ---- roofline of the dominant kernel ---------------------------------------------------------------
+    # ---- rooflines (HBM): algorithmic bytes per launch / live CUDA-event duration of the stage -------------
     peak, peak_src = peaks()
     rois_np = out["rois"].cpu().numpy()
     C, P = 256, 7
     shapes = synth.level_shapes()[:4]
     fp = footprint_bytes(rois_np, shapes, synth.STRIDES[:4], C)
     out_bytes = rois_np.shape[0] * C * P * P * 4
-    alg = out_bytes + fp    # fwd: out write + union footprint read; bwd: dY read + union footprint update
-    achieved = alg / (dom_ms * 1e-3) / 1e9
-    roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "algorithmic_bytes_per_launch": alg, "kernel_ms": dom_ms, "peak_source": peak_src,
-                "note": "algorithmic bytes = RoI tensor (R*C*49*4) + exact union of bilinear footprints of this step's RoIs"}
+    dx_bytes = sum(BATCH * C * h * w * 4 for h, w in shapes)
+    n_anchor = sum(3 * h * w for h, w in synth.level_shapes())
+    alg = {
+        # RoI tensor written + exact union of the bilinear footprints read
+        "roialign_fwd": out_bytes + fp,
+        # dY read + union footprint updated + zero-init of every dX byte
+        "roialign_bwd": out_bytes + fp + dx_bytes,
+        # scores read + (deltas gathered, boxes written, NMS in/out, proposals out) per image
+        "proposal": BATCH * (n_anchor * 4 + 8819 * (16 + 16 + 8 + 25) + 2000 * 21),
+        # anchors + valid read, assigned written and re-read by the samplers
+        "rpn_assign_sample": BATCH * (n_anchor * (16 + 1 + 4 + 4)),
+    }
+    rooflines = {k: {"achieved": alg[k] / (live_ms[k] * 1e-3) / 1e9, "frac": alg[k] / (live_ms[k] * 1e-3) / 1e9 / peak,
+                     "algorithmic_bytes_per_launch": alg[k], "ms": live_ms[k]} for k in alg}
+    dominant = max(("roialign_fwd", "roialign_bwd"), key=lambda k: live_ms[k])
+    roofline = {"kernel": dominant, "bound": "hbm", "achieved": rooflines[dominant]["achieved"], "peak": peak, "unit": "GB/s",
+                "frac": rooflines[dominant]["frac"], "traffic": NCU_TRAFFIC.get(dominant),
+                "algorithmic_bytes_per_launch": alg[dominant], "kernel_ms": live_ms[dominant], "peak_source": peak_src,
+                "note": "stage = the stream kernel + gather kernel for declined RoIs (+ the 4 dX memsets for bwd); "
+                        "algorithmic bytes = RoI tensor (R*C*49*4) + exact union of bilinear footprints of this step's RoIs "
+                        "(+ zero-init of dX for bwd); traffic = dram read+write of the stream kernel from profiles/ (ncu --set full)",
+                "all": rooflines}
 
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -313,7 +370,7 @@ def run_b200(args):
             "clocks": sampler.summary(),
             "e2e": {"value": world * BATCH / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms},
-            "gpu_launches": pipeline.KERNELS_PER_STEP * K,
+            "gpu_launches": pipeline.KERNELS_PER_STEP * K, "nccl_collectives_per_step": 1 if world > 1 else 0,
             "roofline": roofline, "stage_ms": stage_ms, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
@@ -328,14 +385,19 @@ def cpu_baseline():
     nimg = max(1, min(BATCH, cores))
     inp = pipeline.make_inputs(nimg, seed=0xD37)
     cfg = region_cfg(O)
-    t0 = time.perf_counter()
-    O.region_path_batch([x.numpy() for x in inp["cls_scores"]], [x.numpy() for x in inp["bbox_preds"]],
-                        synth.base_anchor_sets(), synth.STRIDES, [x.numpy() for x in inp["feats"]], inp["gts"].numpy(),
-                        inp["gt_labels"].numpy(), inp["gt_valid"].numpy().astype(np.uint8), cfg, dout=inp["dout"].numpy(),
-                        nthreads=cores)
-    dt = time.perf_counter() - t0
-    return {"value": nimg / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{nimg} images of the same workload, {cores} pthreads (one image per task), single run of {dt:.1f} s"}
+    arrs = ([x.numpy() for x in inp["cls_scores"]], [x.numpy() for x in inp["bbox_preds"]], synth.base_anchor_sets(), synth.STRIDES,
+            [x.numpy() for x in inp["feats"]], inp["gts"].numpy(), inp["gt_labels"].numpy(), inp["gt_valid"].numpy().astype(np.uint8))
+    dout = inp["dout"].numpy()
+    O.region_path_batch(*arrs, cfg, dout=dout, nthreads=cores)          # warm-up (page faults, thread start)
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        O.region_path_batch(*arrs, cfg, dout=dout, nthreads=cores)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= 10.0 or reps >= 64:
+            break
+    return {"value": reps * nimg / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{reps} passes over {nimg} images of the same workload ({dt:.1f} s), {cores} pthreads (one image per task)"}
 
 
 def main():

@@ -682,7 +682,7 @@ static EncodeTiledFn get_encode()
 struct MapCache {
     void *ptr[kTmaLevels]; int H[kTmaLevels], W[kTmaLevels], BC, L, mask; TmaMaps maps; bool valid; unsigned long long stamp;
 };
-constexpr int kCacheEntries = 4;
+constexpr int kCacheEntries = 8;
 static MapCache g_cache[kCacheEntries];
 static unsigned long long g_stamp = 0;
 static std::mutex g_cache_mutex;

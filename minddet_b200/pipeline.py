@@ -8,8 +8,9 @@ import torch
 from . import synth
 from .ops import (AnchorGenerator, BboxAssignSample, BboxAssignSampleForRcnn, Proposal, SingleRoIExtractor)
 
-KERNELS_PER_STEP = 16   # select, nms_mask, nms_sweep, merge x2 | gtmax, label, select, finalize |
-                        # gt_head, gtmax, label, select, finalize | roialign fwd | roialign bwd
+KERNELS_PER_STEP = 18   # select, nms_mask, nms_sweep, merge x2 | gtmax, label, select, finalize |
+                        # gt_head, gtmax, label, select, finalize | roialign fwd (stream + gather for declined RoIs)
+                        # | roialign bwd (stream + gather); the 5 cudaMemsetAsync of a step are not counted
 
 
 class RegionPath:
