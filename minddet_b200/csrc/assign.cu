@@ -51,6 +51,33 @@ MD_DEVINL int stage_gts(const AsIn &in, int b, float off, GtS *sg, int *s_count)
     return *s_count;
 }
 
+// Warp-level cull: the 32 consecutive boxes of a warp are (for anchors) ~11 neighbouring grid cells, so almost
+// no gt can overlap any of them.  Lane k tests gt (base + k) against the bounding box of the warp's boxes and the
+// ballot is the ordered hit list (gt order decides arg-max ties and which force-match wins).  Skipping the
+// others is exact: their IoU with every box of the warp is 0 (iw or ih <= 0); a 1-pixel margin keeps the test
+// conservative under the fp32 rounding of the real iw / ih expressions.
+struct WarpBox { float x1, y1, x2, y2; };
+MD_DEVINL WarpBox warp_bbox(bool have, float4 a)
+{
+    WarpBox w = { have ? a.x : 3.0e38f, have ? a.y : 3.0e38f, have ? a.z : -3.0e38f, have ? a.w : -3.0e38f };
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        w.x1 = fminf(w.x1, __shfl_xor_sync(0xffffffffu, w.x1, o)); w.y1 = fminf(w.y1, __shfl_xor_sync(0xffffffffu, w.y1, o));
+        w.x2 = fmaxf(w.x2, __shfl_xor_sync(0xffffffffu, w.x2, o)); w.y2 = fmaxf(w.y2, __shfl_xor_sync(0xffffffffu, w.y2, o));
+    }
+    return w;
+}
+MD_DEVINL uint32_t warp_hits(const GtS *sg, int ng, int base, const WarpBox &w, float off)
+{
+    const int k = base + (threadIdx.x & 31);
+    bool hit = false;
+    if (k < ng) {
+        const float4 g = sg[k].box;
+        hit = !(g.z + off < w.x1 - 1.0f || w.x2 + off < g.x - 1.0f || g.w + off < w.y1 - 1.0f || w.y2 + off < g.y - 1.0f);
+    }
+    return __ballot_sync(0xffffffffu, hit);
+}
+
 __global__ void __launch_bounds__(kAsThreads)
 assign_gtmax_kernel(const AsIn in, uint32_t *__restrict__ gmax /* (B,G) float bits, zeroed */)
 {
@@ -64,14 +91,21 @@ assign_gtmax_kernel(const AsIn in, uint32_t *__restrict__ gmax /* (B,G) float bi
     const int ng = stage_gts(in, b, off, sg, &s_count);
     if (ng == 0) return;
     const float *boxes = in.boxes + (int64_t)b * in.image_stride;
-    for (int n = blockIdx.x * kAsThreads + threadIdx.x; n < in.N; n += gridDim.x * kAsThreads) {
-        if (in.box_valid && !in.box_valid[(int64_t)b * in.valid_stride + n]) continue;
-        const float4 a = load_box(boxes + (int64_t)n * in.ld, in.ld);
-        for (int k = 0; k < ng; k++) {
-            const float o = iou_legacy(a, sg[k].box, sg[k].area, off);
-            if (o > 0.0f) {
-                const uint32_t ob = __float_as_uint(o);      // o > 0: uint order == float order
-                if (ob > smax[k]) atomicMax(&smax[k], ob);
+    for (int n0 = blockIdx.x * kAsThreads; n0 < in.N; n0 += gridDim.x * kAsThreads) {
+        const int n = n0 + threadIdx.x;
+        const bool have = n < in.N && !(in.box_valid && !in.box_valid[(int64_t)b * in.valid_stride + n]);
+        const float4 a = have ? load_box(boxes + (int64_t)n * in.ld, in.ld) : make_float4(0, 0, 0, 0);
+        const WarpBox wb = warp_bbox(have, a);
+        for (int base = 0; base < ng; base += 32) {
+            uint32_t hits = warp_hits(sg, ng, base, wb, off);
+            while (hits) {
+                const int k = base + __ffs(hits) - 1;
+                hits &= hits - 1;
+                const float o = have ? iou_legacy(a, sg[k].box, sg[k].area, off) : 0.0f;
+                if (o > 0.0f) {
+                    const uint32_t ob = __float_as_uint(o);      // o > 0: uint order == float order
+                    if (ob > smax[k]) atomicMax(&smax[k], ob);
+                }
             }
         }
     }
@@ -97,18 +131,27 @@ assign_label_kernel(const AsIn in, const uint32_t *__restrict__ gmax, int32_t *_
     __syncthreads();
     const float *boxes = in.boxes + (int64_t)b * in.image_stride;
     int32_t *out = assigned + (int64_t)b * assigned_stride + assigned_offset;
-    for (int n = blockIdx.x * kAsThreads + threadIdx.x; n < in.N; n += gridDim.x * kAsThreads) {
-        int32_t as = -1;
-        if (!in.box_valid || in.box_valid[(int64_t)b * in.valid_stride + n]) {
-            const float4 a = load_box(boxes + (int64_t)n * in.ld, in.ld);
-            float m = 0.0f;
-            int am = 0, force = 0;
-            for (int k = 0; k < ng; k++) {
+    for (int n0 = blockIdx.x * kAsThreads; n0 < in.N; n0 += gridDim.x * kAsThreads) {
+        const int n = n0 + threadIdx.x;
+        const bool have = n < in.N && (!in.box_valid || in.box_valid[(int64_t)b * in.valid_stride + n]);
+        const float4 a = have ? load_box(boxes + (int64_t)n * in.ld, in.ld) : make_float4(0, 0, 0, 0);
+        const WarpBox wb = warp_bbox(have, a);
+        float m = 0.0f;
+        int am = 0, force = 0;
+        for (int base = 0; base < ng; base += 32) {
+            uint32_t hits = warp_hits(sg, ng, base, wb, off);
+            while (hits) {                               // ascending gt order, uniform across the warp
+                const int k = base + __ffs(hits) - 1;
+                hits &= hits - 1;
                 const float o = iou_legacy(a, sg[k].box, sg[k].area, off);
                 if (o > m) { m = o; am = sg[k].j; }
                 const float gm = smax[k];
                 if (o == gm && gm > 0.0f && (mode != 0 || gm >= min_pos)) force = sg[k].j + 1;
             }
+        }
+        if (n >= in.N) continue;
+        int32_t as = -1;
+        if (have) {
             if (mode == 0) {
                 if (m >= 0.0f && m < neg_thr) as = 0;
                 if (m >= pos_thr) as = am + 1;
@@ -135,17 +178,21 @@ __global__ void rcnn_gt_head_kernel(const uint8_t *__restrict__ gt_valid, int B,
 // ---- sampling on the cluster radix-select -------------------------------------------------------------
 struct SampleSrc {
     const int32_t *assigned; int N; int Sp, Sn; uint32_t stream_base; const int32_t *seed;
-    __device__ int length(int) const { return N; }
-    __device__ int want(int seg) const { return (seg & 1) ? Sn : Sp; }
-    __device__ uint32_t index_of(int, int m) const { return (uint32_t)m; }
-    __device__ bool load(int seg, int m, uint32_t &key, uint32_t &index) const
+    struct Ctx { const int32_t *base; int kind; uint32_t image, seed_lo, seed_hi; };
+    __device__ Ctx prepare(int seg) const
     {
-        const int b = seg >> 1, kind = seg & 1;
-        const int32_t a = __ldg(assigned + (int64_t)b * N + m);
-        index = (uint32_t)m;
-        const bool cand = kind ? (a == 0) : (a > 0);
+        const int b = seg >> 1;
+        return Ctx{ assigned + (int64_t)b * N, seg & 1, (uint32_t)b, (uint32_t)__ldg(seed), (uint32_t)__ldg(seed + 1) };
+    }
+    __device__ int length(const Ctx &) const { return N; }
+    __device__ int want(const Ctx &c) const { return c.kind ? Sn : Sp; }
+    __device__ uint32_t index_of(const Ctx &, int m) const { return (uint32_t)m; }
+    __device__ bool load(const Ctx &c, int m, uint32_t &key) const
+    {
+        const int32_t a = __ldg(c.base + m);
+        const bool cand = c.kind ? (a == 0) : (a > 0);
         if (!cand) return false;
-        key = ~philox_key((uint32_t)m, stream_base + kind, (uint32_t)b, (uint32_t)__ldg(seed), (uint32_t)__ldg(seed + 1));
+        key = ~philox_key((uint32_t)m, stream_base + c.kind, c.image, c.seed_lo, c.seed_hi);
         return true;
     }
 };

@@ -148,20 +148,21 @@ cudaError_t launch_decode_level(const float *deltas, const float *base, int B, i
 // =====================================================================================================
 struct TopkSrc {            // one level, B segments
     const float *scores; int A, HW, N, K; const float *cfg_sigmoid;
-    __device__ int length(int) const { return N; }
-    __device__ int want(int) const { return K; }
-    __device__ uint32_t index_of(int, int m) const
+    struct Ctx { const float *base; bool sigmoid; };
+    __device__ Ctx prepare(int seg) const { return Ctx{ scores + (int64_t)seg * N, __ldg(cfg_sigmoid) != 0.0f }; }
+    __device__ int length(const Ctx &) const { return N; }
+    __device__ int want(const Ctx &) const { return K; }
+    __device__ uint32_t index_of(const Ctx &, int m) const
     {
         if (A == 0) return (uint32_t)m;
         const int a = m / HW, p = m - a * HW;
         return (uint32_t)(p * A + a);
     }
-    __device__ bool load(int seg, int m, uint32_t &key, uint32_t &index) const
+    __device__ bool load(const Ctx &c, int m, uint32_t &key) const
     {
-        float x = __ldg(scores + (int64_t)seg * N + m);
-        if (__ldg(cfg_sigmoid) != 0.0f) x = exact_sigmoid(x);
+        float x = __ldg(c.base + m);
+        if (c.sigmoid) x = exact_sigmoid(x);
         key = score_key(x);
-        index = index_of(seg, m);
         return true;
     }
 };
@@ -197,21 +198,25 @@ struct PropLevels {
 };
 struct PropSrc {
     PropLevels p;
-    __device__ int length(int seg) const { const int l = seg % p.L; return p.A[l] * p.HW[l]; }
-    __device__ int want(int) const { return p.nms_pre; }   // pads up to nms_pre; selection caps at N
-    __device__ uint32_t index_of(int seg, int m) const
-    {
-        const int l = seg % p.L;
-        const int a = m / p.HW[l], q = m - a * p.HW[l];
-        return (uint32_t)(q * p.A[l] + a);
-    }
-    __device__ bool load(int seg, int m, uint32_t &key, uint32_t &index) const
+    struct Ctx { const float *base; int A, HW, N; bool sigmoid; };
+    __device__ Ctx prepare(int seg) const
     {
         const int l = seg % p.L, b = seg / p.L;
-        float x = __ldg(p.scores[l] + (int64_t)b * p.A[l] * p.HW[l] + m);
-        if (__ldg(p.cfg + 15) != 0.0f) x = exact_sigmoid(x);
+        const int N = p.A[l] * p.HW[l];
+        return Ctx{ p.scores[l] + (int64_t)b * N, p.A[l], p.HW[l], N, __ldg(p.cfg + 15) != 0.0f };
+    }
+    __device__ int length(const Ctx &c) const { return c.N; }
+    __device__ int want(const Ctx &) const { return p.nms_pre; }   // pads up to nms_pre; selection caps at N
+    __device__ uint32_t index_of(const Ctx &c, int m) const
+    {
+        const int a = m / c.HW, q = m - a * c.HW;
+        return (uint32_t)(q * c.A + a);
+    }
+    __device__ bool load(const Ctx &c, int m, uint32_t &key) const
+    {
+        float x = __ldg(c.base + m);
+        if (c.sigmoid) x = exact_sigmoid(x);
         key = score_key(x);
-        index = index_of(seg, m);
         return true;
     }
 };
@@ -394,13 +399,15 @@ nms_sweep_kernel(const NmsSegs sg, const unsigned long long *__restrict__ mask,
                 if (nk == kept) break;
                 kept = nk;
             }
-            // OR the kept rows into the removed words of the later chunks
+            // OR the kept rows into the removed words of the later chunks: 64 independent predicated loads
+            // (a data-dependent `while (k)` walk serialises ffs -> address -> load and was 3 us per chunk)
             if (lane > c && lane < nb) {
-                unsigned long long acc = 0ull, k = kept;
-                while (k) {
-                    const int b = __ffsll((long long)k) - 1;
-                    k &= k - 1;
-                    acc |= rows[b * nbp + lane];
+                unsigned long long acc = 0ull;
+                const unsigned long long *col = rows + lane;
+#pragma unroll 16
+                for (int b = 0; b < 64; b++) {
+                    const unsigned long long v = col[b * nbp];
+                    acc |= ((kept >> b) & 1ull) ? v : 0ull;
                 }
                 removed |= acc;
             }
@@ -458,7 +465,7 @@ cudaError_t launch_nms(const float *boxes, int ld, int B, int K, const float *cf
 // Precondition: scores > -65536.
 // =====================================================================================================
 constexpr int kMergeThreads = 512;
-constexpr int kMergeSplit = 4;
+constexpr int kMergeSplit = 16;
 
 __global__ void __launch_bounds__(kMergeThreads)
 merge_levels_kernel(int L, int nms_pre, int max_num, const float4 *__restrict__ ws_boxes,

@@ -43,10 +43,12 @@ struct SelShared {
 };
 
 // Src concept:
-//   __device__ int  length(int seg) const;        elements in the segment (memory order)
-//   __device__ int  want(int seg) const;          K requested (<= kSelMaxK)
-//   __device__ bool load(int seg, int m, uint32_t &key, uint32_t &index) const;  false = not a candidate
-//   __device__ uint32_t index_of(int seg, int m) const;   logical index of memory position m
+//   struct Ctx;  __device__ Ctx prepare(int seg) const;            per-segment constants (hoisted out of the loops)
+//   __device__ int  length(const Ctx&) const;                       elements in the segment (memory order)
+//   __device__ int  want(const Ctx&) const;                         K requested (<= kSelMaxK)
+//   __device__ bool load(const Ctx&, int m, uint32_t &key) const;   false = not a candidate
+//   __device__ uint32_t index_of(const Ctx&, int m) const;          logical index of memory position m (only evaluated
+//                                                                    for tie digits and for the selected elements)
 // Sink concept:
 //   __device__ void emit(int seg, int rank, unsigned long long comp) const;
 //   __device__ void pad(int seg, int rank) const;                 ranks >= #selected, < want(seg)
@@ -63,9 +65,10 @@ select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
     const int rank = (int)cluster.block_rank();
     const int seg = blockIdx.x / kClusterSize;
     const int tid = threadIdx.x, lane = tid & 31;
+    const typename Src::Ctx ctx = src.prepare(seg);
 
-    const int N = src.length(seg);
-    const int K = min(src.want(seg), kSelMaxK);
+    const int N = src.length(ctx);
+    const int K = min(src.want(ctx), kSelMaxK);
     // slice (multiple of 32 so validity words never straddle CTAs)
     int per = (N + kClusterSize - 1) / kClusterSize;
     per = (per + 31) & ~31;
@@ -75,41 +78,49 @@ select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
 
     if (tid == 0) sh.cand_count = 0;
 
-    // every composite has bits 31..22 set (index < 2^22), so those bits are "already matched"
-    unsigned long long prefix = 0xFFC00000ull, known = 0xFFC00000ull;
+    // composite = (key << 32) | ~index.  Every composite has low bits 31..22 set (index < 2^22), so those
+    // bits are "already matched".  The 4 key digits never need the index; it is only computed for the tie
+    // digits (passes 4..6, when a tie straddles K) and for the selected elements.
+    uint32_t prefix_hi = 0u, known_hi = 0u, prefix_lo = 0xFFC00000u, known_lo = 0xFFC00000u;
     int need = K;          // how many still to take among elements matching the prefix
     int candidates = 0;
     bool done = false;
-    // digit schedule: key bits 63..32 (4 digits), then index bits 21..16, 15..8, 7..0
+    constexpr int UNR = 4;
+    // digit schedule: key bits 31..0 (4 digits), then index bits 21..16, 15..8, 7..0
     for (int pass = 0; pass < 7 && !done; pass++) {
-        const int shift = pass < 4 ? 56 - 8 * pass : 16 - 8 * (pass - 4);
+        const bool on_key = pass < 4;
+        const int shift = on_key ? 24 - 8 * pass : 16 - 8 * (pass - 4);
         const uint32_t wmask = pass == 4 ? 0x3Fu : 0xFFu;
         for (int i = tid; i < 256 * 32; i += kSelThreads) sh.hist[i] = 0;
         __syncthreads();
-        // ---- scan the slice -----------------------------------------------------------------
-        for (int base = 0; base < len; base += kSelThreads) {
-            const int i = base + tid;
-            bool ok = false;
-            uint32_t key = 0, index = 0;
-            if (i < len) {
-                if (pass == 0 || !cached) {
-                    ok = src.load(seg, begin + i, key, index);
-                    if (cached) keys[i] = key;
-                } else {
-                    ok = (vbits[i >> 5] >> (i & 31)) & 1u;
-                    key = keys[i];
-                    index = src.index_of(seg, begin + i);
+        // ---- scan the slice (UNR independent loads in flight per thread) -------------------------------
+        for (int base = 0; base < len; base += UNR * kSelThreads) {
+            bool ok[UNR];
+            uint32_t key[UNR];
+#pragma unroll
+            for (int j = 0; j < UNR; j++) {
+                const int i = base + j * kSelThreads + tid;
+                ok[j] = false; key[j] = 0u;
+                if (i < len) {
+                    if (pass == 0 || !cached) ok[j] = src.load(ctx, begin + i, key[j]);
+                    else { ok[j] = (vbits[i >> 5] >> (i & 31)) & 1u; key[j] = keys[i]; }
                 }
             }
-            if (pass == 0 && cached) {
-                const uint32_t b = __ballot_sync(0xffffffffu, ok);
-                if (lane == 0 && i < len) vbits[i >> 5] = b;
-            }
-            if (ok) {
-                const unsigned long long comp = ((unsigned long long)key << 32) | (uint32_t)~index;
-                if ((comp & known) == prefix) {
-                    const uint32_t d = (uint32_t)(comp >> shift) & wmask;
-                    atomicAdd(&sh.hist[d * 32 + lane], 1u);
+#pragma unroll
+            for (int j = 0; j < UNR; j++) {
+                const int i = base + j * kSelThreads + tid;
+                if (pass == 0 && cached) {
+                    if (i < len) keys[i] = key[j];
+                    const uint32_t bal = __ballot_sync(0xffffffffu, ok[j]);
+                    if (lane == 0 && i < len) vbits[i >> 5] = bal;
+                }
+                if (ok[j] && (key[j] & known_hi) == prefix_hi) {
+                    if (on_key) {
+                        atomicAdd(&sh.hist[((key[j] >> shift) & 0xFFu) * 32 + lane], 1u);
+                    } else {
+                        const uint32_t lo = ~src.index_of(ctx, begin + i);
+                        if ((lo & known_lo) == prefix_lo) atomicAdd(&sh.hist[((lo >> shift) & wmask) * 32 + lane], 1u);
+                    }
                 }
             }
         }
@@ -164,8 +175,8 @@ select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
         if (need == 0 || !sh.found) {
             done = true;
         } else {
-            prefix |= (unsigned long long)sh.digit << shift;
-            known |= (unsigned long long)wmask << shift;
+            if (on_key) { prefix_hi |= sh.digit << shift; known_hi |= 0xFFu << shift; }
+            else { prefix_lo |= sh.digit << shift; known_lo |= wmask << shift; }
             need -= (int)sh.above;
             if ((int)sh.eq == need) done = true;   // everything matching the prefix is selected
         }
@@ -173,6 +184,7 @@ select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
     }
     // selected set: every candidate with (comp & known) >= prefix
     const int selected = min(K, candidates);
+    const bool lo_free = known_lo == 0xFFC00000u;    // no index digit fixed: the key alone decides
 
     // ---- collect into the leader's shared memory (DSMEM) -------------------------------------------
     if (selected > 0) {
@@ -181,18 +193,23 @@ select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
         for (int base = 0; base < len; base += kSelThreads) {
             const int i = base + tid;
             bool ok = false;
-            uint32_t key = 0, index = 0;
+            uint32_t key = 0;
             if (i < len) {
-                if (cached) {
-                    ok = (vbits[i >> 5] >> (i & 31)) & 1u;
-                    key = keys[i];
-                    index = src.index_of(seg, begin + i);
-                } else {
-                    ok = src.load(seg, begin + i, key, index);
-                }
+                if (cached) { ok = (vbits[i >> 5] >> (i & 31)) & 1u; key = keys[i]; }
+                else ok = src.load(ctx, begin + i, key);
             }
-            const unsigned long long comp = ((unsigned long long)key << 32) | (uint32_t)~index;
-            const bool take = ok && ((comp & known) >= prefix);
+            bool take = false;
+            uint32_t lo = 0u;
+            if (ok) {
+                const uint32_t kh = key & known_hi;
+                if (kh > prefix_hi) take = true;
+                else if (kh == prefix_hi) {
+                    if (lo_free) take = true;
+                    else { lo = ~src.index_of(ctx, begin + i); take = (lo & known_lo) >= prefix_lo; }
+                }
+                if (take && lo == 0u) lo = ~src.index_of(ctx, begin + i);
+            }
+            const unsigned long long comp = ((unsigned long long)key << 32) | lo;
             const uint32_t m = __ballot_sync(0xffffffffu, take);
             if (m) {
                 uint32_t pos = 0;
@@ -224,7 +241,7 @@ select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
             __syncthreads();
         }
     }
-    const int want = src.want(seg);
+    const int want = src.want(ctx);
     for (int i = tid; i < want; i += kSelThreads) {
         if (i < selected) sink.emit(seg, i, sh.cand[i]);
         else sink.pad(seg, i);

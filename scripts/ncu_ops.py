@@ -1,7 +1,9 @@
-"""Opcode histogram + hottest SASS lines of one kernel in an .ncu-rep: python scripts/ncu_ops.py rep kernel_regex [launch_idx]"""
+"""Opcode histogram + hottest SASS lines of one kernel in an .ncu-rep:
+python scripts/ncu_ops.py rep kernel_regex [regions] [skip=N]   (skip = matching launches to skip)"""
 import csv, subprocess, sys, collections
 rep, kre = sys.argv[1], sys.argv[2]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kre}", "--launch-count", "1"], capture_output=True, text=True).stdout
+skip = next((a.split("=")[1] for a in sys.argv if a.startswith("skip=")), "0")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kre}", "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
