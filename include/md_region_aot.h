@@ -47,7 +47,9 @@ enum { /* MD_CFG_PROPOSAL: MD_CFG_DECODE (0..10) + these + one stride per level 
 };
 enum { /* MD_CFG_ASSIGN: 16 floats */
     MD_AS_POS_THR = 0, MD_AS_NEG_THR = 1, MD_AS_MIN_POS_IOU = 2, MD_AS_IOU_OFFSET = 3, MD_AS_MODE = 4,
-    MD_AS_NUM_TOTAL = 5, MD_AS_MEAN0 = 6, MD_AS_STD0 = 10, MD_AS_LEN = 16
+    MD_AS_NUM_TOTAL = 5, MD_AS_MEAN0 = 6, MD_AS_STD0 = 10,
+    MD_AS_FORCE_FULL = 14, /* != 0: skip the samplers' short-list fast path (test hook; results are identical) */
+    MD_AS_LEN = 16
 };
 enum { /* MD_CFG_ROI: 4 floats + one stride per level */
     MD_ROI_FINEST = 0, MD_ROI_SAMPLE_NUM = 1, MD_ROI_END_MODE = 2, MD_ROI_STRIDE0 = 4

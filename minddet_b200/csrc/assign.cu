@@ -116,7 +116,7 @@ assign_gtmax_kernel(const AsIn in, uint32_t *__restrict__ gmax /* (B,G) float bi
 
 __global__ void __launch_bounds__(kAsThreads)
 assign_label_kernel(const AsIn in, const uint32_t *__restrict__ gmax, int32_t *__restrict__ assigned,
-                    int64_t assigned_stride, int assigned_offset)
+                    int64_t assigned_stride, int assigned_offset, int32_t *__restrict__ cand_count /* (B,2) pos|neg */)
 {
     extern __shared__ unsigned char smem_raw[];
     GtS *sg = reinterpret_cast<GtS *>(smem_raw);
@@ -131,6 +131,7 @@ assign_label_kernel(const AsIn in, const uint32_t *__restrict__ gmax, int32_t *_
     __syncthreads();
     const float *boxes = in.boxes + (int64_t)b * in.image_stride;
     int32_t *out = assigned + (int64_t)b * assigned_stride + assigned_offset;
+    int npos = 0, nneg = 0;                              // per-thread candidate counts (samplers need the totals)
     for (int n0 = blockIdx.x * kAsThreads; n0 < in.N; n0 += gridDim.x * kAsThreads) {
         const int n = n0 + threadIdx.x;
         const bool have = n < in.N && (!in.box_valid || in.box_valid[(int64_t)b * in.valid_stride + n]);
@@ -162,28 +163,116 @@ assign_label_kernel(const AsIn in, const uint32_t *__restrict__ gmax, int32_t *_
             }
         }
         out[n] = as;
+        npos += as > 0; nneg += as == 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { npos += __shfl_xor_sync(0xffffffffu, npos, o); nneg += __shfl_xor_sync(0xffffffffu, nneg, o); }
+    if ((threadIdx.x & 31) == 0) {
+        if (npos) atomicAdd(cand_count + b * 2, npos);
+        if (nneg) atomicAdd(cand_count + b * 2 + 1, nneg);
     }
 }
 
 // gts-as-proposals head of the RCNN candidate list
 __global__ void rcnn_gt_head_kernel(const uint8_t *__restrict__ gt_valid, int B, int G, int32_t *__restrict__ assigned,
-                                    int64_t assigned_stride)
+                                    int64_t assigned_stride, int32_t *__restrict__ cand_count)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * G) return;
     const int b = i / G, j = i - b * G;
-    assigned[(int64_t)b * assigned_stride + j] = (!gt_valid || gt_valid[i]) ? j + 1 : -1;
+    const bool v = !gt_valid || gt_valid[i];
+    assigned[(int64_t)b * assigned_stride + j] = v ? j + 1 : -1;
+    if (v) atomicAdd(cand_count + b * 2, 1);             // a valid gt is a positive candidate of its own image
 }
+
+// ---- fast path of the samplers ------------------------------------------------------------------------------
+// "k smallest (Philox key, index)" over ~N candidates does not need a radix select over all of them: with the
+// candidate totals known (counted by the label kernel), ONE fully parallel pass keeps the candidates whose key is
+// below a threshold chosen so that ~kListCap/2 survive, and the cluster select then runs on that short list.
+// Exact whenever the list holds at least min(k, #candidates) entries and did not overflow (then the k smallest
+// overall are all in it); otherwise the segment is flagged and the full-scan select below handles it.
+constexpr int kListCap = 8192;
+struct SampleLists { unsigned long long *items; int32_t *count; const int32_t *cand_count; };   // per (image, kind)
+
+MD_DEVINL uint32_t sample_threshold(int ncand)
+{
+    if (ncand <= kListCap) return 0xFFFFFFFFu;
+    return (uint32_t)((((unsigned long long)(kListCap / 2)) << 32) / (unsigned long long)ncand);
+}
+MD_DEVINL bool list_is_exact(const SampleLists &L, int seg, int want)
+{
+    const int cnt = L.count[seg], nc = L.cand_count[seg];
+    return cnt <= kListCap && cnt >= min(want, nc);
+}
+
+__global__ void __launch_bounds__(256)
+sample_prefilter_kernel(const int32_t *__restrict__ assigned, int N, uint32_t stream_base, const int32_t *__restrict__ seed,
+                        const float *__restrict__ cfg, const SampleLists L)
+{
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    if (__ldg(cfg + 14) != 0.0f) {                       // MD_AS_FORCE_FULL: mark both lists overflowed -> full-scan select
+        if (blockIdx.x == 0 && threadIdx.x < 2) L.count[b * 2 + threadIdx.x] = kListCap + 1;
+        return;
+    }
+    const uint32_t s0 = (uint32_t)__ldg(seed), s1 = (uint32_t)__ldg(seed + 1);
+    const uint32_t thr_pos = sample_threshold(L.cand_count[b * 2]), thr_neg = sample_threshold(L.cand_count[b * 2 + 1]);
+    const int32_t *a = assigned + (int64_t)b * N;
+    for (int n0 = blockIdx.x * 256; n0 < N; n0 += gridDim.x * 256) {
+        const int n = n0 + threadIdx.x;
+        int kind = -1;
+        uint32_t r = 0u;
+        if (n < N) {
+            const int32_t v = __ldg(a + n);
+            kind = v > 0 ? 0 : (v == 0 ? 1 : -1);
+            if (kind >= 0) {
+                r = philox_key((uint32_t)n, stream_base + kind, (uint32_t)b, s0, s1);
+                if (r > (kind ? thr_neg : thr_pos)) kind = -1;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const uint32_t m = __ballot_sync(0xffffffffu, kind == k);
+            if (m) {
+                int pos = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) pos = atomicAdd(L.count + b * 2 + k, __popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(m & ((1u << lane) - 1u));
+                if (kind == k && pos < kListCap)
+                    L.items[(int64_t)(b * 2 + k) * kListCap + pos] = ((unsigned long long)(~r) << 32) | (uint32_t)(~(uint32_t)n);
+            }
+        }
+    }
+}
+
+struct ListSrc {
+    SampleLists L; int Sp, Sn; int nimg;
+    struct Ctx { const unsigned long long *items; int len, want; bool ok; };
+    __device__ int segment_of(int i) const { return i < nimg ? 2 * i + 1 : 2 * (i - nimg); }
+    __device__ Ctx prepare(int seg) const
+    {
+        const int want = (seg & 1) ? Sn : Sp;
+        return Ctx{ L.items + (int64_t)seg * kListCap, min(L.count[seg], kListCap), want, list_is_exact(L, seg, want) };
+    }
+    __device__ bool active(const Ctx &c) const { return c.ok; }
+    __device__ int length(const Ctx &c) const { return c.len; }
+    __device__ int want(const Ctx &c) const { return c.want; }
+    __device__ uint32_t index_of(const Ctx &c, int m) const { return ~(uint32_t)c.items[m]; }
+    __device__ bool load(const Ctx &c, int m, uint32_t &key) const { key = (uint32_t)(c.items[m] >> 32); return true; }
+};
 
 // ---- sampling on the cluster radix-select -------------------------------------------------------------
 struct SampleSrc {
-    const int32_t *assigned; int N; int Sp, Sn; uint32_t stream_base; const int32_t *seed;
-    struct Ctx { const int32_t *base; int kind; uint32_t image, seed_lo, seed_hi; };
+    const int32_t *assigned; int N; int Sp, Sn; uint32_t stream_base; const int32_t *seed; int nimg; SampleLists L;
+    struct Ctx { const int32_t *base; int kind; uint32_t image, seed_lo, seed_hi; bool on; };
+    // negatives (odd segments, ~all anchors are candidates) first, positives after
+    __device__ int segment_of(int i) const { return i < nimg ? 2 * i + 1 : 2 * (i - nimg); }
     __device__ Ctx prepare(int seg) const
     {
         const int b = seg >> 1;
-        return Ctx{ assigned + (int64_t)b * N, seg & 1, (uint32_t)b, (uint32_t)__ldg(seed), (uint32_t)__ldg(seed + 1) };
+        return Ctx{ assigned + (int64_t)b * N, seg & 1, (uint32_t)b, (uint32_t)__ldg(seed), (uint32_t)__ldg(seed + 1),
+                    !list_is_exact(L, seg, (seg & 1) ? Sn : Sp) };
     }
+    __device__ bool active(const Ctx &c) const { return c.on; }      // full scan only for segments the list path declined
     __device__ int length(const Ctx &) const { return N; }
     __device__ int want(const Ctx &c) const { return c.kind ? Sn : Sp; }
     __device__ uint32_t index_of(const Ctx &, int m) const { return (uint32_t)m; }
@@ -211,7 +300,7 @@ struct SampleSink {
         if (seg & 1) neg_idx[(int64_t)b * neg_stride + rank] = 0;
         else pos_idx[(int64_t)b * pos_stride + rank] = 0;
     }
-    __device__ void finish(int seg, int, int candidates) const { cand_count[seg] = candidates; }
+    __device__ void finish(int, int, int) const {}
 };
 
 // ---- finalisers -------------------------------------------------------------------------------------
@@ -299,26 +388,54 @@ __global__ void rcnn_finalize_kernel(const float *__restrict__ props5, int P_, c
     if (threadIdx.x == 0) num_pos_out[b] = num_pos;
 }
 
-// workspace: gmax (B,G) u32 | cand_count (B,2) i32
-size_t assign_workspace_bytes(int B, int G)
+// workspace: gmax (B,G) u32 | cand_count (B,2) i32 | list_count (B,2) i32 | lists (B,2,kListCap) u64
+struct AssignWs { uint32_t *gmax; int32_t *cand, *list_count; unsigned long long *items; size_t total; };
+static AssignWs carve_assign_ws(void *ws, int B, int G)
 {
-    return (((size_t)B * G * 4 + 255) & ~(size_t)255) + (size_t)B * 2 * 4 + 256;
+    AssignWs w;
+    unsigned char *p = reinterpret_cast<unsigned char *>(ws);
+    size_t o = 0;
+    w.gmax = reinterpret_cast<uint32_t *>(p + o); o += ((size_t)B * G * 4 + 255) & ~(size_t)255;
+    w.cand = reinterpret_cast<int32_t *>(p + o); w.list_count = w.cand + B * 2; o += ((size_t)B * 4 * 4 + 255) & ~(size_t)255;
+    w.items = reinterpret_cast<unsigned long long *>(p + o); o += (size_t)B * 2 * kListCap * 8;
+    w.total = o + 256;
+    return w;
 }
+size_t assign_workspace_bytes(int B, int G) { return carve_assign_ws(nullptr, B, G).total; }
 
-static cudaError_t run_assign(const AsIn &in, int B, uint32_t *gmax, int32_t *assigned, int64_t assigned_stride,
-                              int assigned_offset, cudaStream_t s)
+static cudaError_t run_assign(const AsIn &in, int B, const AssignWs &w, int32_t *assigned, int64_t assigned_stride,
+                              int assigned_offset, bool zero_counts, cudaStream_t s)
 {
     if (in.G > kAsMaxG) return cudaErrorInvalidValue;
-    cudaError_t e = cudaMemsetAsync(gmax, 0, (size_t)B * in.G * 4, s);
+    cudaError_t e = cudaMemsetAsync(w.gmax, 0, (size_t)B * in.G * 4, s);
     if (e != cudaSuccess) return e;
+    if (zero_counts) {
+        e = cudaMemsetAsync(w.cand, 0, (size_t)B * 4 * 4, s);
+        if (e != cudaSuccess) return e;
+    }
     int gx = (in.N + kAsThreads - 1) / kAsThreads;
     const int cap = (148 * 8 + B - 1) / B;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     const size_t smem = (size_t)in.G * (sizeof(GtS) + 4) + 16;
-    assign_gtmax_kernel<<<dim3(gx, B), kAsThreads, smem, s>>>(in, gmax);
-    assign_label_kernel<<<dim3(gx, B), kAsThreads, smem, s>>>(in, gmax, assigned, assigned_stride, assigned_offset);
+    assign_gtmax_kernel<<<dim3(gx, B), kAsThreads, smem, s>>>(in, w.gmax);
+    assign_label_kernel<<<dim3(gx, B), kAsThreads, smem, s>>>(in, w.gmax, assigned, assigned_stride, assigned_offset, w.cand);
     return cudaGetLastError();
+}
+
+// list fast path, then the full-scan select for the segments it declined (normally none: both kernels of the
+// second launch return at once)
+static cudaError_t run_samplers(const int32_t *assigned, int B, int N, int Sp, int Sn, uint32_t stream_base,
+                                const int32_t *seed, const float *cfg, const AssignWs &w, const SampleSink &sink, cudaStream_t s)
+{
+    SampleLists L{ w.items, w.list_count, w.cand };
+    int gx = (N + 255) / 256;
+    const int cap = (148 * 8 + B - 1) / B;
+    if (gx > cap) gx = cap;
+    sample_prefilter_kernel<<<dim3(gx, B), 256, 0, s>>>(assigned, N, stream_base, seed, cfg, L);
+    cudaError_t e = launch_select_sorted(ListSrc{ L, Sp, Sn, B }, sink, 2 * B, kListCap, s);
+    if (e != cudaSuccess) return e;
+    return launch_select_sorted(SampleSrc{ assigned, N, Sp, Sn, stream_base, seed, B, L }, sink, 2 * B, N, s);
 }
 
 cudaError_t launch_assign_sample_rpn(const float *boxes, int boxes_per_image, const uint8_t *box_valid,
@@ -330,16 +447,14 @@ cudaError_t launch_assign_sample_rpn(const float *boxes, int boxes_per_image, co
 {
     if (B == 0) return cudaSuccess;
     if (N >= (1 << kSelMaxIndexBits) || Sp > kSelMaxK || Sn > kSelMaxK) return cudaErrorInvalidValue;
-    uint32_t *gmax = reinterpret_cast<uint32_t *>(ws);
-    int32_t *cand = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(ws) + (((size_t)B * G * 4 + 255) & ~(size_t)255));
+    const AssignWs w = carve_assign_ws(ws, B, G);
     AsIn in{ boxes, 4, boxes_per_image ? (int64_t)N * 4 : 0, box_valid, boxes_per_image ? (int64_t)N : 0, gts, gt_valid, G, N, cfg };
-    cudaError_t e = run_assign(in, B, gmax, assigned, N, 0, s);
+    cudaError_t e = run_assign(in, B, w, assigned, N, 0, true, s);
     if (e != cudaSuccess) return e;
-    SampleSrc src{ assigned, N, Sp, Sn, 0u, seed };
-    SampleSink sink{ pos_idx, neg_idx, Sp, Sn, Sp, Sn, cand };
-    e = launch_select_sorted(src, sink, 2 * B, N, s);
+    SampleSink sink{ pos_idx, neg_idx, Sp, Sn, Sp, Sn, w.cand };
+    e = run_samplers(assigned, B, N, Sp, Sn, 0u, seed, cfg, w, sink, s);
     if (e != cudaSuccess) return e;
-    rpn_finalize_kernel<<<B, 256, 0, s>>>(in, Sp, Sn, cand, assigned, pos_idx, pos_valid, neg_idx, neg_valid,
+    rpn_finalize_kernel<<<B, 256, 0, s>>>(in, Sp, Sn, w.cand, assigned, pos_idx, pos_valid, neg_idx, neg_valid,
                                           pos_gt, reinterpret_cast<float4 *>(pos_target), num_pos);
     return cudaGetLastError();
 }
@@ -354,17 +469,17 @@ cudaError_t launch_assign_sample_rcnn(const float *props5, const uint8_t *prop_m
     if (B == 0) return cudaSuccess;
     const int N = G + P, S = Sp + Sn;
     if (N >= (1 << kSelMaxIndexBits) || Sp > kSelMaxK || Sn > kSelMaxK) return cudaErrorInvalidValue;
-    uint32_t *gmax = reinterpret_cast<uint32_t *>(ws);
-    int32_t *cand = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(ws) + (((size_t)B * G * 4 + 255) & ~(size_t)255));
+    const AssignWs w = carve_assign_ws(ws, B, G);
     AsIn in{ props5, 5, (int64_t)P * 5, prop_mask, (int64_t)P, gts, gt_valid, G, P, cfg };
-    if (G > 0) rcnn_gt_head_kernel<<<(B * G + 255) / 256, 256, 0, s>>>(gt_valid, B, G, assigned, N);
-    cudaError_t e = run_assign(in, B, gmax, assigned, N, G, s);
+    cudaError_t e = cudaMemsetAsync(w.cand, 0, (size_t)B * 4 * 4, s);
     if (e != cudaSuccess) return e;
-    SampleSrc src{ assigned, N, Sp, Sn, 2u, seed };
-    SampleSink sink{ sel_idx, sel_idx + Sp, Sp, Sn, S, S, cand };
-    e = launch_select_sorted(src, sink, 2 * B, N, s);
+    if (G > 0) rcnn_gt_head_kernel<<<(B * G + 255) / 256, 256, 0, s>>>(gt_valid, B, G, assigned, N, w.cand);
+    e = run_assign(in, B, w, assigned, N, G, false, s);
     if (e != cudaSuccess) return e;
-    rcnn_finalize_kernel<<<B, 256, 0, s>>>(props5, P, gts, gt_labels, G, cfg, Sp, Sn, cand, assigned, sel_idx,
+    SampleSink sink{ sel_idx, sel_idx + Sp, Sp, Sn, S, S, w.cand };
+    e = run_samplers(assigned, B, N, Sp, Sn, 2u, seed, cfg, w, sink, s);
+    if (e != cudaSuccess) return e;
+    rcnn_finalize_kernel<<<B, 256, 0, s>>>(props5, P, gts, gt_labels, G, cfg, Sp, Sn, w.cand, assigned, sel_idx,
                                            rois5, reinterpret_cast<float4 *>(deltas), labels, mask, pos_gt, num_pos);
     return cudaGetLastError();
 }

@@ -149,6 +149,8 @@ cudaError_t launch_decode_level(const float *deltas, const float *base, int B, i
 struct TopkSrc {            // one level, B segments
     const float *scores; int A, HW, N, K; const float *cfg_sigmoid;
     struct Ctx { const float *base; bool sigmoid; };
+    __device__ int segment_of(int i) const { return i; }
+    __device__ bool active(const Ctx &) const { return true; }
     __device__ Ctx prepare(int seg) const { return Ctx{ scores + (int64_t)seg * N, __ldg(cfg_sigmoid) != 0.0f }; }
     __device__ int length(const Ctx &) const { return N; }
     __device__ int want(const Ctx &) const { return K; }
@@ -199,12 +201,16 @@ struct PropLevels {
 struct PropSrc {
     PropLevels p;
     struct Ctx { const float *base; int A, HW, N; bool sigmoid; };
+    // level-major launch order: the 8-CTA clusters of the finest (longest) level start first, so the critical
+    // path is one level-0 segment instead of two waves of them
+    __device__ int segment_of(int i) const { const int l = i / p.B, b = i - l * p.B; return b * p.L + l; }
     __device__ Ctx prepare(int seg) const
     {
         const int l = seg % p.L, b = seg / p.L;
         const int N = p.A[l] * p.HW[l];
         return Ctx{ p.scores[l] + (int64_t)b * N, p.A[l], p.HW[l], N, __ldg(p.cfg + 15) != 0.0f };
     }
+    __device__ bool active(const Ctx &) const { return true; }
     __device__ int length(const Ctx &c) const { return c.N; }
     __device__ int want(const Ctx &) const { return p.nms_pre; }   // pads up to nms_pre; selection caps at N
     __device__ uint32_t index_of(const Ctx &c, int m) const

@@ -43,7 +43,9 @@ struct SelShared {
 };
 
 // Src concept:
+//   __device__ int segment_of(int launch_index) const;              launch order -> segment id (put the longest first)
 //   struct Ctx;  __device__ Ctx prepare(int seg) const;            per-segment constants (hoisted out of the loops)
+//   __device__ bool active(const Ctx&) const;                       false = this launch leaves the segment untouched
 //   __device__ int  length(const Ctx&) const;                       elements in the segment (memory order)
 //   __device__ int  want(const Ctx&) const;                         K requested (<= kSelMaxK)
 //   __device__ bool load(const Ctx&, int m, uint32_t &key) const;   false = not a candidate
@@ -63,9 +65,10 @@ select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
     uint32_t *vbits = keys + cache_elems;   // [cache_elems/32] validity bits
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    const int seg = blockIdx.x / kClusterSize;
+    const int seg = src.segment_of(blockIdx.x / kClusterSize);   // launch order -> segment (largest segments first)
     const int tid = threadIdx.x, lane = tid & 31;
     const typename Src::Ctx ctx = src.prepare(seg);
+    if (!src.active(ctx)) return;            // uniform over the cluster: nobody reaches a cluster barrier
 
     const int N = src.length(ctx);
     const int K = min(src.want(ctx), kSelMaxK);

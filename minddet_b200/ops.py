@@ -182,10 +182,11 @@ class BboxAssignSample(_Cell):
 
     def __init__(self, pos_iou_thr=0.7, neg_iou_thr=0.3, min_pos_iou=0.3, num_expected_pos=128,
                  num_expected_neg=256, num_expected_total=256, means=(0.0, 0.0, 0.0, 0.0), stds=(1.0, 1.0, 1.0, 1.0),
-                 seed=0, iou_offset=1.0, mode=0):
+                 seed=0, iou_offset=1.0, mode=0, force_full_scan=False):
         self.Sp, self.Sn = num_expected_pos, num_expected_neg
         self.cfg_values = [float(pos_iou_thr), float(neg_iou_thr), float(min_pos_iou), float(iou_offset), float(mode),
-                           float(num_expected_total)] + [float(m) for m in means] + [float(s) for s in stds] + [0.0, 0.0]
+                           float(num_expected_total)] + [float(m) for m in means] + [float(s) for s in stds] + [
+                               1.0 if force_full_scan else 0.0, 0.0]
         s = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.seed_values = [np.int32(np.uint32(s & 0xFFFFFFFF)).item(), np.int32(np.uint32(s >> 32)).item()]
         self._op = Custom(_so("MdAssignSample"), None,
@@ -209,10 +210,11 @@ class BboxAssignSampleForRcnn(_Cell):
 
     def __init__(self, pos_iou_thr=0.5, neg_iou_thr=0.5, min_pos_iou=0.5, num_expected_pos=128,
                  num_expected_neg=384, num_expected_total=512, means=(0.0, 0.0, 0.0, 0.0), stds=(0.1, 0.1, 0.2, 0.2),
-                 seed=0, iou_offset=1.0, mode=0):
+                 seed=0, iou_offset=1.0, mode=0, force_full_scan=False):
         self.Sp, self.Sn = num_expected_pos, num_expected_neg
         self.cfg_values = [float(pos_iou_thr), float(neg_iou_thr), float(min_pos_iou), float(iou_offset), float(mode),
-                           float(num_expected_total)] + [float(m) for m in means] + [float(s) for s in stds] + [0.0, 0.0]
+                           float(num_expected_total)] + [float(m) for m in means] + [float(s) for s in stds] + [
+                               1.0 if force_full_scan else 0.0, 0.0]
         s = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.seed_values = [np.int32(np.uint32(s & 0xFFFFFFFF)).item(), np.int32(np.uint32(s >> 32)).item()]
         self._op = Custom(_so("MdAssignSampleRcnn"), None,

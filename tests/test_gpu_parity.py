@@ -203,15 +203,17 @@ def _anchors_all():
     return np.concatenate([O.anchor_grid(b, h, w, s) for b, (h, w), s in zip(bases, synth.level_shapes(), synth.STRIDES)])
 
 
-@pytest.mark.parametrize("mode", [0, 1])
-def test_assign_sample_rpn_bit_exact(mode):
+@pytest.mark.parametrize("mode,full", [(0, False), (1, False), (0, True)])
+def test_assign_sample_rpn_bit_exact(mode, full):
+    """full=True forces the samplers' full-scan cluster select (the path taken when the short candidate list is
+    not provably exact); both paths must give the oracle's sample."""
     B = 3
     anchors = _anchors_all()
     N = anchors.shape[0]
     gts, _, gvalid = synth.gt_boxes(B, G=128, seed=21)
     rng = np.random.default_rng(22)
     valid = (rng.uniform(0, 1, N) > 0.05).astype(np.uint8)
-    op = BboxAssignSample(0.7, 0.3, 0.3, 128, 256, 256, seed=0x1234567890, mode=mode)
+    op = BboxAssignSample(0.7, 0.3, 0.3, 128, 256, 256, seed=0x1234567890, mode=mode, force_full_scan=full)
     out = op(dev(gts), dev(gvalid).bool(), dev(anchors), dev(valid).bool())
     cfg = O.assign_cfg(0.7, 0.3, 0.3, 128, 256, 256, seed=0x1234567890, mode=mode)
     for b in range(B):
@@ -257,7 +259,8 @@ def test_assign_edge_cases():
     assert int(out["num_pos"][0]) == 0
 
 
-def test_assign_sample_rcnn_bit_exact():
+@pytest.mark.parametrize("full", [False, True])
+def test_assign_sample_rcnn_bit_exact(full):
     B, P = 3, 2000
     rng = np.random.default_rng(31)
     gts, labels, gvalid = synth.gt_boxes(B, G=128, seed=32)
@@ -270,7 +273,7 @@ def test_assign_sample_rcnn_bit_exact():
         props[b, 600:, :4] = synth.rand_boxes(rng, P - 600)
         props[b, :, 4] = np.sort(rng.uniform(0, 1, P))[::-1]
         pmask[b, :1700] = 1
-    op = BboxAssignSampleForRcnn(0.5, 0.5, 0.5, 128, 384, 512, seed=99)
+    op = BboxAssignSampleForRcnn(0.5, 0.5, 0.5, 128, 384, 512, seed=99, force_full_scan=full)
     out = op(dev(gts), dev(labels), dev(pmask).bool(), dev(props), dev(gvalid).bool())
     cfg = O.assign_cfg(0.5, 0.5, 0.5, 128, 384, 512, stds=(0.1, 0.1, 0.2, 0.2), seed=99)
     for b in range(B):
