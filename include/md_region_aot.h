@@ -135,6 +135,23 @@ MD_API int MdRoiAlignBwd(MD_AOT_ARGS);
 MD_API int MdRoiAlignFwdExact(MD_AOT_ARGS);
 MD_API int MdRoiAlignBwdExact(MD_AOT_ARGS);
 
+/* ---- "next" row 3: the reference's OWN GPU symbols, same names and parameter lists
+ * (minddet/models/centerpoint/det3d_ms/ops/test_custom_pytorch/iou3d_nms_kernel.cu:445, :470, :493, :548; python side
+ * iou_gpu.py:14-80), so `ops.Custom("<this .so>:NmsGpu", ...)` replaces `iou_nms.so:NmsGpu` without touching the cell.
+ * Boxes are (N,7) f32 [x, y, z, dx, dy, dz, heading]; N <= 2048 for the NMS symbols.
+ *   BoxesIouBevGpu / BoxesOverlapBevGpu : in boxes_a (N,7) | boxes_b (M,7)        out ans (N,M) f32
+ *   NmsGpu (rotated) / NmsNormalGpu (axis-aligned): in boxes (N,7) score-sorted | thresh f32[1]
+ *                                          out keep (N) int64 zero padded | num_to_keep int32[1]    (IoU > thresh suppresses)
+ *   BoxesIouNmsGpu: device twin of the CPU op boxes_iou_nms_cpu (iou-bev-nms-org.cpp:237-283; nms_cpu.py:10-27):
+ *                   in boxes (N,7) | thresh f32[1]   out keep (N) int32 | count int32[1]
+ *                   (IoU >= thresh suppresses, zero-area boxes are dropped first; N is read from the shape instead of
+ *                   the reference's hard-coded 1000) */
+MD_API int BoxesIouBevGpu(MD_AOT_ARGS);
+MD_API int BoxesOverlapBevGpu(MD_AOT_ARGS);
+MD_API int NmsGpu(MD_AOT_ARGS);
+MD_API int NmsNormalGpu(MD_AOT_ARGS);
+MD_API int BoxesIouNmsGpu(MD_AOT_ARGS);
+
 /* library info: returns a static string "libmdregion <version> sm_100a" */
 MD_API const char *MdVersion(void);
 

@@ -22,7 +22,9 @@ _DTYPE_NAMES = {
 
 SYMBOLS = ("MdAnchorGrid", "MdDecodeClip", "MdDecodeLevel", "MdTopKPerLevel", "MdNms", "MdProposal",
            "MdAssignSample", "MdAssignSampleRcnn", "MdRoiLevels", "MdRoiAlignFwd", "MdRoiAlignBwd",
-           "MdRoiAlignFwdExact", "MdRoiAlignBwdExact")
+           "MdRoiAlignFwdExact", "MdRoiAlignBwdExact",
+           # the reference's own GPU symbols (iou3d_nms_kernel.cu:445-601) + the device twin of boxes_iou_nms_cpu
+           "BoxesIouBevGpu", "BoxesOverlapBevGpu", "NmsGpu", "NmsNormalGpu", "BoxesIouNmsGpu")
 
 ERRORS = {1: "wrong nparam", 2: "bad dtype/shape", 3: "CUDA error", 4: "unsupported size"}
 

@@ -46,6 +46,7 @@ int get_workspace(void *stream, size_t bytes, void **out)
 
 bool is_f32(const char *d) { return d && std::strcmp(d, "float32") == 0; }
 bool is_i32(const char *d) { return d && std::strcmp(d, "int32") == 0; }
+bool is_i64(const char *d) { return d && std::strcmp(d, "int64") == 0; }
 bool is_u8(const char *d) { return d && (std::strcmp(d, "uint8") == 0 || std::strcmp(d, "bool") == 0 || std::strcmp(d, "int8") == 0); }
 
 int64_t numel(int nd, const int64_t *sh)
@@ -319,6 +320,42 @@ static int roialign_bwd_impl(int mode, MD_AOT_ARGS)
     return cuda_rc(md::launch_roialign_bwd(fs, (const float *)params[0], R, P, (const float *)params[2],
                                            (const float *)params[1], ws, mode, (cudaStream_t)stream));
 }
+
+// ---- the reference's own GPU symbols (iou3d_nms_kernel.cu:445-601), same parameter lists ------------------------
+static int bev_pairs_impl(int want_iou, MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam != 3) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    REQ(is_f32(dtypes[0]) && is_f32(dtypes[1]) && is_f32(dtypes[2]));
+    REQ(ndims[0] == 2 && ndims[1] == 2 && shapes[0][1] == 7 && shapes[1][1] == 7);
+    const int na = (int)shapes[0][0], nb = (int)shapes[1][0];
+    REQ(numel(ndims[2], shapes[2]) == (int64_t)na * nb);
+    return cuda_rc(md::launch_bev_pairs((const float *)params[0], na, (const float *)params[1], nb, want_iou,
+                                        (float *)params[2], (cudaStream_t)stream));
+}
+static int bev_nms_impl(int mode, int keep_is_64, MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam != 4) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    REQ(is_f32(dtypes[0]) && is_f32(dtypes[1]) && is_i32(dtypes[3]));
+    REQ(keep_is_64 ? is_i64(dtypes[2]) : is_i32(dtypes[2]));
+    REQ(ndims[0] == 2 && shapes[0][1] == 7 && numel(ndims[1], shapes[1]) >= 1 && numel(ndims[3], shapes[3]) >= 1);
+    const int n = (int)shapes[0][0];
+    REQ(numel(ndims[2], shapes[2]) == n);
+    if (n > 2048) return MD_ERR_SIZE;
+    void *ws = nullptr;
+    int rc = get_workspace(stream, md::bev_nms_workspace_bytes(n), &ws);
+    if (rc) return rc;
+    return cuda_rc(md::launch_bev_nms((const float *)params[0], n, (const float *)params[1], mode, ws, params[2], keep_is_64,
+                                      (int32_t *)params[3], (cudaStream_t)stream));
+}
+int BoxesIouBevGpu(MD_AOT_ARGS) { return bev_pairs_impl(1, nparam, params, ndims, shapes, dtypes, stream, extra); }
+int BoxesOverlapBevGpu(MD_AOT_ARGS) { return bev_pairs_impl(0, nparam, params, ndims, shapes, dtypes, stream, extra); }
+int NmsGpu(MD_AOT_ARGS) { return bev_nms_impl(0, 1, nparam, params, ndims, shapes, dtypes, stream, extra); }
+int NmsNormalGpu(MD_AOT_ARGS) { return bev_nms_impl(1, 1, nparam, params, ndims, shapes, dtypes, stream, extra); }
+int BoxesIouNmsGpu(MD_AOT_ARGS) { return bev_nms_impl(2, 0, nparam, params, ndims, shapes, dtypes, stream, extra); }
 
 int MdRoiAlignFwd(MD_AOT_ARGS) { return roialign_fwd_impl(0, nparam, params, ndims, shapes, dtypes, stream, extra); }
 int MdRoiAlignBwd(MD_AOT_ARGS) { return roialign_bwd_impl(0, nparam, params, ndims, shapes, dtypes, stream, extra); }

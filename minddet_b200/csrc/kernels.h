@@ -51,6 +51,13 @@ cudaError_t launch_assign_sample_rcnn(const float *props5, const uint8_t *prop_m
                                       int32_t *assigned, int32_t *sel_idx, int32_t *pos_gt, int32_t *num_pos,
                                       cudaStream_t s);
 
+// "next" row 3: rotated BEV overlap / IoU / NMS behind the reference's own symbols (bev.cu)
+cudaError_t launch_bev_pairs(const float *boxes_a, int na, const float *boxes_b, int nb, int want_iou, float *out, cudaStream_t s);
+size_t bev_nms_workspace_bytes(int n);
+// mode 0 rotated '>' (NmsGpu), 1 axis-aligned '>' (NmsNormalGpu), 2 rotated '>=' + zero-area pre-removal (boxes_iou_nms_cpu)
+cudaError_t launch_bev_nms(const float *boxes, int n, const float *thr, int mode, void *ws, void *keep, int keep_is_64,
+                           int32_t *num_out, cudaStream_t s);
+
 // a9..a11
 struct FeatSet {
     int L, B, C;

@@ -358,6 +358,7 @@ constexpr int kSweepMaxNb = 32;    // K <= 2048
 
 __global__ void __launch_bounds__(kSweepThreads)
 nms_sweep_kernel(const NmsSegs sg, const unsigned long long *__restrict__ mask,
+                 const unsigned long long *__restrict__ init_removed /* nullable: (nseg, nbp) boxes dead on entry */,
                  int32_t *__restrict__ keep_pos, int keep_stride, uint8_t *__restrict__ keep_mask,
                  int mask_stride, int32_t *__restrict__ count)
 {
@@ -383,6 +384,7 @@ nms_sweep_kernel(const NmsSegs sg, const unsigned long long *__restrict__ mask,
     };
 
     unsigned long long removed = 0ull;   // lane j: word j
+    if (init_removed && warp == 0 && lane < nb) removed = init_removed[(int64_t)seg * nbp + lane];
     int nkept = 0;
     if (nb > 0) issue(0);
     for (int c = 0; c < nb; c++) {
@@ -450,7 +452,18 @@ static cudaError_t run_nms(const NmsSegs &sg, int nseg, int Kmax, const float *c
     if (nb > kSweepMaxNb) return cudaErrorInvalidValue;
     const int tiles = nb * (nb + 1) / 2;
     if (tiles > 0) nms_mask_kernel<<<dim3(tiles, nseg), 64, 0, s>>>(sg, cfg, mask);
-    nms_sweep_kernel<<<nseg, kSweepThreads, 0, s>>>(sg, mask, keep_pos, keep_stride, keep_mask, mask_stride, count);
+    nms_sweep_kernel<<<nseg, kSweepThreads, 0, s>>>(sg, mask, nullptr, keep_pos, keep_stride, keep_mask, mask_stride, count);
+    return cudaGetLastError();
+}
+
+// one segment of n boxes whose bitmask was produced elsewhere (bev.cu)
+cudaError_t launch_nms_sweep_single(const unsigned long long *mask, const unsigned long long *init_removed, int n, int nbp,
+                                    int32_t *keep_pos, uint8_t *keep_mask, int32_t *count, cudaStream_t s)
+{
+    NmsSegs sg{};
+    sg.L = 1; sg.K[0] = n; sg.nbp = nbp; sg.rows_pad = ((n + 63) / 64) * 64;
+    if ((n + 63) / 64 > kSweepMaxNb) return cudaErrorInvalidValue;
+    nms_sweep_kernel<<<1, kSweepThreads, 0, s>>>(sg, mask, init_removed, keep_pos, n, keep_mask, n, count);
     return cudaGetLastError();
 }
 
