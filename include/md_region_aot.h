@@ -152,6 +152,16 @@ MD_API int NmsGpu(MD_AOT_ARGS);
 MD_API int NmsNormalGpu(MD_AOT_ARGS);
 MD_API int BoxesIouNmsGpu(MD_AOT_ARGS);
 
+/* ---- "next" row 1: YOLOv8 post-process; reg_max = 16 (oracle/CONVENTIONS.md #19-#20)
+ *   MdYoloDecode: in pred (B, 64+nc, A) f32 | cfg f32[1+3L] = {L, then per level H, W, stride}
+ *                 out dets (B, A, 6) f32 [x1,y1,x2,y2,score,label]
+ *   MdYoloNms   : in dets (B, A, 6) | cfg f32[3] = {conf_thr, iou_thr, agnostic}
+ *                 out out (B,max_det,6) f32 zero padded | keep_idx (B,max_det) int32 (-1 padded) | count (B) int32
+ *                     | cand_idx (B,nms_pre) int32: the score-sorted candidates that entered NMS (-1 padded)
+ *                 (nms_pre <= 2048 and max_det are read from the output shapes) */
+MD_API int MdYoloDecode(MD_AOT_ARGS);
+MD_API int MdYoloNms(MD_AOT_ARGS);
+
 /* library info: returns a static string "libmdregion <version> sm_100a" */
 MD_API const char *MdVersion(void);
 

@@ -6,7 +6,7 @@ signature) plus the thin host classes that call it.  No CPU path, no fallback: i
 without the built library raises.
 """
 from .ops import (AnchorGenerator, BboxAssignSample, BboxAssignSampleForRcnn, BoundingBoxDecode,  # noqa: F401
-                  NMSWithMask, Proposal, SingleRoIExtractor, TopKPerLevel)
+                  NMSWithMask, Proposal, SingleRoIExtractor, TopKPerLevel, YoloV8PostProcess)
 from ._aot import LIB_PATH, SYMBOLS, AotError, Custom, call_aot, load_library  # noqa: F401
 
 __version__ = "0.1.0"

@@ -357,6 +357,40 @@ int NmsGpu(MD_AOT_ARGS) { return bev_nms_impl(0, 1, nparam, params, ndims, shape
 int NmsNormalGpu(MD_AOT_ARGS) { return bev_nms_impl(1, 1, nparam, params, ndims, shapes, dtypes, stream, extra); }
 int BoxesIouNmsGpu(MD_AOT_ARGS) { return bev_nms_impl(2, 0, nparam, params, ndims, shapes, dtypes, stream, extra); }
 
+int MdYoloDecode(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam != 3) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    REQ(is_f32(dtypes[0]) && is_f32(dtypes[1]) && is_f32(dtypes[2]));
+    REQ(ndims[0] == 3 && shapes[0][1] > 64 && ndims[2] == 3 && shapes[2][0] == shapes[0][0] && shapes[2][1] == shapes[0][2] && shapes[2][2] == 6);
+    REQ(numel(ndims[1], shapes[1]) >= 4);
+    return cuda_rc(md::launch_yolo_decode((const float *)params[0], (int)shapes[0][0], (int)shapes[0][1], (int)shapes[0][2],
+                                          (const float *)params[1], (float *)params[2], (cudaStream_t)stream));
+}
+
+int MdYoloNms(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam != 6) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    REQ(is_f32(dtypes[0]) && is_f32(dtypes[1]) && is_f32(dtypes[2]) && is_i32(dtypes[3]) && is_i32(dtypes[4]) && is_i32(dtypes[5]));
+    REQ(ndims[0] == 3 && shapes[0][2] == 6 && numel(ndims[1], shapes[1]) >= 3);
+    const int B = (int)shapes[0][0], A = (int)shapes[0][1];
+    REQ(ndims[2] == 3 && shapes[2][0] == B && shapes[2][2] == 6);
+    const int max_det = (int)shapes[2][1];
+    REQ(numel(ndims[3], shapes[3]) == (int64_t)B * max_det && numel(ndims[4], shapes[4]) == B);
+    REQ(ndims[5] == 2 && shapes[5][0] == B);
+    const int nms_pre = (int)shapes[5][1];
+    if (nms_pre > 2048 || nms_pre < 1 || A >= (1 << 22)) return MD_ERR_SIZE;
+    void *ws = nullptr;
+    int rc = get_workspace(stream, md::yolo_nms_workspace_bytes(B, nms_pre), &ws);
+    if (rc) return rc;
+    return cuda_rc(md::launch_yolo_nms((const float *)params[0], B, A, (const float *)params[1], ws, nms_pre, max_det,
+                                       (float *)params[2], (int32_t *)params[3], (int32_t *)params[4], (int32_t *)params[5],
+                                       (cudaStream_t)stream));
+}
+
 int MdRoiAlignFwd(MD_AOT_ARGS) { return roialign_fwd_impl(0, nparam, params, ndims, shapes, dtypes, stream, extra); }
 int MdRoiAlignBwd(MD_AOT_ARGS) { return roialign_bwd_impl(0, nparam, params, ndims, shapes, dtypes, stream, extra); }
 int MdRoiAlignFwdExact(MD_AOT_ARGS) { return roialign_fwd_impl(1, nparam, params, ndims, shapes, dtypes, stream, extra); }

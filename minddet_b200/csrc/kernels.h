@@ -58,6 +58,12 @@ size_t bev_nms_workspace_bytes(int n);
 cudaError_t launch_bev_nms(const float *boxes, int n, const float *thr, int mode, void *ws, void *keep, int keep_is_64,
                            int32_t *num_out, cudaStream_t s);
 
+// "next" row 1: YOLOv8 post-process (yolo.cu); reg_max = 16
+cudaError_t launch_yolo_decode(const float *pred, int B, int C, int A, const float *cfg, float *dets, cudaStream_t s);
+size_t yolo_nms_workspace_bytes(int B, int nms_pre);
+cudaError_t launch_yolo_nms(const float *dets, int B, int A, const float *cfg, void *ws, int nms_pre, int max_det,
+                            float *out, int32_t *keep_idx, int32_t *num_out, int32_t *cand_idx, cudaStream_t s);
+
 // a9..a11
 struct FeatSet {
     int L, B, C;

@@ -1,0 +1,23 @@
+// nms.cuh -- segment descriptor + launcher of the bitmask NMS (proposal.cu), shared with yolo.cu
+#pragma once
+#include "kernels.h"
+
+namespace md {
+
+struct NmsSegs {                 // segment s -> boxes + K
+    const float *boxes; int ld;  // rows of `ld` floats, segment stride = seg_stride rows
+    int seg_stride;              // rows between consecutive segments
+    int L;                       // K depends on (s % L)
+    int K[kMaxLv];
+    int nbp;                     // mask row pitch in u64 words (even)
+    int rows_pad;                // mask rows per segment (multiple of 64)
+    const int32_t *labels;       // optional (nseg, seg_stride): only boxes of equal label suppress each other ...
+    const float *agnostic;       // ... unless *agnostic != 0 (device flag); both null for class-agnostic NMS
+};
+
+// cfg: MD_CFG_NMS (thr, offset, inclusive, union_eps) on the device; keep_pos/keep_mask strides in elements
+cudaError_t run_nms(const NmsSegs &sg, int nseg, int Kmax, const float *cfg, unsigned long long *mask,
+                    int32_t *keep_pos, int keep_stride, uint8_t *keep_mask, int mask_stride,
+                    int32_t *count, cudaStream_t s);
+
+}  // namespace md

@@ -11,6 +11,7 @@
 //   * graph order top-k -> gather -> NMS -> gather-keep: center_head.py:435-459.
 // Semantics: oracle/CONVENTIONS.md #1-8, #17; oracle/region_oracle.c (o_topk, o_nms, o_proposal_image).
 #include "kernels.h"
+#include "nms.cuh"
 #include "select.cuh"
 
 namespace md {
@@ -284,15 +285,6 @@ MD_DEVINL bool nms_suppresses(const BoxA &a, const BoxA &b, const NmsCfg &c, boo
     return c.inclusive ? (iou >= c.thr) : (iou > c.thr);
 }
 
-struct NmsSegs {                 // segment s -> boxes + K
-    const float *boxes; int ld;  // rows of `ld` floats, segment stride = seg_stride rows
-    int seg_stride;              // rows between consecutive segments
-    int L;                       // K depends on (s % L)
-    int K[kMaxLv];
-    int nbp;                     // mask row pitch in u64 words (even)
-    int rows_pad;                // mask rows per segment (multiple of 64)
-};
-
 // grid: (triangular tile index, segment); 64 threads: thread r owns row box r of the tile.
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(const NmsSegs sg, const float *__restrict__ cfg, unsigned long long *__restrict__ mask)
@@ -312,10 +304,13 @@ nms_mask_kernel(const NmsSegs sg, const float *__restrict__ cfg, unsigned long l
     const bool zero_cond = c.inclusive ? (0.0f >= c.thr) : (0.0f > c.thr);
     const float *boxes = sg.boxes + (int64_t)seg * sg.seg_stride * sg.ld;
     __shared__ BoxA cols[64];
+    __shared__ int32_t col_label[64];
     const int tid = threadIdx.x;
+    const int32_t *labels = (sg.labels && !(sg.agnostic && __ldg(sg.agnostic) != 0.0f)) ? sg.labels + (int64_t)seg * sg.seg_stride : nullptr;
     {
         const int cidx = j * 64 + tid;
         BoxA b = { 0, 0, 0, 0, 0 };
+        col_label[tid] = (labels && cidx < K) ? labels[cidx] : 0;
         if (cidx < K) {
             const float *p = boxes + (int64_t)cidx * sg.ld;
             b.x1 = __ldg(p); b.y1 = __ldg(p + 1); b.x2 = __ldg(p + 2); b.y2 = __ldg(p + 3);
@@ -335,8 +330,14 @@ nms_mask_kernel(const NmsSegs sg, const float *__restrict__ cfg, unsigned long l
     const int ncol = min(64, K - j * 64);
     const int start = (i == j) ? tid + 1 : 0;
     unsigned long long bits = 0ull;
-    for (int k = start; k < ncol; k++)
-        if (nms_suppresses(a, cols[k], c, zero_cond)) bits |= 1ull << k;
+    if (labels) {
+        const int32_t la = labels[ridx];
+        for (int k = start; k < ncol; k++)
+            if (col_label[k] == la && nms_suppresses(a, cols[k], c, zero_cond)) bits |= 1ull << k;
+    } else {
+        for (int k = start; k < ncol; k++)
+            if (nms_suppresses(a, cols[k], c, zero_cond)) bits |= 1ull << k;
+    }
     mask[((int64_t)seg * sg.rows_pad + ridx) * sg.nbp + j] = bits;
 }
 
@@ -443,9 +444,9 @@ size_t nms_workspace_bytes(int nseg, int Kmax)
     return (size_t)nseg * nb * 64 * nbp * sizeof(unsigned long long) + 256;
 }
 
-static cudaError_t run_nms(const NmsSegs &sg, int nseg, int Kmax, const float *cfg, unsigned long long *mask,
-                           int32_t *keep_pos, int keep_stride, uint8_t *keep_mask, int mask_stride,
-                           int32_t *count, cudaStream_t s)
+cudaError_t run_nms(const NmsSegs &sg, int nseg, int Kmax, const float *cfg, unsigned long long *mask,
+                    int32_t *keep_pos, int keep_stride, uint8_t *keep_mask, int mask_stride,
+                    int32_t *count, cudaStream_t s)
 {
     if (nseg == 0) return cudaSuccess;
     const int nb = (Kmax + 63) / 64;

@@ -277,3 +277,32 @@ class SingleRoIExtractor(_Cell):
         if any(f.requires_grad for f in feats):
             return _RoIAlignFn.apply(self, rois, *feats)
         return self._forward(rois, feats)
+
+
+class YoloV8PostProcess(_Cell):
+    """a14 ("next" row 1).  ``construct(pred)``: pred (B, 64+nc, A) raw head output, anchors level after level ->
+    (dets (B,max_det,6) [x1,y1,x2,y2,score,label], keep_idx (B,max_det), count (B)).  DFL decode of every anchor
+    (``MdYoloDecode``) + class-aware NMS (``MdYoloNms``)."""
+
+    def __init__(self, level_shapes, strides=(8, 16, 32), conf_thr=0.25, iou_thr=0.7, agnostic=False, nms_pre=2048,
+                 max_det=300):
+        self.level_shapes = [tuple(s) for s in level_shapes]
+        self.nms_pre, self.max_det = nms_pre, max_det
+        self.dec_cfg = [float(len(strides))] + [float(v) for (h, w), s in zip(self.level_shapes, strides) for v in (h, w, s)]
+        self.nms_cfg = [float(conf_thr), float(iou_thr), 1.0 if agnostic else 0.0]
+        self._dec = Custom(_so("MdYoloDecode"), lambda p, c: (p[0], p[2], 6), torch.float32)
+        self._nms = Custom(_so("MdYoloNms"), None, (torch.float32, torch.int32, torch.int32, torch.int32))
+        self.last_candidates = None
+
+    def decode(self, pred):
+        return self._dec(pred, self._cfg(self.dec_cfg, pred.device))
+
+    def nms(self, dets):
+        B = dets.shape[0]
+        self._nms.out_shape = lambda d, c: ((B, self.max_det, 6), (B, self.max_det), (B,), (B, self.nms_pre))
+        out, keep_idx, count, cand = self._nms(dets, self._cfg(self.nms_cfg, dets.device))
+        self.last_candidates = cand
+        return out, keep_idx, count
+
+    def construct(self, pred):
+        return self.nms(self.decode(pred))

@@ -353,3 +353,31 @@ def region_path_batch(logits, deltas, bases, strides, feats, gts, gt_labels, gt_
         _p(o["rois"], f32p), _p(o["roi_labels"], i32p), _p(o["roi_mask"], u8p), _p(o["roi_deltas"], f32p),
         _p(o["roi_feats"], f32p), _p(dout, f32p) if cfg.do_backward else None, pdf)
     return o
+
+
+# ------------------------------------------------------------------------------------------------
+# "next" row 1: YOLOv8 post-process (parity unpinned; CONVENTIONS #19-#20)
+def yolo_decode(pred, shapes, strides, reg_max=16):
+    """pred (4*reg_max+nc, A) -> dets (A,6) [x1,y1,x2,y2,score,label]"""
+    pred = _f(pred)
+    A = pred.shape[1]
+    nc = pred.shape[0] - 4 * reg_max
+    L = len(shapes)
+    H = (C.c_int * L)(*[s[0] for s in shapes])
+    W = (C.c_int * L)(*[s[1] for s in shapes])
+    st = (C.c_float * L)(*[float(s) for s in strides])
+    assert sum(h * w for h, w in shapes) == A
+    out = np.zeros((A, 6), np.float32)
+    lib().o_yolo_decode(_p(pred, f32p), reg_max, nc, L, H, W, st, _p(out, f32p))
+    return out
+
+
+def yolo_nms(dets, conf_thr=0.25, nms_pre=2048, iou_thr=0.7, agnostic=False, max_det=300):
+    dets = _f(dets)
+    out = np.zeros((max_det, 6), np.float32)
+    idx = np.zeros(max_det, np.int32)
+    L = lib()
+    L.o_yolo_nms.restype = C.c_int
+    cnt = L.o_yolo_nms(_p(dets, f32p), C.c_int64(dets.shape[0]), C.c_float(conf_thr), int(nms_pre), C.c_float(iou_thr),
+                       int(agnostic), int(max_det), _p(out, f32p), _p(idx, i32p))
+    return out, idx, cnt

@@ -848,3 +848,95 @@ O_API void o_region_path_batch(int B, int L, const float *const *logits, const f
     region_worker(&x);
     for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* a14 ("next" row 1): YOLOv8 post-process.  No reference code exists (README.md:13 names the   */
+/* model only): PARITY UNPINNED, conventions #19-#20 of oracle/CONVENTIONS.md.                 */
+/* ------------------------------------------------------------------------------------------ */
+/* pred: (4*reg_max + nc, A) channel-major, A = sum_l H_l*W_l anchors, level after level, row-major, x fastest.
+ * dets: (A,6) = x1,y1,x2,y2,score,label.  DFL: max-subtracted softmax over reg_max bins, expectation in bins,
+ * sequential fp32 accumulation; box = (cell centre -/+ distance) * stride; score = sigmoid(max logit), first max wins. */
+O_API void o_yolo_decode(const float *pred, int reg_max, int nc, int L, const int *H_, const int *W_,
+                         const float *stride_, float *dets)
+{
+    int64_t A = 0;
+    for (int l = 0; l < L; l++) A += (int64_t)H_[l] * W_[l];
+    int64_t a0 = 0;
+    for (int l = 0; l < L; l++) {
+        for (int y = 0; y < H_[l]; y++)
+            for (int x = 0; x < W_[l]; x++) {
+                const int64_t a = a0 + (int64_t)y * W_[l] + x;
+                float d[4];
+                for (int s = 0; s < 4; s++) {
+                    const float *p = pred + (int64_t)(s * reg_max) * A + a;
+                    float m = p[0];
+                    for (int i = 1; i < reg_max; i++) m = fmaxf(m, p[(int64_t)i * A]);
+                    float den = 0.0f, num = 0.0f;
+                    for (int i = 0; i < reg_max; i++) {
+                        float t = p[(int64_t)i * A] - m;
+                        float e = o_exp(t);
+                        den = den + e;
+                        float w = e * (float)i;
+                        num = num + w;
+                    }
+                    d[s] = num / den;
+                }
+                const float cx = (float)x + 0.5f, cy = (float)y + 0.5f, st = stride_[l];
+                float *o = dets + a * 6;
+                float t;
+                t = cx - d[0]; o[0] = t * st;
+                t = cy - d[1]; o[1] = t * st;
+                t = cx + d[2]; o[2] = t * st;
+                t = cy + d[3]; o[3] = t * st;
+                const float *c = pred + (int64_t)(4 * reg_max) * A + a;
+                float best = c[0];
+                int lab = 0;
+                for (int k = 1; k < nc; k++) {
+                    float v = c[(int64_t)k * A];
+                    if (v > best) { best = v; lab = k; }
+                }
+                o[4] = o_sigmoid(best);
+                o[5] = (float)lab;
+            }
+        a0 += (int64_t)H_[l] * W_[l];
+    }
+}
+
+/* Class-aware NMS of one image: candidates score > conf_thr; the nms_pre best by (score desc, index asc); greedy
+ * with nms_iou(off 0, eps 1e-8, strict >) between boxes of the same label (any label when agnostic); the first
+ * max_det kept rows in order.  out (max_det,6) zero padded, keep_idx (max_det) = anchor index or -1. returns count. */
+O_API int o_yolo_nms(const float *dets, int64_t A, float conf_thr, int nms_pre, float iou_thr, int agnostic,
+                     int max_det, float *out, int32_t *keep_idx)
+{
+    uint64_t *v = (uint64_t *)malloc((size_t)(A > 0 ? A : 1) * sizeof(uint64_t));
+    int64_t n = 0;
+    for (int64_t a = 0; a < A; a++)
+        if (dets[a * 6 + 4] > conf_thr) v[n++] = ((uint64_t)score_key(dets[a * 6 + 4]) << 32) | (uint32_t)~(uint32_t)a;
+    qsort(v, (size_t)n, sizeof(uint64_t), cmp_u64_desc);
+    int64_t K = n < nms_pre ? n : nms_pre;
+    uint8_t *sup = (uint8_t *)calloc((size_t)(K > 0 ? K : 1), 1);
+    int cnt = 0;
+    for (int i = 0; i < max_det; i++) {
+        for (int k = 0; k < 6; k++) out[i * 6 + k] = 0.0f;
+        keep_idx[i] = -1;
+    }
+    for (int64_t i = 0; i < K; i++) {
+        if (sup[i]) continue;
+        const int64_t ai = (int64_t)(uint32_t)~(uint32_t)v[i];
+        const float *bi = dets + ai * 6;
+        if (cnt < max_det) {
+            for (int k = 0; k < 6; k++) out[cnt * 6 + k] = bi[k];
+            keep_idx[cnt] = (int32_t)ai;
+        }
+        cnt++;
+        for (int64_t j = i + 1; j < K; j++) {
+            if (sup[j]) continue;
+            const float *bj = dets + (int64_t)(uint32_t)~(uint32_t)v[j] * 6;
+            if (!agnostic && bi[5] != bj[5]) continue;
+            if (nms_iou(bi, bj, 0.0f, 1e-8f) > iou_thr) sup[j] = 1;
+        }
+    }
+    free(sup);
+    free(v);
+    return cnt < max_det ? cnt : max_det;
+}

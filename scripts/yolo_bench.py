@@ -1,0 +1,34 @@
+"""YOLOv8 post-process at config-5 size (B=64, 640x640, 8400 anchors, 80 classes): decode roofline + NMS time.
+python scripts/yolo_bench.py [iters]"""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from minddet_b200 import YoloV8PostProcess
+
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+B, nc = 64, 80
+shapes, strides = [(80, 80), (40, 40), (20, 20)], (8, 16, 32)
+A = sum(h * w for h, w in shapes)
+g = torch.Generator(device="cuda").manual_seed(0)
+preds = [torch.randn(B, 64 + nc, A, device="cuda", generator=g) for _ in range(2)]      # 2 x 310 MB: alternating inputs > L2
+for p in preds:
+    p[:, 64:] -= 5.0
+op = YoloV8PostProcess(shapes, strides, conf_thr=0.25, nms_pre=2048, max_det=300)
+res = {}
+for name, fn in (("decode", lambda i: op.decode(preds[i & 1])), ("decode+nms", lambda i: op(preds[i & 1]))):
+    for i in range(3):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    res[name] = e0.elapsed_time(e1) / iters * 1e3
+alg = B * A * ((64 + nc) * 4 + 24)
+peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+gbs = alg / (res["decode"] * 1e-6) / 1e9
+print(json.dumps({"workload": "configs[4]: YOLOv8 640x640 batch 64 post-process", "decode_us": res["decode"], "decode_nms_us": res["decode+nms"],
+                  "decode_algorithmic_bytes": alg, "decode_GBps": gbs, "decode_roofline_frac": gbs / peak, "peak_GBps": peak,
+                  "images_per_s_decode_nms": B / (res["decode+nms"] * 1e-6)}))
