@@ -20,26 +20,28 @@ MD_DEVINL float add(float a, float b) { return __fadd_rn(a, b); }
 MD_DEVINL float sub(float a, float b) { return __fsub_rn(a, b); }
 MD_DEVINL float div(float a, float b) { return __fdiv_rn(a, b); }
 
-// Deterministic fp32 exp: floor-based range reduction, Cody-Waite, degree-5 polynomial, every op
-// individually rounded, exact 2^k scaling.  <= 2 ulp.  Input clamped to [-87, 88].
+// Deterministic fp32 exp (oracle: o_exp): round-to-nearest range reduction through the 1.5*2^23 magic constant,
+// Cody-Waite with two FMAs, degree-5 polynomial in Horner form with FMAs (an fma.rn is ONE rounding of the exact
+// product-sum, so it is reproduced bit for bit by fmaf() on the CPU), exact 2^k scaling.  <= 2 ulp.
+// Input clamped to [-87, 88].  18 instructions, all on the FMA/ALU pipes (no F2I / FRND).
 MD_DEVINL float exact_exp(float x)
 {
     x = fminf(x, 88.0f);
     x = fmaxf(x, -87.0f);
-    float t = mul(x, 1.44269504088896341f);
-    float kf = floorf(add(t, 0.5f));
-    float r = sub(x, mul(kf, 0.693359375f));
-    r = sub(r, mul(kf, -2.12194440e-4f));
+    const float t = mul(x, 1.44269504088896341f);
+    const float z = add(t, 12582912.0f);
+    const float kf = sub(z, 12582912.0f);
+    float r = __fmaf_rn(kf, -0.693359375f, x);
+    r = __fmaf_rn(kf, 2.12194440e-4f, r);
     float p = 1.9875691500E-4f;
-    p = add(mul(p, r), 1.3981999507E-3f);
-    p = add(mul(p, r), 8.3334519073E-3f);
-    p = add(mul(p, r), 4.1665795894E-2f);
-    p = add(mul(p, r), 1.6666665459E-1f);
-    p = add(mul(p, r), 5.0000001201E-1f);
-    p = mul(p, mul(r, r));
-    p = add(p, r);
+    p = __fmaf_rn(p, r, 1.3981999507E-3f);
+    p = __fmaf_rn(p, r, 8.3334519073E-3f);
+    p = __fmaf_rn(p, r, 4.1665795894E-2f);
+    p = __fmaf_rn(p, r, 1.6666665459E-1f);
+    p = __fmaf_rn(p, r, 5.0000001201E-1f);
+    p = __fmaf_rn(p, mul(r, r), r);
     p = add(p, 1.0f);
-    int k = (int)kf;
+    const int k = __float_as_int(z) - 0x4B400000;
     return mul(p, __int_as_float((k + 127) << 23));
 }
 

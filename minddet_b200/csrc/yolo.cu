@@ -55,14 +55,17 @@ MD_DEVINL float dfl_expectation(const float (&x)[kRegMax])
 
 template <int V>   // anchors per thread: 4 (128-bit path) or 1
 __global__ void __launch_bounds__(kYoloThreads)
-yolo_decode_kernel(const float *__restrict__ pred, int A, int nc, const float *__restrict__ cfg, float *__restrict__ dets)
+yolo_decode_kernel(const float *__restrict__ pred, int B, int A, int nc, int tiles_per_image, const float *__restrict__ cfg,
+                   float *__restrict__ dets)
 {
     __shared__ YoloLevels lv;                 // dynamic level lookup per anchor: keep it out of local memory
     if (threadIdx.x == 0) lv = load_levels(cfg);
     __syncthreads();
-    const int b = blockIdx.y;
-    const int a0 = (blockIdx.x * kYoloThreads + threadIdx.x) * V;
-    if (a0 >= A) return;
+    // persistent: the grid is one full wave (148 x resident CTAs); tiles = (image, 128*V anchors) are strided
+    for (int tile = blockIdx.x; tile < tiles_per_image * B; tile += gridDim.x) {
+    const int b = tile / tiles_per_image;
+    const int a0 = ((tile - b * tiles_per_image) * kYoloThreads + threadIdx.x) * V;
+    if (a0 >= A) continue;
     const float *base = pred + (int64_t)b * (4 * kRegMax + nc) * A + a0;
     float d[4][V];
 #pragma unroll
@@ -126,6 +129,7 @@ yolo_decode_kernel(const float *__restrict__ pred, int A, int nc, const float *_
 #pragma unroll
         for (int q = 0; q < 6; q++) dst[q] = o[q];
     }
+    }
 }
 
 cudaError_t launch_yolo_decode(const float *pred, int B, int C, int A, const float *cfg, float *dets, cudaStream_t s)
@@ -134,12 +138,20 @@ cudaError_t launch_yolo_decode(const float *pred, int B, int C, int A, const flo
     if (nc < 1) return cudaErrorInvalidValue;
     if (B == 0 || A == 0) return cudaSuccess;
     const bool vec = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dets) & 15) == 0);
-    if (vec) {
-        const int threads = A / 4;
-        yolo_decode_kernel<4><<<dim3((threads + kYoloThreads - 1) / kYoloThreads, B), kYoloThreads, 0, s>>>(pred, A, nc, cfg, dets);
-    } else {
-        yolo_decode_kernel<1><<<dim3((A + kYoloThreads - 1) / kYoloThreads, B), kYoloThreads, 0, s>>>(pred, A, nc, cfg, dets);
+    static int resident[2] = { 0, 0 };                  // CTAs per SM of the two instantiations (occupancy query, once)
+    if (!resident[vec]) {
+        int n = 0;
+        cudaError_t e = vec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, yolo_decode_kernel<4>, kYoloThreads, 0)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, yolo_decode_kernel<1>, kYoloThreads, 0);
+        if (e != cudaSuccess) return e;
+        resident[vec] = n > 0 ? n : 1;
     }
+    const int per = vec ? 4 * kYoloThreads : kYoloThreads;
+    const int tiles_per_image = (A + per - 1) / per;
+    const long long tiles = (long long)tiles_per_image * B;
+    const int grid = (int)(tiles < 148LL * resident[vec] ? tiles : 148LL * resident[vec]);
+    if (vec) yolo_decode_kernel<4><<<grid, kYoloThreads, 0, s>>>(pred, B, A, nc, tiles_per_image, cfg, dets);
+    else yolo_decode_kernel<1><<<grid, kYoloThreads, 0, s>>>(pred, B, A, nc, tiles_per_image, cfg, dets);
     return cudaGetLastError();
 }
 

@@ -33,23 +33,26 @@ static inline uint32_t bits_from_f(float f) { uint32_t u; memcpy(&u, &f, 4); ret
 
 O_API float o_exp(float x)
 {
+    /* fused multiply-adds are single roundings of the exact product-sum (fmaf here, fma.rn.f32 on the device), so
+     * the result is still bit-reproducible; round-to-nearest via the 1.5*2^23 magic constant keeps the whole
+     * function on plain add/mul/fma units (no float<->int conversion instructions on the device). */
     if (x > 88.0f) x = 88.0f;
     if (x < -87.0f) x = -87.0f;
     float t = x * 1.44269504088896341f;
-    float kf = floorf(t + 0.5f);
-    float r = x - kf * 0.693359375f;
-    r = r - kf * -2.12194440e-4f;
+    float z = t + 12582912.0f;
+    float kf = z - 12582912.0f;
+    float r = fmaf(kf, -0.693359375f, x);
+    r = fmaf(kf, 2.12194440e-4f, r);
     float p = 1.9875691500E-4f;
-    p = p * r; p = p + 1.3981999507E-3f;
-    p = p * r; p = p + 8.3334519073E-3f;
-    p = p * r; p = p + 4.1665795894E-2f;
-    p = p * r; p = p + 1.6666665459E-1f;
-    p = p * r; p = p + 5.0000001201E-1f;
+    p = fmaf(p, r, 1.3981999507E-3f);
+    p = fmaf(p, r, 8.3334519073E-3f);
+    p = fmaf(p, r, 4.1665795894E-2f);
+    p = fmaf(p, r, 1.6666665459E-1f);
+    p = fmaf(p, r, 5.0000001201E-1f);
     float r2 = r * r;
-    p = p * r2;
-    p = p + r;
+    p = fmaf(p, r2, r);
     p = p + 1.0f;
-    int k = (int)kf;
+    int32_t k = (int32_t)bits_from_f(z) - 0x4B400000;
     float scale = f_from_bits((uint32_t)(k + 127) << 23);
     return p * scale;
 }
