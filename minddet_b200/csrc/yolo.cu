@@ -4,11 +4,13 @@
 //
 // Decode is the streaming kernel of this repo: (4*16 + nc) * 4 bytes read and 24 bytes written per anchor
 // (algorithmic 4.84 MB + 0.20 MB per 640x640 image), no reuse, so it is judged against the HBM roofline.
-// Each thread owns 4 consecutive anchors: every channel plane is read with one 128-bit streaming load per thread
-// (512 contiguous bytes per warp), a side's 16 bins live in registers, and the 4 x 6 results leave as six 128-bit
-// stores.  All arithmetic that decides a label or a keep index is individually rounded (bit-exact vs the oracle).
+// Each thread owns V consecutive anchors (V = 2 by default: 64 registers, 8 CTAs/SM; V = 4 is the 128-bit variant):
+// every channel plane is read with one vector streaming load per thread (256-512 contiguous bytes per warp), a
+// side's 16 bins live in registers, and the V x 6 results leave as 128-bit stores; the grid is one persistent wave.  All arithmetic that decides a label or a keep index is individually rounded (bit-exact vs the oracle).
 // NMS re-uses the region path's machinery: cluster radix select (top nms_pre of the candidates above the confidence
 // threshold, sorted), label-aware 64-bit bitmask tiles, on-device sweep.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "nms.cuh"
 #include "select.cuh"
@@ -48,7 +50,7 @@ MD_DEVINL float dfl_expectation(const float (&x)[kRegMax])
     for (int i = 0; i < kRegMax; i++) {
         const float e = exact_exp(sub(x[i], m));
         den = add(den, e);
-        num = add(num, mul(e, (float)i));
+        num = __fmaf_rn(e, (float)i, num);
     }
     return div(num, den);
 }
@@ -77,6 +79,9 @@ yolo_decode_kernel(const float *__restrict__ pred, int B, int A, int nc, int til
             if (V == 4) {
                 const float4 v = ldg_stream(reinterpret_cast<const float4 *>(p));
                 x[0][i] = v.x; x[1 % V][i] = v.y; x[2 % V][i] = v.z; x[3 % V][i] = v.w;
+            } else if (V == 2) {
+                const float2 v = __ldcs(reinterpret_cast<const float2 *>(p));
+                x[0][i] = v.x; x[1 % V][i] = v.y;
             } else {
                 x[0][i] = __ldg(p);
             }
@@ -90,12 +95,15 @@ yolo_decode_kernel(const float *__restrict__ pred, int B, int A, int nc, int til
         const float *c = base + (int64_t)(4 * kRegMax) * A;
 #pragma unroll
         for (int j = 0; j < V; j++) { best[j] = -3.0e38f; lab[j] = 0; }
-#pragma unroll 8
+#pragma unroll 16
         for (int k = 0; k < nc; k++) {
             float v[V];
             if (V == 4) {
                 const float4 t = ldg_stream(reinterpret_cast<const float4 *>(c + (int64_t)k * A));
                 v[0] = t.x; v[1 % V] = t.y; v[2 % V] = t.z; v[3 % V] = t.w;
+            } else if (V == 2) {
+                const float2 t = __ldcs(reinterpret_cast<const float2 *>(c + (int64_t)k * A));
+                v[0] = t.x; v[1 % V] = t.y;
             } else {
                 v[0] = __ldg(c + (int64_t)k * A);
             }
@@ -125,6 +133,10 @@ yolo_decode_kernel(const float *__restrict__ pred, int B, int A, int nc, int til
 #pragma unroll
         for (int q = 0; q < 6; q++)
             stg_stream(reinterpret_cast<float4 *>(dst) + q, make_float4(o[4 * q], o[(4 * q + 1) % (V * 6)], o[(4 * q + 2) % (V * 6)], o[(4 * q + 3) % (V * 6)]));
+    } else if (V == 2) {
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+            stg_stream(reinterpret_cast<float4 *>(dst) + q, make_float4(o[4 * q], o[(4 * q + 1) % (V * 6)], o[(4 * q + 2) % (V * 6)], o[(4 * q + 3) % (V * 6)]));
     } else {
 #pragma unroll
         for (int q = 0; q < 6; q++) dst[q] = o[q];
@@ -138,20 +150,21 @@ cudaError_t launch_yolo_decode(const float *pred, int B, int C, int A, const flo
     if (nc < 1) return cudaErrorInvalidValue;
     if (B == 0 || A == 0) return cudaSuccess;
     const bool vec = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dets) & 15) == 0);
-    static int resident[2] = { 0, 0 };                  // CTAs per SM of the two instantiations (occupancy query, once)
-    if (!resident[vec]) {
+    const char *ev = getenv("MD_YOLO_V");
+    const int V = !vec ? 1 : (ev ? atoi(ev) : 2);   // measured at config 5: V=2 61 us, V=1 63 us, V=4 66 us (occupancy wins)
+    auto kern = V == 4 ? yolo_decode_kernel<4> : (V == 2 ? yolo_decode_kernel<2> : yolo_decode_kernel<1>);
+    static int resident[5] = { 0, 0, 0, 0, 0 };         // CTAs per SM per instantiation (occupancy query, once)
+    if (!resident[V]) {
         int n = 0;
-        cudaError_t e = vec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, yolo_decode_kernel<4>, kYoloThreads, 0)
-                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, yolo_decode_kernel<1>, kYoloThreads, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kYoloThreads, 0);
         if (e != cudaSuccess) return e;
-        resident[vec] = n > 0 ? n : 1;
+        resident[V] = n > 0 ? n : 1;
     }
-    const int per = vec ? 4 * kYoloThreads : kYoloThreads;
+    const int per = V * kYoloThreads;
     const int tiles_per_image = (A + per - 1) / per;
     const long long tiles = (long long)tiles_per_image * B;
-    const int grid = (int)(tiles < 148LL * resident[vec] ? tiles : 148LL * resident[vec]);
-    if (vec) yolo_decode_kernel<4><<<grid, kYoloThreads, 0, s>>>(pred, B, A, nc, tiles_per_image, cfg, dets);
-    else yolo_decode_kernel<1><<<grid, kYoloThreads, 0, s>>>(pred, B, A, nc, tiles_per_image, cfg, dets);
+    const int grid = (int)(tiles < 148LL * resident[V] ? tiles : 148LL * resident[V]);
+    kern<<<grid, kYoloThreads, 0, s>>>(pred, B, A, nc, tiles_per_image, cfg, dets);
     return cudaGetLastError();
 }
 

@@ -879,8 +879,7 @@ O_API void o_yolo_decode(const float *pred, int reg_max, int nc, int L, const in
                         float t = p[(int64_t)i * A] - m;
                         float e = o_exp(t);
                         den = den + e;
-                        float w = e * (float)i;
-                        num = num + w;
+                        num = fmaf(e, (float)i, num);
                     }
                     d[s] = num / den;
                 }
