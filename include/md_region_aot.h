@@ -152,6 +152,13 @@ MD_API int NmsGpu(MD_AOT_ARGS);
 MD_API int NmsNormalGpu(MD_AOT_ARGS);
 MD_API int BoxesIouNmsGpu(MD_AOT_ARGS);
 
+/* ---- "next" row 2: Mask R-CNN mask targets (oracle/CONVENTIONS.md #21).  The 14x14 mask
+ * RoIAlign itself is MdRoiAlignFwd / MdRoiAlignBwd with a (R,C,14,14) output.
+ *   MdMaskTargets: in gt_masks (B,G,H,W) uint8/bool | rois (R,5) f32 [batch,x1,y1,x2,y2] | gt_idx (R) int32 (<0: none)
+ *                     | cfg f32[1] = {sample_num}
+ *                  out targets (R,M,M) uint8/bool        (M is read from the output shape; 28 upstream) */
+MD_API int MdMaskTargets(MD_AOT_ARGS);
+
 /* ---- "next" row 1: YOLOv8 post-process; reg_max = 16 (oracle/CONVENTIONS.md #19-#20)
  *   MdYoloDecode: in pred (B, 64+nc, A) f32 | cfg f32[1+3L] = {L, then per level H, W, stride}
  *                 out dets (B, A, 6) f32 [x1,y1,x2,y2,score,label]

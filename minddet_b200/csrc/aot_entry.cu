@@ -357,6 +357,20 @@ int NmsGpu(MD_AOT_ARGS) { return bev_nms_impl(0, 1, nparam, params, ndims, shape
 int NmsNormalGpu(MD_AOT_ARGS) { return bev_nms_impl(1, 1, nparam, params, ndims, shapes, dtypes, stream, extra); }
 int BoxesIouNmsGpu(MD_AOT_ARGS) { return bev_nms_impl(2, 0, nparam, params, ndims, shapes, dtypes, stream, extra); }
 
+int MdMaskTargets(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam != 5) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    REQ(is_u8(dtypes[0]) && is_f32(dtypes[1]) && is_i32(dtypes[2]) && is_f32(dtypes[3]) && is_u8(dtypes[4]));
+    REQ(ndims[0] == 4 && ndims[1] == 2 && shapes[1][1] == 5 && numel(ndims[3], shapes[3]) >= 1);
+    const int R = (int)shapes[1][0];
+    REQ(numel(ndims[2], shapes[2]) == R && ndims[4] == 3 && shapes[4][0] == R && shapes[4][1] == shapes[4][2]);
+    return cuda_rc(md::launch_mask_targets((const uint8_t *)params[0], (int)shapes[0][0], (int)shapes[0][1], (int)shapes[0][2],
+                                           (int)shapes[0][3], (const float *)params[1], (const int32_t *)params[2], R,
+                                           (int)shapes[4][1], (const float *)params[3], (uint8_t *)params[4], (cudaStream_t)stream));
+}
+
 int MdYoloDecode(MD_AOT_ARGS)
 {
     (void)extra;

@@ -70,6 +70,9 @@ struct FeatSet {
     int H[kMaxLv], W[kMaxLv];
     float *feat[kMaxLv];    // (B,C,H,W)  (const for fwd, written by bwd)
 };
+// a13: masks (B,G,H,W) u8, rois5 (R,5) [batch,x1,y1,x2,y2], gt_idx (R) -> out (R,M,M) u8; cfg = {sample_num}
+cudaError_t launch_mask_targets(const uint8_t *masks, int B, int G, int H, int W, const float *rois5, const int32_t *gt_idx,
+                                int R, int M, const float *cfg, uint8_t *out, cudaStream_t s);
 cudaError_t launch_roi_levels(const float *rois5, int R, const float *cfg, int32_t *out, cudaStream_t s);
 size_t roialign_workspace_bytes(int R);
 // mode (cfg slot MD_ROI_MODE): 0 = TMA separable kernels (+ gather for RoIs they decline), 1 = gather only

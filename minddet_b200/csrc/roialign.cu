@@ -107,6 +107,50 @@ roialign_bwd_gather_kernel(const RoiFeat f, const float *__restrict__ rois5, int
     }
 }
 
+// ---- a13: mask targets = RoIAlign (scale 1) of the assigned gt's uint8 mask plane, binarised with >= 0.5 --------------
+// One thread per output pixel; op order identical to oracle/region_oracle.c:o_mask_targets (bit-exact).
+__global__ void __launch_bounds__(256)
+mask_target_kernel(const uint8_t *__restrict__ masks, int B, int G, int H, int W, const float *__restrict__ rois5,
+                   const int32_t *__restrict__ gt_idx, int R, int M, const float *__restrict__ cfg, uint8_t *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)R * M * M) return;
+    const int S = (int)__ldg(cfg);
+    const int r = (int)(i / (M * M)), pq = (int)(i - (int64_t)r * M * M), ph = pq / M, pw = pq - ph * M;
+    const float *roi = rois5 + (int64_t)r * 5;
+    const int b = (int)__ldg(roi), g = __ldg(gt_idx + r);
+    uint8_t res = 0;
+    if (g >= 0 && g < G && b >= 0 && b < B) {
+        const uint8_t *plane = masks + ((int64_t)b * G + g) * H * W;
+        const float sw = mul(__ldg(roi + 1), 1.0f), sh = mul(__ldg(roi + 2), 1.0f);
+        const float ew = mul(add(__ldg(roi + 3), 0.0f), 1.0f), eh = mul(add(__ldg(roi + 4), 0.0f), 1.0f);
+        const float rw = fmaxf(sub(ew, sw), 1.0f), rh = fmaxf(sub(eh, sh), 1.0f);
+        const float bw = div(rw, (float)M), bh = div(rh, (float)M);
+        float sum = 0.0f;
+        for (int iy = 0; iy < S; iy++)
+            for (int ix = 0; ix < S; ix++) {
+                float y = sample_coord(sh, bh, ph, iy, S), x = sample_coord(sw, bw, pw, ix, S);
+                if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) continue;
+                const Tap t = make_tap(y, x, H, W);
+                float v = add(mul(t.w1, (float)plane[t.o1]), mul(t.w2, (float)plane[t.o2]));
+                v = add(v, mul(t.w3, (float)plane[t.o3]));
+                v = add(v, mul(t.w4, (float)plane[t.o4]));
+                sum = add(sum, v);
+            }
+        res = div(sum, (float)(S * S)) >= 0.5f ? 1 : 0;
+    }
+    out[i] = res;
+}
+
+cudaError_t launch_mask_targets(const uint8_t *masks, int B, int G, int H, int W, const float *rois5, const int32_t *gt_idx,
+                                int R, int M, const float *cfg, uint8_t *out, cudaStream_t s)
+{
+    const int64_t n = (int64_t)R * M * M;
+    if (n == 0) return cudaSuccess;
+    mask_target_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(masks, B, G, H, W, rois5, gt_idx, R, M, cfg, out);
+    return cudaGetLastError();
+}
+
 static RoiFeat to_roifeat(const FeatSet &fs, const float *cfg)
 {
     RoiFeat f{};

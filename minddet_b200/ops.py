@@ -306,3 +306,18 @@ class YoloV8PostProcess(_Cell):
 
     def construct(self, pred):
         return self.nms(self.decode(pred))
+
+
+class MaskTargets(_Cell):
+    """a13 ("next" row 2).  ``construct(gt_masks (B,G,H,W) bool/uint8, rois (R,5), gt_idx (R) int32)`` ->
+    (R,M,M) bool mask targets: the assigned gt's mask cropped to the RoI and resized by RoIAlign, >= 0.5."""
+
+    def __init__(self, mask_size=28, sample_num=2):
+        self.M = mask_size
+        self.cfg_values = [float(sample_num)]
+        self._op = Custom(_so("MdMaskTargets"), None, torch.bool)
+
+    def construct(self, gt_masks, rois, gt_idx):
+        R, M = rois.shape[0], self.M
+        self._op.out_shape = lambda *s: (R, M, M)
+        return self._op(gt_masks, rois, gt_idx, self._cfg(self.cfg_values, rois.device))

@@ -381,3 +381,15 @@ def yolo_nms(dets, conf_thr=0.25, nms_pre=2048, iou_thr=0.7, agnostic=False, max
     cnt = L.o_yolo_nms(_p(dets, f32p), C.c_int64(dets.shape[0]), C.c_float(conf_thr), int(nms_pre), C.c_float(iou_thr),
                        int(agnostic), int(max_det), _p(out, f32p), _p(idx, i32p))
     return out, idx, cnt
+
+
+def mask_targets(masks, rois, gt_idx, M=28, S=2):
+    """masks (G,H,W) uint8, rois (R,4), gt_idx (R) int32 -> (R,M,M) uint8   (a13, parity unpinned, CONVENTIONS #21)"""
+    masks = np.ascontiguousarray(masks, np.uint8)
+    rois = _f(rois)
+    gt_idx = np.ascontiguousarray(gt_idx, np.int32)
+    G, H, W = masks.shape
+    R = rois.shape[0]
+    out = np.zeros((R, M, M), np.uint8)
+    lib().o_mask_targets(_p(masks, u8p), G, H, W, _p(rois, f32p), _p(gt_idx, i32p), C.c_int64(R), M, S, _p(out, u8p))
+    return out

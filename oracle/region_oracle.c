@@ -942,3 +942,39 @@ O_API int o_yolo_nms(const float *dets, int64_t A, float conf_thr, int nms_pre, 
     free(v);
     return cnt < max_det ? cnt : max_det;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* a13 ("next" row 2): Mask R-CNN mask targets.  No reference code (README.md:7): PARITY        */
+/* UNPINNED, convention #21.                                                                   */
+/* ------------------------------------------------------------------------------------------ */
+/* masks (G,H,W) uint8 {0,1}; rois (R,4) image coordinates; gt_idx (R) row of `masks` per RoI (<0: empty target);
+ * out (R,M,M) uint8.  RoIAlign (aligned=False, scale 1, S x S samples averaged, same tap rules as a10) of the gt's
+ * mask plane, binarised with >= 0.5. */
+O_API void o_mask_targets(const uint8_t *masks, int G, int H, int W, const float *rois, const int32_t *gt_idx,
+                          int64_t R, int M, int S, uint8_t *out)
+{
+    for (int64_t r = 0; r < R; r++) {
+        uint8_t *o = out + r * M * M;
+        const int g = gt_idx[r];
+        if (g < 0 || g >= G) { memset(o, 0, (size_t)M * M); continue; }
+        const uint8_t *plane = masks + (int64_t)g * H * W;
+        float sw, sh, bw, bh;
+        roi_geometry(rois + r * 4, 1.0f, 0.0f, M, &sw, &sh, &bw, &bh);
+        for (int ph = 0; ph < M; ph++)
+            for (int pw = 0; pw < M; pw++) {
+                float sum = 0.0f;
+                for (int iy = 0; iy < S; iy++)
+                    for (int ix = 0; ix < S; ix++) {
+                        Tap t = make_tap(sample_coord(sh, bh, ph, iy, S), sample_coord(sw, bw, pw, ix, S), H, W);
+                        if (!t.ok) continue;
+                        float v = t.w1 * (float)plane[(int64_t)t.yl * W + t.xl];
+                        float u = t.w2 * (float)plane[(int64_t)t.yl * W + t.xh]; v = v + u;
+                        u = t.w3 * (float)plane[(int64_t)t.yh * W + t.xl]; v = v + u;
+                        u = t.w4 * (float)plane[(int64_t)t.yh * W + t.xh]; v = v + u;
+                        sum = sum + v;
+                    }
+                float avg = sum / (float)(S * S);
+                o[ph * M + pw] = avg >= 0.5f ? 1 : 0;
+            }
+    }
+}
