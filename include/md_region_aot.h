@@ -152,6 +152,15 @@ MD_API int NmsGpu(MD_AOT_ARGS);
 MD_API int NmsNormalGpu(MD_AOT_ARGS);
 MD_API int BoxesIouNmsGpu(MD_AOT_ARGS);
 
+/* ---- "next" row 4: BoundingBoxEncode + RCNN-head post-process (oracle/CONVENTIONS.md #9, #22)
+ *   MdEncode: in proposals (K,4) | gts (K,4) | cfg f32[8] = {means[4], stds[4]}      out deltas (K,4) f32
+ *   MdRcnnPostProcess: in rois (B,P,4|5) f32 | roi_valid (B,P) uint8/bool | cls_logits (B,P,nc+1) f32 (class 0 = background)
+ *                         | bbox_deltas (B,P,(nc+1)*4) f32 | cfg f32[13] = MD_CFG_DECODE (0..10) + {score_thr, iou_thr}
+ *                      out dets (B,max_det,6) f32 [x1,y1,x2,y2,score,label] | keep_idx (B,max_det) int32 = roi*(nc+1)+class, -1 padded
+ *                         | count (B) int32 | cand_idx (B,nms_pre) int32 (score-sorted NMS candidates, -1 padded; nms_pre <= 2048) */
+MD_API int MdEncode(MD_AOT_ARGS);
+MD_API int MdRcnnPostProcess(MD_AOT_ARGS);
+
 /* ---- "next" row 2: Mask R-CNN mask targets (oracle/CONVENTIONS.md #21).  The 14x14 mask
  * RoIAlign itself is MdRoiAlignFwd / MdRoiAlignBwd with a (R,C,14,14) output.
  *   MdMaskTargets: in gt_masks (B,G,H,W) uint8/bool | rois (R,5) f32 [batch,x1,y1,x2,y2] | gt_idx (R) int32 (<0: none)

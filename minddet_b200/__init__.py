@@ -5,7 +5,7 @@ FPN RoIAlign fwd/bwd, as ONE C-ABI library (lib/libmdregion.so, MindSpore ops.Cu
 signature) plus the thin host classes that call it.  No CPU path, no fallback: importing the ops
 without the built library raises.
 """
-from .ops import (AnchorGenerator, MaskTargets, BboxAssignSample, BboxAssignSampleForRcnn, BoundingBoxDecode,  # noqa: F401
+from .ops import (AnchorGenerator, BoundingBoxEncode, MaskTargets, RcnnPostProcess, BboxAssignSample, BboxAssignSampleForRcnn, BoundingBoxDecode,  # noqa: F401
                   NMSWithMask, Proposal, SingleRoIExtractor, TopKPerLevel, YoloV8PostProcess)
 from ._aot import LIB_PATH, SYMBOLS, AotError, Custom, call_aot, load_library  # noqa: F401
 

@@ -25,7 +25,7 @@ SYMBOLS = ("MdAnchorGrid", "MdDecodeClip", "MdDecodeLevel", "MdTopKPerLevel", "M
            "MdRoiAlignFwdExact", "MdRoiAlignBwdExact",
            # the reference's own GPU symbols (iou3d_nms_kernel.cu:445-601) + the device twin of boxes_iou_nms_cpu
            "BoxesIouBevGpu", "BoxesOverlapBevGpu", "NmsGpu", "NmsNormalGpu", "BoxesIouNmsGpu",
-           "MdYoloDecode", "MdYoloNms", "MdMaskTargets")
+           "MdYoloDecode", "MdYoloNms", "MdMaskTargets", "MdEncode", "MdRcnnPostProcess")
 
 ERRORS = {1: "wrong nparam", 2: "bad dtype/shape", 3: "CUDA error", 4: "unsupported size"}
 

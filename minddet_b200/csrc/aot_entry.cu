@@ -357,6 +357,44 @@ int NmsGpu(MD_AOT_ARGS) { return bev_nms_impl(0, 1, nparam, params, ndims, shape
 int NmsNormalGpu(MD_AOT_ARGS) { return bev_nms_impl(1, 1, nparam, params, ndims, shapes, dtypes, stream, extra); }
 int BoxesIouNmsGpu(MD_AOT_ARGS) { return bev_nms_impl(2, 0, nparam, params, ndims, shapes, dtypes, stream, extra); }
 
+int MdRcnnPostProcess(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam != 9) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    REQ(is_f32(dtypes[0]) && is_u8(dtypes[1]) && is_f32(dtypes[2]) && is_f32(dtypes[3]) && is_f32(dtypes[4]));
+    REQ(is_f32(dtypes[5]) && is_i32(dtypes[6]) && is_i32(dtypes[7]) && is_i32(dtypes[8]));
+    REQ(ndims[0] == 3 && (shapes[0][2] == 4 || shapes[0][2] == 5) && ndims[2] == 3);
+    const int B = (int)shapes[0][0], P = (int)shapes[0][1], nc1 = (int)shapes[2][2];
+    REQ(shapes[2][0] == B && shapes[2][1] == P && nc1 >= 2);
+    REQ(numel(ndims[1], shapes[1]) == (int64_t)B * P && numel(ndims[3], shapes[3]) == (int64_t)B * P * nc1 * 4);
+    REQ(numel(ndims[4], shapes[4]) >= 13);
+    REQ(ndims[5] == 3 && shapes[5][0] == B && shapes[5][2] == 6);
+    const int max_det = (int)shapes[5][1];
+    REQ(numel(ndims[6], shapes[6]) == (int64_t)B * max_det && numel(ndims[7], shapes[7]) == B && ndims[8] == 2 && shapes[8][0] == B);
+    const int nms_pre = (int)shapes[8][1];
+    if (nms_pre > 2048 || nms_pre < 1 || (int64_t)P * nc1 >= (1 << 22)) return MD_ERR_SIZE;
+    void *ws = nullptr;
+    int rc = get_workspace(stream, md::rcnn_post_workspace_bytes(B, P, nc1, nms_pre), &ws);
+    if (rc) return rc;
+    return cuda_rc(md::launch_rcnn_post((const float *)params[0], (int)shapes[0][2], (const uint8_t *)params[1], (const float *)params[2],
+                                        (const float *)params[3], B, P, nc1, (const float *)params[4], ws, nms_pre, max_det,
+                                        (float *)params[5], (int32_t *)params[6], (int32_t *)params[7], (int32_t *)params[8],
+                                        (cudaStream_t)stream));
+}
+
+int MdEncode(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam != 4) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    for (int i = 0; i < 4; i++) REQ(is_f32(dtypes[i]));
+    REQ(ndims[0] == 2 && shapes[0][1] == 4 && ndims[1] == 2 && shapes[1][1] == 4 && shapes[1][0] == shapes[0][0]);
+    REQ(numel(ndims[2], shapes[2]) >= 8 && numel(ndims[3], shapes[3]) == shapes[0][0] * 4);
+    return cuda_rc(md::launch_encode_rows((const float *)params[0], (const float *)params[1], shapes[0][0], (const float *)params[2],
+                                          (float *)params[3], (cudaStream_t)stream));
+}
+
 int MdMaskTargets(MD_AOT_ARGS)
 {
     (void)extra;

@@ -64,6 +64,13 @@ size_t yolo_nms_workspace_bytes(int B, int nms_pre);
 cudaError_t launch_yolo_nms(const float *dets, int B, int A, const float *cfg, void *ws, int nms_pre, int max_det,
                             float *out, int32_t *keep_idx, int32_t *num_out, int32_t *cand_idx, cudaStream_t s);
 
+// "next" row 4: RCNN-head post-process + BoundingBoxEncode (rcnn_post.cu)
+size_t rcnn_post_workspace_bytes(int B, int P, int nc1, int nms_pre);
+cudaError_t launch_rcnn_post(const float *rois, int roi_ld, const uint8_t *roi_valid, const float *logits, const float *deltas,
+                             int B, int P, int nc1, const float *cfg, void *ws, int nms_pre, int max_det,
+                             float *out, int32_t *keep_idx, int32_t *num_out, int32_t *cand_idx, cudaStream_t s);
+cudaError_t launch_encode_rows(const float *props, const float *gts, int64_t K, const float *cfg, float *out, cudaStream_t s);
+
 // a9..a11
 struct FeatSet {
     int L, B, C;

@@ -321,3 +321,34 @@ class MaskTargets(_Cell):
         R, M = rois.shape[0], self.M
         self._op.out_shape = lambda *s: (R, M, M)
         return self._op(gt_masks, rois, gt_idx, self._cfg(self.cfg_values, rois.device))
+
+
+class BoundingBoxEncode(_Cell):
+    """a2 inverse (legacy +1 bbox2delta) on rows: ``construct(proposals (K,4), gts (K,4))`` -> deltas (K,4)."""
+
+    def __init__(self, means=(0.0, 0.0, 0.0, 0.0), stds=(1.0, 1.0, 1.0, 1.0)):
+        self.cfg_values = [float(m) for m in means] + [float(s) for s in stds]
+        self._op = Custom(_so("MdEncode"), lambda p, g, c: p, torch.float32)
+
+    def construct(self, proposals, gts):
+        return self._op(proposals, gts, self._cfg(self.cfg_values, proposals.device))
+
+
+class RcnnPostProcess(_Cell):
+    """"next" row 4: ``construct(rois (B,P,4|5), roi_valid (B,P), cls_logits (B,P,nc+1), bbox_deltas (B,P,(nc+1)*4))`` ->
+    (dets (B,max_det,6) [x1,y1,x2,y2,score,label], keep_idx, count).  Softmax, per-class decode, score threshold,
+    class-aware NMS, top max_det -- one aot call."""
+
+    def __init__(self, img_shape, score_thr=0.05, iou_thr=0.5, max_det=100, nms_pre=2048, means=(0.0, 0.0, 0.0, 0.0),
+                 stds=(0.1, 0.1, 0.2, 0.2), max_ratio=MAX_RATIO):
+        self.max_det, self.nms_pre = max_det, nms_pre
+        self.cfg_values = decode_cfg(img_shape, means, stds, max_ratio) + [float(score_thr), float(iou_thr)]
+        self._op = Custom(_so("MdRcnnPostProcess"), None, (torch.float32, torch.int32, torch.int32, torch.int32))
+        self.last_candidates = None
+
+    def construct(self, rois, roi_valid, cls_logits, bbox_deltas):
+        B = rois.shape[0]
+        self._op.out_shape = lambda *s: ((B, self.max_det, 6), (B, self.max_det), (B,), (B, self.nms_pre))
+        out, keep_idx, count, cand = self._op(rois, roi_valid, cls_logits, bbox_deltas, self._cfg(self.cfg_values, rois.device))
+        self.last_candidates = cand
+        return out, keep_idx, count

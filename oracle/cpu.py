@@ -393,3 +393,28 @@ def mask_targets(masks, rois, gt_idx, M=28, S=2):
     out = np.zeros((R, M, M), np.uint8)
     lib().o_mask_targets(_p(masks, u8p), G, H, W, _p(rois, f32p), _p(gt_idx, i32p), C.c_int64(R), M, S, _p(out, u8p))
     return out
+
+
+def softmax_rows(logits):
+    logits = _f(logits)
+    out = np.empty_like(logits)
+    lib().o_softmax_rows(_p(logits, f32p), C.c_int64(logits.shape[0]), int(logits.shape[1]), _p(out, f32p))
+    return out
+
+
+def rcnn_post(rois, roi_valid, logits, deltas, img_h, img_w, means=(0, 0, 0, 0), stds=(0.1, 0.1, 0.2, 0.2),
+              max_ratio=MAX_RATIO, score_thr=0.05, nms_pre=2048, iou_thr=0.5, max_det=100):
+    """'next' row 4 (parity unpinned, CONVENTIONS #22) -> (out (max_det,6), keep_idx (max_det), count)"""
+    rois, logits, deltas = _f(rois), _f(logits), _f(deltas)
+    P, nc1 = logits.shape
+    valid = np.ascontiguousarray(roi_valid, np.uint8) if roi_valid is not None else None
+    m = (C.c_float * 4)(*[float(x) for x in means])
+    s = (C.c_float * 4)(*[float(x) for x in stds])
+    out = np.zeros((max_det, 6), np.float32)
+    idx = np.zeros(max_det, np.int32)
+    L = lib()
+    L.o_rcnn_post.restype = C.c_int
+    cnt = L.o_rcnn_post(_p(rois, f32p), _p(valid, u8p), _p(logits, f32p), _p(deltas, f32p), C.c_int64(P), int(nc1), m, s,
+                        C.c_float(max_ratio), C.c_float(img_h), C.c_float(img_w), C.c_float(score_thr), int(nms_pre),
+                        C.c_float(iou_thr), int(max_det), _p(out, f32p), _p(idx, i32p))
+    return out, idx, cnt

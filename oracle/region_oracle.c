@@ -978,3 +978,74 @@ O_API void o_mask_targets(const uint8_t *masks, int G, int H, int W, const float
             }
     }
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* "next" row 4: RCNN-head post-process (per-class decode, score threshold, class-aware NMS,    */
+/* top max_det).  No reference code: PARITY UNPINNED, convention #22.                           */
+/* ------------------------------------------------------------------------------------------ */
+/* probs (P, nc1) softmax over nc1 = num_classes + 1 logits, background = class 0:
+ *   m = max_j x_j; e_j = o_exp(x_j - m); den = sum_j e_j (sequential); p_j = e_j / den */
+O_API void o_softmax_rows(const float *logits, int64_t P, int nc1, float *probs)
+{
+    for (int64_t r = 0; r < P; r++) {
+        const float *x = logits + r * nc1;
+        float *o = probs + r * nc1;
+        float m = x[0];
+        for (int j = 1; j < nc1; j++) m = fmaxf(m, x[j]);
+        float den = 0.0f;
+        for (int j = 0; j < nc1; j++) { float t = x[j] - m; o[j] = o_exp(t); den = den + o[j]; }
+        for (int j = 0; j < nc1; j++) o[j] = o[j] / den;
+    }
+}
+
+/* rois (P,4), roi_valid (P), logits (P,nc1), deltas (P,nc1*4).  Candidates: (r, c>=1) with roi_valid and
+ * prob > score_thr; the nms_pre best by (prob desc, r*nc1+c asc); box = decode_one(roi, deltas[r][c]); greedy NMS
+ * (offset 0, strict >, eps 1e-8) between equal labels; first max_det kept.  out (max_det,6) = box, prob, label;
+ * keep_idx (max_det) = r*nc1+c or -1.  returns count. */
+O_API int o_rcnn_post(const float *rois, const uint8_t *roi_valid, const float *logits, const float *deltas,
+                      int64_t P, int nc1, const float *means, const float *stds, float max_ratio, float img_h,
+                      float img_w, float score_thr, int nms_pre, float iou_thr, int max_det, float *out, int32_t *keep_idx)
+{
+    float *probs = (float *)malloc((size_t)P * nc1 * sizeof(float));
+    o_softmax_rows(logits, P, nc1, probs);
+    uint64_t *v = (uint64_t *)malloc((size_t)(P * nc1 > 0 ? P * nc1 : 1) * sizeof(uint64_t));
+    int64_t n = 0;
+    for (int64_t r = 0; r < P; r++) {
+        if (roi_valid && !roi_valid[r]) continue;
+        for (int c = 1; c < nc1; c++) {
+            float p = probs[r * nc1 + c];
+            if (p > score_thr) v[n++] = ((uint64_t)score_key(p) << 32) | (uint32_t)~(uint32_t)(r * nc1 + c);
+        }
+    }
+    qsort(v, (size_t)n, sizeof(uint64_t), cmp_u64_desc);
+    int64_t K = n < nms_pre ? n : nms_pre;
+    float *box = (float *)malloc((size_t)(K > 0 ? K : 1) * 4 * sizeof(float));
+    int32_t *lab = (int32_t *)malloc((size_t)(K > 0 ? K : 1) * sizeof(int32_t));
+    for (int64_t i = 0; i < K; i++) {
+        const int64_t id = (int64_t)(uint32_t)~(uint32_t)v[i];
+        const int64_t r = id / nc1;
+        const int c = (int)(id - r * nc1);
+        decode_one(rois + r * 4, deltas + (r * nc1 + c) * 4, means, stds, max_ratio, img_h, img_w, box + i * 4);
+        lab[i] = c;
+    }
+    uint8_t *sup = (uint8_t *)calloc((size_t)(K > 0 ? K : 1), 1);
+    int cnt = 0;
+    for (int i = 0; i < max_det; i++) { for (int k = 0; k < 6; k++) out[i * 6 + k] = 0.0f; keep_idx[i] = -1; }
+    for (int64_t i = 0; i < K; i++) {
+        if (sup[i]) continue;
+        if (cnt < max_det) {
+            const int64_t id = (int64_t)(uint32_t)~(uint32_t)v[i];
+            for (int k = 0; k < 4; k++) out[cnt * 6 + k] = box[i * 4 + k];
+            out[cnt * 6 + 4] = probs[id];
+            out[cnt * 6 + 5] = (float)lab[i];
+            keep_idx[cnt] = (int32_t)id;
+        }
+        cnt++;
+        for (int64_t j = i + 1; j < K; j++) {
+            if (sup[j] || lab[j] != lab[i]) continue;
+            if (nms_iou(box + i * 4, box + j * 4, 0.0f, 1e-8f) > iou_thr) sup[j] = 1;
+        }
+    }
+    free(sup); free(lab); free(box); free(v); free(probs);
+    return cnt < max_det ? cnt : max_det;
+}
