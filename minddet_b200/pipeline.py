@@ -8,9 +8,10 @@ import torch
 from . import synth
 from .ops import (AnchorGenerator, BboxAssignSample, BboxAssignSampleForRcnn, Proposal, SingleRoIExtractor)
 
-KERNELS_PER_STEP = 18   # select, nms_mask, nms_sweep, merge x2 | gtmax, label, select, finalize |
-                        # gt_head, gtmax, label, select, finalize | roialign fwd (stream + gather for declined RoIs)
-                        # | roialign bwd (stream + gather); the 5 cudaMemsetAsync of a step are not counted
+KERNELS_PER_STEP = 22   # select, nms_mask, nms_sweep, merge x2 | gtmax, label, prefilter, select(list), select(full scan,
+                        # returns at once), finalize | gt_head, gtmax, label, prefilter, select x2, finalize |
+                        # roialign fwd (stream + gather for declined RoIs) | roialign bwd (stream + gather);
+                        # the cudaMemsetAsync nodes of a step (dX zero-fill, small counters) are not counted
 
 
 class RegionPath:
