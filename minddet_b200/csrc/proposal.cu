@@ -19,29 +19,31 @@ namespace md {
 // =====================================================================================================
 // a1: anchor grid -- pure 128-bit stores, 16 B / anchor
 // =====================================================================================================
+// one grid row (blockIdx.y) per feature-map row; 32-bit index math (one division by A per anchor)
 __global__ void __launch_bounds__(256)
 anchor_grid_kernel(const float *__restrict__ base, int A, int H, int W, const float *__restrict__ cfg,
                    float4 *__restrict__ out)
 {
     const float stride = __ldg(cfg);
-    const int64_t total = (int64_t)H * W * A;
-    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < total; n += (int64_t)gridDim.x * blockDim.x) {
-        const int a = (int)(n % A);
-        const int64_t p = n / A;
-        const int w = (int)(p % W), h = (int)(p / W);
-        const float sx = mul((float)w, stride), sy = mul((float)h, stride);
-        const float4 b = __ldg(reinterpret_cast<const float4 *>(base) + a);
-        stg_stream(out + n, make_float4(add(b.x, sx), add(b.y, sy), add(b.z, sx), add(b.w, sy)));
+    const int row_len = W * A;
+    for (int h = blockIdx.y; h < H; h += gridDim.y) {
+        const float sy = mul((float)h, stride);
+        float4 *orow = out + (int64_t)h * row_len;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row_len; i += gridDim.x * blockDim.x) {
+            const int w = i / A, a = i - w * A;
+            const float sx = mul((float)w, stride);
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(base) + a);
+            stg_stream(orow + i, make_float4(add(b.x, sx), add(b.y, sy), add(b.z, sx), add(b.w, sy)));
+        }
     }
 }
 
 cudaError_t launch_anchor_grid(const float *base, int A, int H, int W, const float *cfg, float *out, cudaStream_t s)
 {
-    const int64_t total = (int64_t)H * W * A;
-    if (total == 0) return cudaSuccess;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    anchor_grid_kernel<<<blocks, 256, 0, s>>>(base, A, H, W, cfg, reinterpret_cast<float4 *>(out));
+    if ((int64_t)H * W * A == 0) return cudaSuccess;
+    const int row_len = W * A;
+    const int gx = (row_len + 255) / 256 < 8 ? (row_len + 255) / 256 : 8;
+    anchor_grid_kernel<<<dim3(gx, H < 65535 ? H : 65535), 256, 0, s>>>(base, A, H, W, cfg, reinterpret_cast<float4 *>(out));
     return cudaGetLastError();
 }
 
@@ -132,9 +134,7 @@ cudaError_t launch_decode_level(const float *deltas, const float *base, int B, i
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(deltas) & 15) == 0);
     const int tiles = (HW + kDecCells - 1) / kDecCells;
-    int gx = tiles;
-    const int cap = (148 * 6 + B - 1) / B;
-    if (gx > cap) gx = cap;
+    const int gx = tiles;                                  // one tile per CTA: several waves hide the load -> sync -> store phases
     auto kern = vec ? decode_level_kernel<true> : decode_level_kernel<false>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

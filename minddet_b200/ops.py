@@ -81,8 +81,7 @@ class AnchorGenerator(_Cell):
         base = self.base_tensor(device)
         A = base.shape[0]
         self._grid.out_shape = lambda b, c: (feat_h, feat_w, A, 4)
-        cfg = torch.tensor([float(stride)], dtype=torch.float32, device=device)
-        return self._grid(base, cfg).reshape(-1, 4)
+        return self._grid(base, self._cfg([float(stride)], device)).reshape(-1, 4)
 
     construct = grid_anchors
 
@@ -103,8 +102,7 @@ class BoundingBoxDecode(_Cell):
         return self._rows(anchors, deltas, self._cfg(self.cfg_values, anchors.device))
 
     def decode_level(self, deltas_nchw, base_anchors, stride):
-        cfg = torch.tensor(self.cfg_values + [float(stride)], dtype=torch.float32, device=deltas_nchw.device)
-        return self._level(deltas_nchw, base_anchors, cfg)
+        return self._level(deltas_nchw, base_anchors, self._cfg(self.cfg_values + [float(stride)], deltas_nchw.device))
 
 
 class TopKPerLevel(_Cell):
