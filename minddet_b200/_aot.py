@@ -13,7 +13,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmdregion.so")
+LIB_PATH = os.environ.get("MD_REGION_LIB", os.path.join(_HERE, "lib", "libmdregion.so"))   # override: experiments only
 
 _DTYPE_NAMES = {
     torch.float32: "float32", torch.int32: "int32", torch.int64: "int64", torch.uint8: "uint8",

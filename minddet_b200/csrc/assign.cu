@@ -32,21 +32,39 @@ MD_DEVINL float4 load_box(const float *p, int ld)
     return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
 }
 
-// compact the valid gts of image b into shared memory (original order kept)
+// compact the valid gts of image b into shared memory (original order kept): ordered block-wide compaction with
+// warp ballots (a serial walk by thread 0 cost ~3 us at the head of every CTA)
 MD_DEVINL int stage_gts(const AsIn &in, int b, float off, GtS *sg, int *s_count)
 {
-    if (threadIdx.x == 0) {
-        int c = 0;
-        for (int j = 0; j < in.G; j++) {
-            if (in.gt_valid && !in.gt_valid[(int64_t)b * in.G + j]) continue;
+    __shared__ int warp_tot[kAsThreads / 32];
+    __shared__ int base_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < in.G; j0 += kAsThreads) {
+        const int j = j0 + threadIdx.x;
+        const bool v = j < in.G && (!in.gt_valid || in.gt_valid[(int64_t)b * in.G + j]);
+        const uint32_t m = __ballot_sync(0xffffffffu, v);
+        if (lane == 0) warp_tot[warp] = __popc(m);
+        __syncthreads();
+        int before = base_s;
+        for (int w = 0; w < warp; w++) before += warp_tot[w];
+        if (v) {
             GtS g;
             g.box = __ldg(reinterpret_cast<const float4 *>(in.gts) + (int64_t)b * in.G + j);
             g.area = area_legacy(g.box, off);
             g.j = j;
-            sg[c++] = g;
+            sg[before + __popc(m & ((1u << lane) - 1u))] = g;
         }
-        *s_count = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < kAsThreads / 32; w++) t += warp_tot[w];
+            base_s += t;
+        }
+        __syncthreads();
     }
+    if (threadIdx.x == 0) *s_count = base_s;
     __syncthreads();
     return *s_count;
 }

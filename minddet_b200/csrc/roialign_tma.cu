@@ -39,7 +39,13 @@ namespace md {
 
 constexpr int kStWarps = 4;
 constexpr int kStThreads = kStWarps * 32;
-constexpr int kRingFloats = 4608;          // forward ring per warp (18 KB; a consumed stage doubles as the U buffer)
+#ifndef MD_RING
+#define MD_RING 4608
+#endif
+#ifndef MD_FWD_CTAS
+#define MD_FWD_CTAS 3
+#endif
+constexpr int kRingFloats = MD_RING;       // forward ring per warp (18 KB; a consumed stage doubles as the U buffer)
 constexpr int kMaxBW = 128;                // footprint width limit (floats)
 constexpr int kMaxSlots = 16;
 constexpr int kBwdSlots = 4;               // fixed: cp.async.bulk.wait_group needs an immediate
@@ -203,7 +209,7 @@ MD_DEVINL void fwd_step2(const float *U, int CPW, const SampleTap t0, const Samp
 }
 
 template <int P>
-__global__ void __launch_bounds__(kStThreads, 3)
+__global__ void __launch_bounds__(kStThreads, MD_FWD_CTAS)
 roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f, const int tma_mask,
                            const float *__restrict__ rois5, const int R, const int seg, const int nchunk,
                            float *__restrict__ out, int32_t *__restrict__ fallback_flag)
