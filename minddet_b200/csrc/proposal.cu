@@ -271,6 +271,27 @@ MD_DEVINL NmsCfg load_nms_cfg(const float *__restrict__ cfg)
 }
 struct BoxA { float x1, y1, x2, y2, area; };
 
+// Decision `inter / max(union, eps) > thr` (>= when inclusive), identical to the oracle's rounded expression.
+// Hot path without the division and without branches: e = inter - thr*union differs from its real value by
+// < 2e-7*union, and the correctly rounded quotient from the real one by < 6e-8, so outside a 2e-6*union band the
+// sign of e decides exactly as the division would.  Pairs inside the band (and NaN / non-positive unions) are
+// flagged `unsure` and re-evaluated with the exact expression after the loop.
+struct NmsVote { bool sup, unsure; };
+MD_DEVINL NmsVote nms_vote(const BoxA &a, const BoxA &b, const NmsCfg &c)
+{
+    const float left = fmaxf(a.x1, b.x1), right = fminf(a.x2, b.x2);
+    const float top = fmaxf(a.y1, b.y1), bottom = fminf(a.y2, b.y2);
+    const float w = fmaxf(add(sub(right, left), c.off), 0.0f);
+    const float h = fmaxf(add(sub(bottom, top), c.off), 0.0f);
+    const float inter = mul(w, h);
+    float uni = sub(add(a.area, b.area), inter);
+    uni = fmaxf(uni, c.eps);                                      // eps == 0 leaves positive unions untouched
+    const float e = sub(inter, mul(c.thr, uni)), band = mul(2e-6f, uni);
+    NmsVote v;
+    v.sup = (uni > 0.0f) & (e > band);
+    v.unsure = !((uni > 0.0f) & ((e > band) | (e < -band)));
+    return v;
+}
 MD_DEVINL bool nms_suppresses(const BoxA &a, const BoxA &b, const NmsCfg &c, bool zero_cond)
 {
     const float left = fmaxf(a.x1, b.x1), right = fminf(a.x2, b.x2);
@@ -286,6 +307,7 @@ MD_DEVINL bool nms_suppresses(const BoxA &a, const BoxA &b, const NmsCfg &c, boo
 }
 
 // grid: (triangular tile index, segment); 64 threads: thread r owns row box r of the tile.
+template <bool LABELS>
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(const NmsSegs sg, const float *__restrict__ cfg, unsigned long long *__restrict__ mask)
 {
@@ -303,20 +325,23 @@ nms_mask_kernel(const NmsSegs sg, const float *__restrict__ cfg, unsigned long l
     const NmsCfg c = load_nms_cfg(cfg);
     const bool zero_cond = c.inclusive ? (0.0f >= c.thr) : (0.0f > c.thr);
     const float *boxes = sg.boxes + (int64_t)seg * sg.seg_stride * sg.ld;
-    __shared__ BoxA cols[64];
+    __shared__ float4 cbox[64];            // 128-bit + 32-bit broadcast loads per column (a 5-float struct costs 5 LDS)
+    __shared__ float carea[64];
     __shared__ int32_t col_label[64];
     const int tid = threadIdx.x;
-    const int32_t *labels = (sg.labels && !(sg.agnostic && __ldg(sg.agnostic) != 0.0f)) ? sg.labels + (int64_t)seg * sg.seg_stride : nullptr;
+    const int32_t *labels = (LABELS && sg.labels && !(sg.agnostic && __ldg(sg.agnostic) != 0.0f)) ? sg.labels + (int64_t)seg * sg.seg_stride : nullptr;
     {
         const int cidx = j * 64 + tid;
-        BoxA b = { 0, 0, 0, 0, 0 };
-        col_label[tid] = (labels && cidx < K) ? labels[cidx] : 0;
+        float4 b = make_float4(0, 0, 0, 0);
+        float area = 0.0f;
+        if (LABELS) col_label[tid] = (labels && cidx < K) ? labels[cidx] : 0;
         if (cidx < K) {
             const float *p = boxes + (int64_t)cidx * sg.ld;
-            b.x1 = __ldg(p); b.y1 = __ldg(p + 1); b.x2 = __ldg(p + 2); b.y2 = __ldg(p + 3);
-            b.area = mul(add(sub(b.x2, b.x1), c.off), add(sub(b.y2, b.y1), c.off));
+            b = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+            area = mul(add(sub(b.z, b.x), c.off), add(sub(b.w, b.y), c.off));
         }
-        cols[tid] = b;
+        cbox[tid] = b;
+        carea[tid] = area;
     }
     __syncthreads();
     const int ridx = i * 64 + tid;
@@ -329,15 +354,46 @@ nms_mask_kernel(const NmsSegs sg, const float *__restrict__ cfg, unsigned long l
     }
     const int ncol = min(64, K - j * 64);
     const int start = (i == j) ? tid + 1 : 0;
-    unsigned long long bits = 0ull;
-    if (labels) {
-        const int32_t la = labels[ridx];
-        for (int k = start; k < ncol; k++)
-            if (col_label[k] == la && nms_suppresses(a, cols[k], c, zero_cond)) bits |= 1ull << k;
-    } else {
-        for (int k = start; k < ncol; k++)
-            if (nms_suppresses(a, cols[k], c, zero_cond)) bits |= 1ull << k;
+    const bool use_labels = LABELS && labels;
+    const int32_t la = use_labels ? labels[ridx] : 0;
+    // all 64 columns, fully unrolled (constant bit positions), branch-free; columns outside [start, ncol) are masked
+    // off below; the rare pairs the division-free test cannot decide are redone exactly afterwards
+    uint32_t half[2] = { 0u, 0u }, unsure[2] = { 0u, 0u };
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+        if (hh * 32 >= ncol || hh * 32 + 32 <= start) continue;
+        uint32_t acc = 0u, uns = 0u;
+#pragma unroll
+        for (int kk = 0; kk < 32; kk++) {
+            const int k = hh * 32 + kk;
+            const float4 bx = cbox[k];
+            const BoxA b = { bx.x, bx.y, bx.z, bx.w, carea[k] };
+            const NmsVote v = nms_vote(a, b, c);
+            bool sup = v.sup;
+            if (LABELS) sup = sup && (!use_labels || col_label[k] == la);
+            acc |= (sup ? 1u : 0u) << kk;
+            uns |= (v.unsure ? 1u : 0u) << kk;
+        }
+        half[hh] = acc;
+        unsure[hh] = uns;
     }
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+        uint32_t u = unsure[hh];
+        while (u) {
+            const int kk = __ffs(u) - 1, k = hh * 32 + kk;
+            u &= u - 1;
+            const float4 bx = cbox[k];
+            const BoxA b = { bx.x, bx.y, bx.z, bx.w, carea[k] };
+            bool sup = nms_suppresses(a, b, c, zero_cond);
+            if (LABELS) sup = sup && (!use_labels || col_label[k] == la);
+            half[hh] = (half[hh] & ~(1u << kk)) | ((sup ? 1u : 0u) << kk);
+        }
+    }
+    unsigned long long bits = ((unsigned long long)half[1] << 32) | half[0];
+    const unsigned long long lo_mask = start >= 64 ? 0ull : (~0ull << start);
+    const unsigned long long hi_mask = ncol >= 64 ? ~0ull : ((1ull << ncol) - 1ull);
+    bits &= lo_mask & hi_mask;
     mask[((int64_t)seg * sg.rows_pad + ridx) * sg.nbp + j] = bits;
 }
 
@@ -452,7 +508,10 @@ cudaError_t run_nms(const NmsSegs &sg, int nseg, int Kmax, const float *cfg, uns
     const int nb = (Kmax + 63) / 64;
     if (nb > kSweepMaxNb) return cudaErrorInvalidValue;
     const int tiles = nb * (nb + 1) / 2;
-    if (tiles > 0) nms_mask_kernel<<<dim3(tiles, nseg), 64, 0, s>>>(sg, cfg, mask);
+    if (tiles > 0) {
+        if (sg.labels) nms_mask_kernel<true><<<dim3(tiles, nseg), 64, 0, s>>>(sg, cfg, mask);
+        else nms_mask_kernel<false><<<dim3(tiles, nseg), 64, 0, s>>>(sg, cfg, mask);
+    }
     nms_sweep_kernel<<<nseg, kSweepThreads, 0, s>>>(sg, mask, nullptr, keep_pos, keep_stride, keep_mask, mask_stride, count);
     return cudaGetLastError();
 }
