@@ -28,19 +28,66 @@ namespace cg = cooperative_groups;
 constexpr int kClusterSize = 8;
 constexpr int kSelThreads = 512;
 constexpr int kSelMaxK = 2048;            // sorted output limit per segment
+constexpr int kSelDirectMax = 1024;       // segments up to this length skip the radix passes: the leader sorts them all
+                                          // (a single-CTA bitonic sort of 4096 costs ~50 us: measured, so keep this small)
 constexpr int kSelMaxIndexBits = 22;      // segment length < 4 Mi elements
 constexpr int kSelMaxCacheElems = 44 * 1024; // key cache per CTA (dynamic smem)
 
 struct SelShared {
     union {
         uint32_t hist[256 * 32];            // [bin][lane]  (select passes)
-        unsigned long long cand[kSelMaxK];  // leader only: selected composites (after the passes)
+        unsigned long long cand[kSelMaxK];  // leader only: selected composites (after the passes) / the whole short segment
     };
-    uint32_t local[256];       // this CTA's per-bin totals (read remotely through DSMEM)
+    uint32_t local[2][256];    // this CTA's per-bin totals (read remotely through DSMEM); double-buffered per pass
     uint32_t tot[256];         // cluster totals
     uint32_t cand_count;       // leader only
     uint32_t digit, above, eq, total, found;
 };
+
+// Bitonic sort (descending) of n2 (power of two, >= 32, <= kSelMaxK) 64-bit values in shared memory by one CTA of
+// kSelThreads.  Element e lives in lane e & 31, so every compare-exchange distance below 32 is a warp shuffle on
+// register copies: only the distances >= 32 go through shared memory with a block barrier (21 instead of 66 barriers
+// for 2048 values).
+MD_DEVINL void bitonic_sort_desc(unsigned long long *v, int n2)
+{
+    constexpr int R = kSelMaxK / kSelThreads;           // values per thread
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j >= 32; j >>= 1) {
+            for (int i = tid; i < n2; i += kSelThreads) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = v[i], b = v[ixj];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) { v[i] = b; v[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+        if (k >= 64 || k == 32) {
+            // all remaining distances (< 32) of this k, plus -- for k == 32 -- the whole k = 2..32 prefix, in registers
+            unsigned long long r[R];
+#pragma unroll
+            for (int m = 0; m < R; m++) r[m] = (tid + m * kSelThreads < n2) ? v[tid + m * kSelThreads] : 0ull;
+            for (int kk = (k == 32 ? 2 : k); kk <= k; kk <<= 1) {
+                for (int j = min(kk >> 1, 16); j > 0; j >>= 1) {
+#pragma unroll
+                    for (int m = 0; m < R; m++) {
+                        const int i = tid + m * kSelThreads;
+                        const unsigned long long o = __shfl_xor_sync(0xffffffffu, r[m], j);
+                        const bool desc = (i & kk) == 0, lower = (lane & j) == 0;
+                        // the lower index keeps the larger value when descending
+                        const bool take_max = desc == lower;
+                        r[m] = take_max ? (r[m] > o ? r[m] : o) : (r[m] < o ? r[m] : o);
+                    }
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < R; m++) if (tid + m * kSelThreads < n2) v[tid + m * kSelThreads] = r[m];
+            __syncthreads();
+        }
+    }
+}
 
 // Src concept:
 //   __device__ int segment_of(int launch_index) const;              launch order -> segment id (put the longest first)
@@ -80,6 +127,39 @@ select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
     const bool cached = len <= cache_elems;
 
     if (tid == 0) sh.cand_count = 0;
+
+    if (N <= kSelDirectMax) {
+        // ---- short segment: no radix passes.  The leader gathers every candidate, sorts them all and emits the K best.
+        if (rank != 0) return;                   // uniform over the cluster; nobody touches distributed shared memory
+        __syncthreads();
+        for (int base = 0; base < N; base += kSelThreads) {
+            const int i = base + tid;
+            uint32_t key = 0u;
+            const bool ok = i < N && src.load(ctx, i, key);
+            const uint32_t m = __ballot_sync(0xffffffffu, ok);
+            if (m) {
+                uint32_t pos = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) pos = atomicAdd(&sh.cand_count, (uint32_t)__popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, leader);
+                if (ok) sh.cand[pos + __popc(m & ((1u << lane) - 1u))] = ((unsigned long long)key << 32) | (uint32_t)~src.index_of(ctx, i);
+            }
+        }
+        __syncthreads();
+        const int ncand = (int)sh.cand_count;
+        int n2 = 32;
+        while (n2 < ncand) n2 <<= 1;
+        for (int i = ncand + tid; i < n2; i += kSelThreads) sh.cand[i] = 0ull;
+        __syncthreads();
+        bitonic_sort_desc(sh.cand, n2);
+        const int sel = min(K, ncand), want = src.want(ctx);
+        for (int i = tid; i < want; i += kSelThreads) {
+            if (i < sel) sink.emit(seg, i, sh.cand[i]);
+            else sink.pad(seg, i);
+        }
+        if (tid == 0) sink.finish(seg, sel, ncand);
+        return;
+    }
 
     // composite = (key << 32) | ~index.  Every composite has low bits 31..22 set (index < 2^22), so those
     // bits are "already matched".  The 4 key digits never need the index; it is only computed for the tie
@@ -132,12 +212,12 @@ select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
             uint32_t s = 0;
 #pragma unroll 8
             for (int r = 0; r < 32; r++) s += sh.hist[tid * 32 + ((r + tid) & 31)];
-            sh.local[tid] = s;
+            sh.local[pass & 1][tid] = s;
         }
         cluster.sync();
         if (tid < 256) {
             uint32_t s = 0;
-            for (int r = 0; r < kClusterSize; r++) s += cluster.map_shared_rank(sh.local, r)[tid];
+            for (int r = 0; r < kClusterSize; r++) s += cluster.map_shared_rank(sh.local[pass & 1], r)[tid];
             sh.tot[tid] = s;
         }
         __syncthreads();
@@ -183,7 +263,8 @@ select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
             need -= (int)sh.above;
             if ((int)sh.eq == need) done = true;   // everything matching the prefix is selected
         }
-        cluster.sync();   // remote reads of sh.local are finished before the next pass overwrites it
+        // no second cluster barrier: the next pass writes the OTHER sh.local buffer, and the barrier of that pass
+        // orders this pass's remote reads before the buffer is written again two passes later
     }
     // selected set: every candidate with (comp & known) >= prefix
     const int selected = min(K, candidates);
@@ -231,19 +312,7 @@ select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
     while (n2 < selected) n2 <<= 1;
     for (int i = selected + tid; i < n2; i += kSelThreads) sh.cand[i] = 0ull;
     __syncthreads();
-    for (int k = 2; k <= n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < n2; i += kSelThreads) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long a = sh.cand[i], b = sh.cand[ixj];
-                    const bool desc = (i & k) == 0;
-                    if (desc ? (a < b) : (a > b)) { sh.cand[i] = b; sh.cand[ixj] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    }
+    bitonic_sort_desc(sh.cand, n2);
     const int want = src.want(ctx);
     for (int i = tid; i < want; i += kSelThreads) {
         if (i < selected) sink.emit(seg, i, sh.cand[i]);
