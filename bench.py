@@ -263,7 +263,7 @@ def run_b200(args):
             side.synchronize()
             for (n0, ev0), (n1, ev1) in zip(tm[:-1], tm[1:]):
                 per.setdefault(n1, []).append(ev0.elapsed_time(ev1))
-        live_ms = {k: float(np.mean(v)) for k, v in per.items()}
+        live_ms = {k: float(np.median(v)) for k, v in per.items()}     # median: robust to host-side launch hiccups of the eager pass
 
         # ---- e2e: every step copies ALL inputs pinned host -> device and reads the step's compact results back.
         # Two device input sets + a copy stream: the H2D of step i+1 overlaps the kernels of step i (a user
