@@ -427,7 +427,7 @@ struct BwdShared {
     float4 row_w[kMaxRowsBwd];         // weights of bins row_p .. row_p+3
     int row_p[kMaxRowsBwd];            // first contributing bin of each footprint row (-1: none)
     int row_p2[kMaxRowsBwd];           // same with empty rows filled in
-    float ay_dense[16][8];             // rows x bins, only when some row has more than 4 contributing bins
+    float ay_dense[16][16];            // rows x bins (padded), only when some row has more than 4 contributing bins
     int rs[P + 1];                     // rows [rs[p], rs[p+1]) have first contributing bin p (row_p is non-decreasing)
     int dense;
 };
@@ -450,20 +450,43 @@ MD_DEVINL void row_from_bins(const float (&T)[P][4], const float4 w, float &d0, 
 }
 #undef MD_ACC
 
+// walks the footprint rows bin by bin: rows [rs[PA], rs[PA+1]) have first contributing bin PA (static register index)
+template <int P, int PA>
+struct BinWalk {
+    template <class Emit>
+    static MD_DEVINL void run(const float (&T)[P][4], const int *rs, const float4 *row_w, int &y, Emit &emit)
+    {
+        for (const int ye = rs[PA + 1]; y < ye; y++) {
+            const float4 w = row_w[y];
+            float d0, d1, d2, d3;
+            row_from_bins<P, PA>(T, w, d0, d1, d2, d3);
+            emit(y, d0, d1, d2, d3);
+        }
+        BinWalk<P, PA + 1>::run(T, rs, row_w, y, emit);
+    }
+};
 template <int P>
-__global__ void __launch_bounds__(kStThreads, 4)
+struct BinWalk<P, P> {
+    template <class Emit>
+    static MD_DEVINL void run(const float (&)[P][4], const int *, const float4 *, int &, Emit &) {}
+};
+
+template <int P>
+__global__ void __launch_bounds__(kStThreads, P <= 8 ? 4 : 2)
 roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f, const int tma_mask,
                            const float *__restrict__ rois5, const int R, const int seg, const int nchunk,
                            const float *__restrict__ dout, int32_t *__restrict__ fallback_flag)
 {
-    static_assert(P == 7, "backward stream kernel is specialised for 7x7");
+    static_assert(P == 7 || P == 14, "backward stream kernel: 7x7 (box head) and 14x14 (mask head)");
     constexpr int S = 2, NS = P * S, PP = P * P;
-    constexpr int kGFloats = 8 * P * 8;                   // CPW(max 8) x P x 8 (q padded to 8)
+    constexpr int QP = P <= 8 ? 8 : 16;                   // dY rows padded to a multiple of 4 floats
+    constexpr int NBUF = P <= 8 ? 2 : 1;                  // dY staging buffers per warp (one for 14x14: shared memory)
+    constexpr int kGFloats = 8 * P * QP;                  // CPW(max 8) x P x QP
     constexpr int kAxFloats = P * 132;                    // Ax dense [q][<=128 + 4]
     extern __shared__ __align__(128) unsigned char dsm[];
     float *ring_all = reinterpret_cast<float *>(dsm);
-    float *G_all = ring_all + kStWarps * kBwdRingFloats; // [warp][2][kGFloats]
-    float *AxD = G_all + kStWarps * 2 * kGFloats;        // [q][BWA]
+    float *G_all = ring_all + kStWarps * kBwdRingFloats; // [warp][NBUF][kGFloats]
+    float *AxD = G_all + kStWarps * NBUF * kGFloats;     // [q][BWA]
     BwdShared<P> &bs = *reinterpret_cast<BwdShared<P> *>(AxD + kAxFloats);
     StreamShared<P> &sh = bs.st;
 
@@ -527,7 +550,7 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
         if (pz - pa > 3) bs.dense = 1;                               // benign race: every writer stores 1
         if (y < 16) {
 #pragma unroll
-            for (int p = 0; p < 8; p++) bs.ay_dense[y][p] = p < P ? w[p] : 0.0f;
+            for (int p = 0; p < 16; p++) bs.ay_dense[y][p] = p < P ? w[p] : 0.0f;
         }
     }
     if (tid <= P) bs.rs[tid] = h_fp;
@@ -558,7 +581,7 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
     const int ngroups = CH / CPW;
     const int ng_w = (ngroups - warp + kStWarps - 1) / kStWarps;
     float *ring = ring_all + warp * kBwdRingFloats;
-    float *Gs = G_all + warp * 2 * kGFloats;
+    float *Gs = G_all + warp * NBUF * kGFloats;
     const CUtensorMap *map = &maps.m[g.l * kNumBW + (BW >> 2) - 1];
     const int H = g.H, W = g.W;
     float *dplane = f.feat[g.l] + ((int64_t)g.b * C + cbase) * H * W;
@@ -574,11 +597,11 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
         ax[q][0] = v.x; ax[q][1] = v.y; ax[q][2] = v.z; ax[q][3] = v.w;
     }
 
-    auto stage_g = [&](int gi) {                          // dY of group gi -> Gs[gi & 1][cs][p][8]
+    auto stage_g = [&](int gi) {                          // dY of group gi -> Gs[gi % NBUF][cs][p][QP]
         const int c0 = (warp + kStWarps * gi) * CPW;
-        float *dst = Gs + (gi & 1) * kGFloats;
+        float *dst = Gs + (gi % NBUF) * kGFloats;
         const float *src = grow + (int64_t)c0 * PP;
-        for (int e = lane; e < CPW * PP; e += 32) cp_async4(dst + e + e / P, src + e);   // rows of P padded to 8
+        for (int e = lane; e < CPW * PP; e += 32) cp_async4(dst + e + (e / P) * (QP - P), src + e);   // rows of P padded to QP
         cp_async_commit_group();
     };
 
@@ -586,17 +609,20 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
     if (ng_w > 0) stage_g(0);
     for (int gi = 0; gi < ng_w; gi++) {
         const int c0 = (warp + kStWarps * gi) * CPW;
-        if (gi + 1 < ng_w) { stage_g(gi + 1); cp_async_wait_group<1>(); } else { cp_async_wait_group<0>(); }
+        if (NBUF == 2 && gi + 1 < ng_w) { stage_g(gi + 1); cp_async_wait_group<1>(); } else { cp_async_wait_group<0>(); }
         __syncwarp();
         // ---- step 1: T[p][4 cols] = sum_q dY[p][q] * Ax[q][cols] -----------------------------------------
         float T[P][4];
         {
-            const float *gs = Gs + (gi & 1) * kGFloats + csub * P * 8;
+            const float *gs = Gs + (gi % NBUF) * kGFloats + csub * P * QP;
 #pragma unroll
             for (int p = 0; p < P; p++) {
-                const float4 g0 = *reinterpret_cast<const float4 *>(gs + p * 8);
-                const float4 g1 = *reinterpret_cast<const float4 *>(gs + p * 8 + 4);
-                const float gq[7] = { g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z };
+                float gq[QP];
+#pragma unroll
+                for (int v4 = 0; v4 < QP / 4; v4++) {
+                    const float4 t = *reinterpret_cast<const float4 *>(gs + p * QP + 4 * v4);
+                    gq[4 * v4] = t.x; gq[4 * v4 + 1] = t.y; gq[4 * v4 + 2] = t.z; gq[4 * v4 + 3] = t.w;
+                }
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     float acc = mul(gq[0], ax[0][k]);
@@ -606,6 +632,7 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
                 }
             }
         }
+        if (NBUF == 1 && gi + 1 < ng_w) { __syncwarp(); stage_g(gi + 1); }      // single buffer: refill once step 1 has read it
         // ---- step 2: D[row][4 cols] = sum_p Ay[p][row] * T[p].  Rows are walked bin by bin (row_p is
         //      non-decreasing, so the register index of T stays static and no per-row dispatch is needed).
         //      TMA levels: rows go conflict-free into a ring slot; every completed 4-row block is folded into
@@ -638,20 +665,15 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
         };
         if (!dense) {
             int y = 0;
-#define MD_BIN(PA)                                                                                   \
-    for (const int ye = bs.rs[PA + 1]; y < ye; y++) {                                                \
-        const float4 w = bs.row_w[y];                                                                \
-        float d0, d1, d2, d3;                                                                        \
-        row_from_bins<P, PA>(T, w, d0, d1, d2, d3);                                                  \
-        emit_row(y, d0, d1, d2, d3);                                                                 \
-    }
-            MD_BIN(0) MD_BIN(1) MD_BIN(2) MD_BIN(3) MD_BIN(4) MD_BIN(5) MD_BIN(6)
-#undef MD_BIN
+            BinWalk<P, 0>::run(T, bs.rs, bs.row_w, y, emit_row);
         } else {
             for (int y = 0; y < h_fp; y++) {
-                const float4 w0 = *reinterpret_cast<const float4 *>(&bs.ay_dense[y][0]);
-                const float4 w1 = *reinterpret_cast<const float4 *>(&bs.ay_dense[y][4]);
-                const float wp[7] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z };
+                float wp[16];
+#pragma unroll
+                for (int v4 = 0; v4 < 4; v4++) {
+                    const float4 t = *reinterpret_cast<const float4 *>(&bs.ay_dense[y][4 * v4]);
+                    wp[4 * v4] = t.x; wp[4 * v4 + 1] = t.y; wp[4 * v4 + 2] = t.z; wp[4 * v4 + 3] = t.w;
+                }
                 float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
 #pragma unroll
                 for (int p = 0; p < P; p++) {
@@ -661,7 +683,7 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
                 emit_row(y, d0, d1, d2, d3);
             }
         }
-        __syncwarp();                                     // Gs[gi & 1] may be overwritten by stage_g(gi + 2)
+        __syncwarp();                                     // the dY buffer may be overwritten by the next stage_g
     }
     if (use_tma && lane == 0) bulk_wait_all<0>();
 }
@@ -759,7 +781,8 @@ template <int P> static size_t fwd_smem()
 }
 template <int P> static size_t bwd_smem()
 {
-    return (size_t)(kStWarps * kBwdRingFloats + kStWarps * 2 * 8 * P * 8 + P * 132) * sizeof(float) + sizeof(BwdShared<P>) + 128;
+    return (size_t)(kStWarps * kBwdRingFloats + kStWarps * (P <= 8 ? 2 : 1) * 8 * P * (P <= 8 ? 8 : 16) + P * 132) * sizeof(float) +
+           sizeof(BwdShared<P>) + 128;
 }
 
 template <int P>
@@ -791,24 +814,33 @@ cudaError_t launch_roialign_fwd_tma(const FeatSet &fs, const RoiFeat &f, const f
     return e;
 }
 
-cudaError_t launch_roialign_bwd_tma(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P,
-                                    const float *dout, int32_t *fallback_flag, cudaStream_t s, bool *launched)
+template <int P>
+static cudaError_t launch_bwd(const TmaMaps &maps, const RoiFeat &f, int mask, const float *rois5, int R, const float *dout,
+                              int32_t *flag, cudaStream_t s)
 {
-    *launched = false;
-    if ((fs.C & 7) || P != 7) return cudaSuccess;
-    TmaMaps maps;
-    const int mask = build_maps(fs, &maps);
     static bool configured = false;
-    auto kern = roialign_bwd_stream_kernel<7>;
+    auto kern = roialign_bwd_stream_kernel<P>;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<7>());
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<P>());
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int nchunk = chunks_for(f.C);
-    kern<<<R * nchunk, kStThreads, bwd_smem<7>(), s>>>(maps, f, mask, rois5, R, kSegRois, nchunk, dout, fallback_flag);
-    *launched = true;
+    kern<<<R * nchunk, kStThreads, bwd_smem<P>(), s>>>(maps, f, mask, rois5, R, kSegRois, nchunk, dout, flag);
     return cudaGetLastError();
+}
+
+cudaError_t launch_roialign_bwd_tma(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P,
+                                    const float *dout, int32_t *fallback_flag, cudaStream_t s, bool *launched)
+{
+    *launched = false;
+    if ((fs.C & 7) || (P != 7 && P != 14)) return cudaSuccess;
+    TmaMaps maps;
+    const int mask = build_maps(fs, &maps);
+    cudaError_t e = P == 7 ? launch_bwd<7>(maps, f, mask, rois5, R, dout, fallback_flag, s)
+                           : launch_bwd<14>(maps, f, mask, rois5, R, dout, fallback_flag, s);
+    *launched = e == cudaSuccess;
+    return e;
 }
 
 }  // namespace md
