@@ -30,7 +30,7 @@ METRIC = "Faster R-CNN RPN+RoI region path throughput"
 UNIT = "img/s"
 BATCH = 8
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the stream kernels (ncu --set full, profiles/r1_roialign_ncu.md)
-NCU_TRAFFIC = {"roialign_fwd": 855e6, "roialign_bwd": 1277e6}
+NCU_TRAFFIC = {"roialign_fwd": 843e6, "roialign_bwd": 1260e6}     # r1 v6: 652.7+190.5 MB / 791.4+469.1 MB (profiles/r1_roialign_ncu_v6.txt)
 WORKLOAD = ("configs[1]: Faster R-CNN R50-FPN region path, batch 8/GPU, 800x1344, 5 levels (268569 anchors), "
             "2000 pre-NMS/level, NMS 0.7, max_num 2000, G<=128 gts, 512 sampled RoIs, 256-ch 7x7 RoIAlign fwd+bwd")
 
@@ -351,9 +351,19 @@ def run_b200(args):
         t = torch.tensor([ms, e2e_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_ms = float(t[0]), float(t[1])
-    if rank != 0:
+    def leave():
+        # N > 1: leave through a barrier and a hard exit.  Tearing the NCCL communicator down while CUDA graphs, pinned
+        # buffers and side streams are still alive has been seen to hang a rank after the result was already printed.
         if world > 1:
-            dist.destroy_process_group()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            try:
+                dist.barrier()
+            finally:
+                os._exit(0)
+
+    if rank != 0:
+        leave()
         return
 
     value = world * BATCH / (ms * 1e-3)
@@ -402,8 +412,7 @@ def run_b200(args):
             "gpu_launches": pipeline.KERNELS_PER_STEP * K, "nccl_collectives_per_step": 1 if world > 1 else 0,
             "roofline": roofline, "stage_ms": stage_ms, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 def cpu_baseline():
