@@ -242,12 +242,22 @@ def run_b200(args):
                 o = out
             else:
                 o = step(dev)
-            if world > 1:   # the path's only collective: all-gather of the final detections (top-100 proposals / image)
-                o["gathered"] = shard.gather_detections(o["props"][:, :100].contiguous(), world * BATCH)
+            if world > 1:
+                # the path's only collective: all-gather of the final detections (top-100 proposals / image).  Asynchronous:
+                # the records of step i travel on NCCL's stream while step i+1 computes; at most 2 in flight.
+                pending.append(shard.gather_detections(o["props"][:, :100].contiguous(), world * BATCH, async_op=True))
+                if len(pending) > 2:
+                    o["gathered"] = pending.pop(0).result()
             return o
 
+        def drain():
+            while pending:
+                pending.pop(0).result()
+
+        pending = []
         for _ in range(3):          # warm the whole step incl. the collective (NCCL connects lazily on first use)
             run_step()
+        drain()
         side.synchronize()
         if saved_stdout is not None:
             sys.stdout.flush()
@@ -264,6 +274,7 @@ def run_b200(args):
         e0.record()
         for _ in range(K):
             run_step()
+        drain()                     # every collective of the K steps completes inside the timed region
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -322,7 +333,9 @@ def run_b200(args):
             else:
                 o = step(sets[b])
             if world > 1:
-                o["gathered"] = shard.gather_detections(o["props"][:, :100].contiguous(), world * BATCH)
+                pending.append(shard.gather_detections(o["props"][:, :100].contiguous(), world * BATCH, async_op=True))
+                if len(pending) > 2:
+                    o["gathered"] = pending.pop(0).result()
             res = results_of(o)
             if pinned[b] is None:
                 pinned[b] = [torch.empty(r.shape, dtype=r.dtype, pin_memory=True) for r in res]
@@ -342,6 +355,7 @@ def run_b200(args):
         t0 = time.perf_counter()
         for i in range(K):
             e2e_step(i + 2)
+        drain()
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / K
         sampler.stop_flag = True

@@ -23,12 +23,30 @@ def shard_sizes(num_images, world_size):
     return [image_shard(num_images, world_size, r)[1] - image_shard(num_images, world_size, r)[0] for r in range(world_size)]
 
 
-def gather_detections(local, num_images=None, group=None):
+class PendingGather:
+    """Handle of an asynchronous `gather_detections`: `.result()` waits (stream-side) and returns the gathered tensor."""
+
+    def __init__(self, work, out, sizes, bmax):
+        self.work, self.out, self.sizes, self.bmax = work, out, sizes, bmax
+
+    def result(self):
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        if all(s == self.bmax for s in self.sizes):
+            return self.out
+        return torch.cat([self.out[r * self.bmax:r * self.bmax + self.sizes[r]] for r in range(len(self.sizes))])
+
+
+def gather_detections(local, num_images=None, group=None, async_op=False):
     """All-gather per-image detection records.  local: (B_local, K, D) on this rank (B_local as given by
     `image_shard`).  Returns (num_images, K, D) in global image order on every rank.  One collective;
-    ragged shards are padded to the largest shard so that the NCCL call stays a single fixed-size all-gather."""
+    ragged shards are padded to the largest shard so that the NCCL call stays a single fixed-size all-gather.
+    async_op=True returns a `PendingGather`: the collective then runs on NCCL's stream beside whatever the caller
+    enqueues next (the detections of step i travel while step i+1 computes); `local` must not be overwritten
+    before `.result()`."""
     if not (dist.is_available() and dist.is_initialized()):
-        return local
+        return PendingGather(None, local, [local.shape[0]], local.shape[0]) if async_op else local
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if num_images is None:
         num_images = local.shape[0] * world
@@ -41,6 +59,8 @@ def gather_detections(local, num_images=None, group=None):
         pad = torch.zeros((bmax - send.shape[0],) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
         send = torch.cat([send, pad])
     out = torch.empty((world * bmax,) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+    if async_op:
+        return PendingGather(dist.all_gather_into_tensor(out, send, group=group, async_op=True), out, sizes, bmax)
     dist.all_gather_into_tensor(out, send, group=group)
     if all(s == bmax for s in sizes):
         return out

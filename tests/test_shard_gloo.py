@@ -28,7 +28,8 @@ def _worker(rank, world, port, num_images, out_dir):
         full = torch.arange(num_images * 100 * 5, dtype=torch.float32).reshape(num_images, 100, 5)
         a, b = shard.image_shard(num_images, world, rank)
         got = shard.gather_detections(full[a:b].clone(), num_images)
-        ok = got.shape == full.shape and torch.equal(got, full)
+        got2 = shard.gather_detections(full[a:b].clone(), num_images, async_op=True).result()
+        ok = got.shape == full.shape and torch.equal(got, full) and torch.equal(got2, full)
         np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(ok), a, b]))
     finally:
         dist.destroy_process_group()
