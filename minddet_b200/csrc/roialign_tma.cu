@@ -712,7 +712,7 @@ static EncodeTiledFn get_encode()
 struct MapCache {
     void *ptr[kTmaLevels]; int H[kTmaLevels], W[kTmaLevels], BC, L, mask; TmaMaps maps; bool valid; unsigned long long stamp;
 };
-constexpr int kCacheEntries = 8;
+constexpr int kCacheEntries = 32;
 static MapCache g_cache[kCacheEntries];
 static unsigned long long g_stamp = 0;
 static std::mutex g_cache_mutex;
