@@ -402,16 +402,27 @@ MD_DEVINL void cp_async16(void *smem, const void *gmem)
     const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gmem) : "memory");
 }
+MD_DEVINL void cp_async8(void *smem, const void *gmem)
+{
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(gmem) : "memory");
+}
 MD_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> MD_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-// One CTA per segment.  All 128 threads stream 64-row chunks of the bitmask into a double-buffered
-// shared-memory stage with cp.async; warp 0 resolves each chunk:
-//   kept <- alive & ~OR_{b in kept} diag[b]        iterated to its (unique) fixed point == greedy NMS,
-// with the OR taken across the warp by redux.or, then ORs the kept rows into the running `removed`
-// words (lane j owns word j).
-constexpr int kSweepThreads = 128;
+// One CTA per segment: warp 0 (the resolver) walks the 64-box chunks in score order, warps 1..8 (the helpers) stream
+// the chunks' bitmask rows into a kSweepStages-deep shared-memory ring with cp.async and fold them into `removed`.
+//   resolver, chunk c:  kept <- alive & ~OR_{b in kept} diag[b]   iterated to its (unique) fixed point == greedy NMS
+//                       (the OR across the warp is redux.or), then the kept rows' word c + 1 - the only word chunk c + 1
+//                       cannot start without - is ORed into removed[c + 1] from a packed copy of that column;
+//   helpers, chunk c-1: the kept rows' words c + 1 .. nb - 1 are ORed into removed[] one iteration later, off the
+//                       critical path (8 rows per warp, lane j = word j).
+// One __syncthreads per chunk; keep_mask / keep_pos are written by all threads after the walk from kept_all[].
+constexpr int kSweepHelpers = 8;                            // helper warps
+constexpr int kSweepThreads = 32 * (1 + kSweepHelpers);
 constexpr int kSweepMaxNb = 32;    // K <= 2048
+constexpr int kSweepStages = 6;    // a chunk is issued 4 iterations (~1 us) before the resolver needs its diagonal
+constexpr size_t kSweepSmem = (size_t)kSweepStages * 64 * kSweepMaxNb * sizeof(unsigned long long);
 
 __global__ void __launch_bounds__(kSweepThreads)
 nms_sweep_kernel(const NmsSegs sg, const unsigned long long *__restrict__ mask,
@@ -419,41 +430,52 @@ nms_sweep_kernel(const NmsSegs sg, const unsigned long long *__restrict__ mask,
                  int32_t *__restrict__ keep_pos, int keep_stride, uint8_t *__restrict__ keep_mask,
                  int mask_stride, int32_t *__restrict__ count)
 {
-    __shared__ __align__(16) unsigned long long stage[2][64 * kSweepMaxNb];
+    extern __shared__ __align__(16) unsigned long long stage_raw[];
+    unsigned long long (*stage)[64 * kSweepMaxNb] = reinterpret_cast<unsigned long long (*)[64 * kSweepMaxNb]>(stage_raw);
+    __shared__ unsigned long long diag[kSweepStages][64];    // word c     of the rows of chunk c (the 64 x 64 diagonal block)
+    __shared__ unsigned long long next[kSweepStages][64];    // word c + 1 of the rows of chunk c
+    __shared__ unsigned long long removed[kSweepMaxNb];      // word j of "suppressed by an earlier kept box"
+    __shared__ unsigned long long kept_all[kSweepMaxNb];
+    __shared__ int kept_before[kSweepMaxNb + 1];
     const int seg = blockIdx.x;
     const int K = sg.K[seg % sg.L];
     const int nb = (K + 63) >> 6, nbp = sg.nbp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int htid = tid - 32, hw = warp - 1;                // helper thread / warp index
     const unsigned long long *m = mask + (int64_t)seg * sg.rows_pad * nbp;
     int32_t *kp = keep_pos + (int64_t)seg * keep_stride;
     uint8_t *km = keep_mask + (int64_t)seg * mask_stride;
 
-    auto issue = [&](int c) {   // rows c*64..c*64+63, words [c&~1, nbp)
-        const int w0 = c & ~1;
-        const int chunks_per_row = (nbp - w0) >> 1;       // 16-byte chunks
-        const int total = 64 * chunks_per_row;
-        unsigned long long *dst = stage[c & 1];
-        for (int q = tid; q < total; q += kSweepThreads) {
-            const int r = q / chunks_per_row, k = q - r * chunks_per_row;
-            cp_async16(dst + r * nbp + w0 + 2 * k, m + (int64_t)(c * 64 + r) * nbp + w0 + 2 * k);
+    // helpers only.  Rows are contiguous in the workspace and in the stage (same pitch), so a chunk is ONE flat copy of
+    // 64 * nbp words in 16-byte pieces; the two columns the resolver reads are copied once more, packed (in the stage
+    // they sit nbp words apart, i.e. in one bank)
+    auto issue = [&](int c) {
+        if (c < nb) {
+            unsigned long long *dst = stage[c % kSweepStages];
+            const unsigned long long *src = m + (int64_t)c * 64 * nbp;
+            const int total = 32 * nbp;                        // 16-byte pieces
+            for (int q = htid; q < total; q += 32 * kSweepHelpers) cp_async16(dst + 2 * q, src + 2 * q);
+            if (htid < 64) cp_async8(&diag[c % kSweepStages][htid], src + (int64_t)htid * nbp + c);
+            else if (htid < 128 && c + 1 < nb) cp_async8(&next[c % kSweepStages][htid - 64], src + (int64_t)(htid - 64) * nbp + c + 1);
         }
-        cp_async_commit();
+        cp_async_commit();                                      // empty groups keep the wait count uniform
     };
 
-    unsigned long long removed = 0ull;   // lane j: word j
-    if (init_removed && warp == 0 && lane < nb) removed = init_removed[(int64_t)seg * nbp + lane];
-    int nkept = 0;
-    if (nb > 0) issue(0);
+    if (tid < kSweepMaxNb) removed[tid] = (init_removed && tid < nb) ? init_removed[(int64_t)seg * nbp + tid] : 0ull;
+    if (warp > 0)
+        for (int c = 0; c < kSweepStages - 2; c++) issue(c);
+    constexpr int kRowsPerWarp = 64 / kSweepHelpers;
     for (int c = 0; c < nb; c++) {
-        if (c + 1 < nb) { issue(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-        __syncthreads();
+        if (warp > 0) cp_async_wait<kSweepStages - 3>();        // chunk c has landed (this thread's pieces)
+        __syncthreads();    // ... all pieces; removed[c] is final; kept_all[c - 1] is visible; stage (c - 2) % S is free
         if (warp == 0) {
-            const unsigned long long *rows = stage[c & 1];
             const int nrows = min(64, K - c * 64);
             const unsigned long long vmask = nrows == 64 ? ~0ull : ((1ull << nrows) - 1ull);
-            const unsigned long long cur = __shfl_sync(0xffffffffu, removed, c);
-            const unsigned long long alive = ~cur & vmask;
-            const unsigned long long d_lo = rows[lane * nbp + c], d_hi = rows[(lane + 32) * nbp + c];
+            const unsigned long long alive = ~removed[c] & vmask;
+            const unsigned long long *dg = diag[c % kSweepStages], *nx = next[c % kSweepStages];
+            const unsigned long long d_lo = dg[lane], d_hi = dg[lane + 32];
+            unsigned long long n_lo = 0ull, n_hi = 0ull;
+            if (c + 1 < nb) { n_lo = nx[lane]; n_hi = nx[lane + 32]; }
             unsigned long long kept = alive;
             for (int it = 0; it < 64; it++) {
                 unsigned long long sup = (((kept >> lane) & 1ull) ? d_lo : 0ull) |
@@ -464,34 +486,57 @@ nms_sweep_kernel(const NmsSegs sg, const unsigned long long *__restrict__ mask,
                 if (nk == kept) break;
                 kept = nk;
             }
-            // OR the kept rows into the removed words of the later chunks: 64 independent predicated loads
-            // (a data-dependent `while (k)` walk serialises ffs -> address -> load and was 3 us per chunk)
-            if (lane > c && lane < nb) {
-                unsigned long long acc = 0ull;
-                const unsigned long long *col = rows + lane;
-#pragma unroll 16
-                for (int b = 0; b < 64; b++) {
-                    const unsigned long long v = col[b * nbp];
-                    acc |= ((kept >> b) & 1ull) ? v : 0ull;
-                }
-                removed |= acc;
+            if (c + 1 < nb) {
+                unsigned long long sup = (((kept >> lane) & 1ull) ? n_lo : 0ull) |
+                                         (((kept >> (lane + 32)) & 1ull) ? n_hi : 0ull);
+                const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)sup);
+                const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(sup >> 32));
+                const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+                if (lane == 0 && v) atomicOr(&removed[c + 1], v);    // helpers OR chunk c - 1's rows into the same word
             }
-            // outputs
-            const int b0 = lane, b1 = lane + 32;
-            const bool k0 = (kept >> b0) & 1ull, k1 = (kept >> b1) & 1ull;
-            if (b0 < nrows) km[c * 64 + b0] = k0;
-            if (b1 < nrows) km[c * 64 + b1] = k1;
-            if (k0) kp[nkept + __popcll(kept & ((1ull << b0) - 1ull))] = c * 64 + b0;
-            if (k1) kp[nkept + __popcll(kept & ((1ull << b1) - 1ull))] = c * 64 + b1;
-            nkept += __popcll(kept);
+            if (lane == 0) kept_all[c] = kept;
+        } else {
+            issue(c + kSweepStages - 2);
+            // rows of chunk c - 1, words c + 1 ..: `kept` is warp-uniform, so a row that was not kept costs one predicate
+            if (c >= 1 && lane > c && lane < nb) {
+                const unsigned long long kept = kept_all[c - 1] >> (hw * kRowsPerWarp);
+                const unsigned long long *col = stage[(c - 1) % kSweepStages] + (hw * kRowsPerWarp) * nbp + lane;
+                unsigned long long acc = 0ull;
+#pragma unroll
+                for (int b = 0; b < kRowsPerWarp; b++)
+                    if ((kept >> b) & 1ull) acc |= col[b * nbp];
+                if (acc) atomicOr(&removed[lane], acc);
+            }
         }
-        __syncthreads();
     }
+    cp_async_wait<0>();
+    __syncthreads();
+    // outputs: kept_before[c] = boxes kept in chunks < c, then every thread writes its boxes
     if (warp == 0) {
-        for (int i = nkept + lane; i < keep_stride; i += 32) kp[i] = 0;
-        for (int i = K + lane; i < mask_stride; i += 32) km[i] = 0;
-        if (lane == 0) count[seg] = nkept;
+        const int n = lane < nb ? __popcll(kept_all[lane]) : 0;
+        int incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        kept_before[lane] = incl - n;
+        if (lane == 31) kept_before[32] = incl;
     }
+    __syncthreads();
+    const int nkept = kept_before[32];
+    for (int i = tid; i < mask_stride; i += kSweepThreads) {
+        bool k = false;
+        if (i < K) {
+            const unsigned long long w = kept_all[i >> 6];
+            const int b = i & 63;
+            k = (w >> b) & 1ull;
+            if (k) kp[kept_before[i >> 6] + __popcll(w & ((1ull << b) - 1ull))] = i;
+        }
+        km[i] = k;
+    }
+    for (int i = nkept + tid; i < keep_stride; i += kSweepThreads) kp[i] = 0;
+    if (tid == 0) count[seg] = nkept;
 }
 
 size_t nms_workspace_bytes(int nseg, int Kmax)
@@ -512,7 +557,14 @@ cudaError_t run_nms(const NmsSegs &sg, int nseg, int Kmax, const float *cfg, uns
         if (sg.labels) nms_mask_kernel<true><<<dim3(tiles, nseg), 64, 0, s>>>(sg, cfg, mask);
         else nms_mask_kernel<false><<<dim3(tiles, nseg), 64, 0, s>>>(sg, cfg, mask);
     }
-    nms_sweep_kernel<<<nseg, kSweepThreads, 0, s>>>(sg, mask, nullptr, keep_pos, keep_stride, keep_mask, mask_stride, count);
+    const size_t sweep_smem = kSweepSmem;
+    static bool sweep_configured = false;
+    if (!sweep_configured) {
+        cudaError_t e = cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem);
+        if (e != cudaSuccess) return e;
+        sweep_configured = true;
+    }
+    nms_sweep_kernel<<<nseg, kSweepThreads, sweep_smem, s>>>(sg, mask, nullptr, keep_pos, keep_stride, keep_mask, mask_stride, count);
     return cudaGetLastError();
 }
 
@@ -523,7 +575,10 @@ cudaError_t launch_nms_sweep_single(const unsigned long long *mask, const unsign
     NmsSegs sg{};
     sg.L = 1; sg.K[0] = n; sg.nbp = nbp; sg.rows_pad = ((n + 63) / 64) * 64;
     if ((n + 63) / 64 > kSweepMaxNb) return cudaErrorInvalidValue;
-    nms_sweep_kernel<<<1, kSweepThreads, 0, s>>>(sg, mask, init_removed, keep_pos, n, keep_mask, n, count);
+    const size_t sweep_smem = kSweepSmem;
+    cudaError_t e = cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem);
+    if (e != cudaSuccess) return e;
+    nms_sweep_kernel<<<1, kSweepThreads, sweep_smem, s>>>(sg, mask, init_removed, keep_pos, n, keep_mask, n, count);
     return cudaGetLastError();
 }
 
