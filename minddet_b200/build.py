@@ -12,6 +12,7 @@ HEADERS = ["common.cuh", "select.cuh", "nms.cuh", "kernels.h", "roialign_common.
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "-cudart", "static", "-Xptxas", "-v"]
+FLAGS += os.environ.get("MD_NVCC_EXTRA", "").split()   # e.g. -DMD_SEL_TIMING for a one-off instrumented build
 
 
 def _stale():

@@ -14,6 +14,37 @@ namespace md {
 
 constexpr int kMaxLevels = 8;
 
+// ---- shared memory through explicit 32-bit shared-space addresses ------------------------------------------
+// In a cluster kernel nvcc rebuilds the shared-window base from SR_CgaCtaId (S2R / S2UR) in front of nearly every
+// access made through a pointer, also inside hot loops.  smem_addr() computes the address once and hides it behind
+// an opaque asm so it stays in a register; the helpers below take such addresses.
+MD_DEVINL uint32_t smem_addr(const void *p)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+MD_DEVINL uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+MD_DEVINL uint4 lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+MD_DEVINL unsigned long long lds64(uint32_t a) { unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+MD_DEVINL void sts64(uint32_t a, unsigned long long v) { asm volatile("st.shared.b64 [%0], %1;" :: "r"(a), "l"(v) : "memory"); }
+MD_DEVINL void sts128(uint32_t a, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+MD_DEVINL uint32_t atoms_add(uint32_t a, uint32_t v)
+{
+    uint32_t r;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(a), "r"(v) : "memory");
+    return r;
+}
+MD_DEVINL void reds_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+
 // ---- explicitly rounded arithmetic ------------------------------------------------------------
 MD_DEVINL float mul(float a, float b) { return __fmul_rn(a, b); }
 MD_DEVINL float add(float a, float b) { return __fadd_rn(a, b); }

@@ -161,13 +161,15 @@ struct TopkSrc {            // one level, B segments
         const int a = m / HW, p = m - a * HW;
         return (uint32_t)(p * A + a);
     }
-    __device__ bool load(const Ctx &c, int m, uint32_t &key) const
+    __device__ const uint32_t *raw_ptr(const Ctx &c, int m) const { return reinterpret_cast<const uint32_t *>(c.base + m); }
+    __device__ bool from_raw(const Ctx &c, int, uint32_t raw, uint32_t &key) const
     {
-        float x = __ldg(c.base + m);
+        float x = __uint_as_float(raw);
         if (c.sigmoid) x = exact_sigmoid(x);
         key = score_key(x);
         return true;
     }
+    __device__ bool load(const Ctx &c, int m, uint32_t &key) const { return from_raw(c, m, __ldg(raw_ptr(c, m)), key); }
 };
 struct TopkSink {
     float *values; int32_t *indices; int K;
@@ -219,18 +221,22 @@ struct PropSrc {
         const int a = m / c.HW, q = m - a * c.HW;
         return (uint32_t)(q * c.A + a);
     }
-    __device__ bool load(const Ctx &c, int m, uint32_t &key) const
+    __device__ const uint32_t *raw_ptr(const Ctx &c, int m) const { return reinterpret_cast<const uint32_t *>(c.base + m); }
+    __device__ bool from_raw(const Ctx &c, int, uint32_t raw, uint32_t &key) const
     {
-        float x = __ldg(c.base + m);
+        float x = __uint_as_float(raw);
         if (c.sigmoid) x = exact_sigmoid(x);
         key = score_key(x);
         return true;
     }
+    __device__ bool load(const Ctx &c, int m, uint32_t &key) const { return from_raw(c, m, __ldg(raw_ptr(c, m)), key); }
 };
 struct PropSink {
     PropLevels p;
     float4 *ws_boxes; float *ws_scores; int32_t *topk_idx;
-    __device__ void emit(int seg, int rank, unsigned long long comp) const
+    struct Pre { float4 dl, bs; float sx, sy; };
+    // the four strided delta loads are the long pole of emit: start them before the ranking
+    __device__ Pre prefetch(int seg, unsigned long long comp) const
     {
         const int l = seg % p.L, b = seg / p.L;
         const int A = p.A[l], W = p.W[l], HW = p.HW[l];
@@ -238,17 +244,23 @@ struct PropSink {
         const int a = n % A, q = n / A;
         const int w = q % W, h = q / W;
         const float stride = __ldg(p.cfg + 16 + l);
-        const float sx = mul((float)w, stride), sy = mul((float)h, stride);
-        const float4 bs = __ldg(reinterpret_cast<const float4 *>(p.base[l]) + a);
-        const float4 anc = make_float4(add(bs.x, sx), add(bs.y, sy), add(bs.z, sx), add(bs.w, sy));
+        Pre r;
+        r.sx = mul((float)w, stride); r.sy = mul((float)h, stride);
+        r.bs = __ldg(reinterpret_cast<const float4 *>(p.base[l]) + a);
         const float *d = p.deltas[l] + ((int64_t)b * 4 * A + a * 4) * HW + q;
-        const float4 dl = make_float4(__ldg(d), __ldg(d + HW), __ldg(d + 2 * (int64_t)HW), __ldg(d + 3 * (int64_t)HW));
+        r.dl = make_float4(__ldg(d), __ldg(d + HW), __ldg(d + 2 * (int64_t)HW), __ldg(d + 3 * (int64_t)HW));
+        return r;
+    }
+    __device__ void emit_pre(int seg, int rank, unsigned long long comp, const Pre &r) const
+    {
+        const float4 anc = make_float4(add(r.bs.x, r.sx), add(r.bs.y, r.sy), add(r.bs.z, r.sx), add(r.bs.w, r.sy));
         const DecodeCfg c = load_decode_cfg(p.cfg);
         const int64_t o = (int64_t)seg * p.nms_pre + rank;
-        ws_boxes[o] = decode_box(anc, dl, c);
+        ws_boxes[o] = decode_box(anc, r.dl, c);
         ws_scores[o] = key_score((uint32_t)(comp >> 32));
-        topk_idx[o] = (int32_t)n;
+        topk_idx[o] = (int32_t)(~(uint32_t)comp);
     }
+    __device__ void emit(int seg, int rank, unsigned long long comp) const { emit_pre(seg, rank, comp, prefetch(seg, comp)); }
     __device__ void pad(int seg, int rank) const
     {
         const int64_t o = (int64_t)seg * p.nms_pre + rank;
