@@ -265,7 +265,7 @@ sample_prefilter_kernel(const int32_t *__restrict__ assigned, int N, uint32_t st
 struct ListSrc {
     SampleLists L; int Sp, Sn; int nimg;
     struct Ctx { const unsigned long long *items; int len, want; bool ok; };
-    __device__ int segment_of(int i) const { return i < nimg ? 2 * i + 1 : 2 * (i - nimg); }
+    __device__ int segment_of(int i, int it) const { return it ? -1 : (i < nimg ? 2 * i + 1 : 2 * (i - nimg)); }
     __device__ Ctx prepare(int seg) const
     {
         const int want = (seg & 1) ? Sn : Sp;
@@ -283,7 +283,7 @@ struct SampleSrc {
     const int32_t *assigned; int N; int Sp, Sn; uint32_t stream_base; const int32_t *seed; int nimg; SampleLists L;
     struct Ctx { const int32_t *base; int kind; uint32_t image, seed_lo, seed_hi; bool on; };
     // negatives (odd segments, ~all anchors are candidates) first, positives after
-    __device__ int segment_of(int i) const { return i < nimg ? 2 * i + 1 : 2 * (i - nimg); }
+    __device__ int segment_of(int i, int it) const { return it ? -1 : (i < nimg ? 2 * i + 1 : 2 * (i - nimg)); }
     __device__ Ctx prepare(int seg) const
     {
         const int b = seg >> 1;

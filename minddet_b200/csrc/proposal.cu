@@ -150,7 +150,7 @@ cudaError_t launch_decode_level(const float *deltas, const float *base, int B, i
 struct TopkSrc {            // one level, B segments
     const float *scores; int A, HW, N, K; const float *cfg_sigmoid;
     struct Ctx { const float *base; bool sigmoid; };
-    __device__ int segment_of(int i) const { return i; }
+    __device__ int segment_of(int i, int it) const { return it ? -1 : i; }
     __device__ bool active(const Ctx &) const { return true; }
     __device__ Ctx prepare(int seg) const { return Ctx{ scores + (int64_t)seg * N, __ldg(cfg_sigmoid) != 0.0f }; }
     __device__ int length(const Ctx &) const { return N; }
@@ -204,9 +204,16 @@ struct PropLevels {
 struct PropSrc {
     PropLevels p;
     struct Ctx { const float *base; int A, HW, N; bool sigmoid; };
-    // level-major launch order: the 8-CTA clusters of the finest (longest) level start first, so the critical
-    // path is one level-0 segment instead of two waves of them
-    __device__ int segment_of(int i) const { const int l = i / p.B, b = i - l * p.B; return b * p.L + l; }
+    // One cluster per (image, level), level-major: the clusters of the finest (longest) level start first.  About 15
+    // clusters of eight 139 KB CTAs are resident at a time; the hardware hands the freed slots to the next clusters.
+    // (Measured: giving each image two clusters that work through {0, L-1} and {1 .. L-2} in turn -- 16 clusters -- is
+    // slower, 101 vs 66 us: the 16th cluster does not fit and starts when the first level-0 segment ends.)
+    __device__ int segment_of(int i, int it) const
+    {
+        if (it) return -1;
+        const int l = i / p.B, b = i - l * p.B;
+        return b * p.L + l;
+    }
     __device__ Ctx prepare(int seg) const
     {
         const int l = seg % p.L, b = seg / p.L;

@@ -34,7 +34,7 @@ softmax_rows_kernel(const float *__restrict__ logits, int64_t rows, int nc1, flo
 struct RcnnSrc {
     const float *probs; const uint8_t *roi_valid; int P, nc1, nms_pre; const float *cfg;      // cfg[11] = score_thr
     struct Ctx { const float *base; const uint8_t *valid; float thr; };
-    __device__ int segment_of(int i) const { return i; }
+    __device__ int segment_of(int i, int it) const { return it ? -1 : i; }
     __device__ Ctx prepare(int seg) const
     {
         return Ctx{ probs + (int64_t)seg * P * nc1, roi_valid ? roi_valid + (int64_t)seg * P : nullptr, __ldg(cfg + 11) };

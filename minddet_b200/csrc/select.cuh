@@ -124,7 +124,9 @@ MD_DEVINL void bitonic_sort_desc(unsigned long long *v, int n2)
 }
 
 // Src concept:
-//   __device__ int segment_of(int launch_index) const;              launch order -> segment id (put the longest first)
+//   __device__ int segment_of(int cluster, int it) const;          it-th segment served by this cluster, -1 = no more
+//                                                                    (a cluster works through its segments in turn; give
+//                                                                    the clusters similar totals and the longest first)
 //   struct Ctx;  __device__ Ctx prepare(int seg) const;            per-segment constants (hoisted out of the loops)
 //   __device__ bool active(const Ctx&) const;                       false = this launch leaves the segment untouched
 //   __device__ int  length(const Ctx&) const;                       elements in the segment (memory order)
@@ -137,16 +139,9 @@ MD_DEVINL void bitonic_sort_desc(unsigned long long *v, int n2)
 //   __device__ void pad(int seg, int rank) const;                 ranks >= #selected, < want(seg)
 //   __device__ void finish(int seg, int selected, int candidates) const;   once per segment (thread 0)
 template <class Src, class Sink>
-__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSelThreads)
-select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
+__device__ void select_segment(const Src &src, const Sink &sink, const int cache_elems, const int seg,
+                               SelShared &sh, uint32_t *keys, uint32_t *vbits, cg::cluster_group &cluster, const int rank)
 {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    SelShared &sh = *reinterpret_cast<SelShared *>(dyn_smem);
-    uint32_t *keys = reinterpret_cast<uint32_t *>(dyn_smem + sizeof(SelShared));
-    uint32_t *vbits = keys + cache_elems;   // [cache_elems/32] validity bits
-    cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank();
-    const int seg = src.segment_of(blockIdx.x / kClusterSize);   // launch order -> segment (largest segments first)
     const int tid = threadIdx.x, lane = tid & 31;
     const typename Src::Ctx ctx = src.prepare(seg);
     if (!src.active(ctx)) return;            // uniform over the cluster: nobody reaches a cluster barrier
@@ -573,7 +568,7 @@ select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
     }
     MD_STAMP();
 #ifdef MD_SEL_TIMING
-    if (tid == 0 && blockIdx.x == 0) {
+    if (tid == 0 && blockIdx.x == 0) {       // phase durations of the first cluster's leader (one-off instrumented builds)
         printf("select N=%d K=%d sel=%d mine=%d:", N, K, selected, cnt);
         for (int i = 1; i < n_ph; i++) printf(" %lld", t_ph[i] - t_ph[i - 1]);
         printf(" cycles\n");
@@ -582,12 +577,35 @@ select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // nobody still reads my list
 }
 
+template <class Src, class Sink>
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSelThreads)
+select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    SelShared &sh = *reinterpret_cast<SelShared *>(dyn_smem);
+    uint32_t *keys = reinterpret_cast<uint32_t *>(dyn_smem + sizeof(SelShared));
+    uint32_t *vbits = keys + cache_elems;   // [cache_elems/32] validity bits
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int cid = blockIdx.x / kClusterSize;
+    for (int it = 0;; it++) {
+        const int seg = src.segment_of(cid, it);       // uniform over the cluster
+        if (seg < 0) break;
+        select_segment(src, sink, cache_elems, seg, sh, keys, vbits, cluster, rank);
+        // Shared memory is reused by the next segment.  Inside the CTA this barrier is enough; across the cluster the
+        // closing barrier.cluster.wait of a cluster-mode segment has already seen every CTA finish its remote reads,
+        // and solo segments touch no remote memory (CTAs that sat one out simply wait at the next cluster barrier).
+        __syncthreads();
+    }
+}
+
 // max_slice: the largest per-CTA slice any segment of this launch will have (host-known); decides
 // how much dynamic shared memory is spent on the key cache.
 template <class Src, class Sink>
-cudaError_t launch_select_sorted(const Src &src, const Sink &sink, int nseg, int max_segment_len,
+cudaError_t launch_select_sorted(const Src &src, const Sink &sink, int nclusters, int max_segment_len,
                                  cudaStream_t stream)
 {
+    const int nseg = nclusters;          // one cluster per segment unless Src::segment_of hands a cluster several
     if (nseg <= 0) return cudaSuccess;
     auto kern = select_sorted_kernel<Src, Sink>;
     int per = (max_segment_len + kClusterSize - 1) / kClusterSize;

@@ -172,7 +172,7 @@ cudaError_t launch_yolo_decode(const float *pred, int B, int C, int A, const flo
 struct YoloSrc {
     const float *dets; int A, nms_pre; const float *cfg;      // cfg: conf_thr, iou_thr, agnostic
     struct Ctx { const float *base; float conf; };
-    __device__ int segment_of(int i) const { return i; }
+    __device__ int segment_of(int i, int it) const { return it ? -1 : i; }
     __device__ Ctx prepare(int seg) const { return Ctx{ dets + (int64_t)seg * A * 6, __ldg(cfg) }; }
     __device__ bool active(const Ctx &) const { return true; }
     __device__ int length(const Ctx &) const { return A; }
