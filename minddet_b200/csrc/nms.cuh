@@ -13,6 +13,8 @@ struct NmsSegs {                 // segment s -> boxes + K
     int rows_pad;                // mask rows per segment (multiple of 64)
     const int32_t *labels;       // optional (nseg, seg_stride): only boxes of equal label suppress each other ...
     const float *agnostic;       // ... unless *agnostic != 0 (device flag); both null for class-agnostic NMS
+    const float *scores;         // optional (nseg, seg_stride) with kept_keys: the sweep also writes the monotone keys of
+    uint32_t *kept_keys;         // the kept boxes' scores, in kept order, (nseg, keep_stride) -- the cross-level merge's input
 };
 
 // cfg: MD_CFG_NMS (thr, offset, inclusive, union_eps) on the device; keep_pos/keep_mask strides in elements

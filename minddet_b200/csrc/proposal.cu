@@ -325,101 +325,165 @@ MD_DEVINL bool nms_suppresses(const BoxA &a, const BoxA &b, const NmsCfg &c, boo
     return c.inclusive ? (iou >= c.thr) : (iou > c.thr);
 }
 
-// grid: (triangular tile index, segment); 64 threads: thread r owns row box r of the tile.
+// grid: (tile, 1, segment) over the upper triangle of 64 x 64 tiles; 64 threads: thread r owns row box r of the tile.
+// (kMaskGroup > 1: grid (row block, group of column blocks, segment) and a block walks its group with double-buffered
+// column boxes -- kept for reference, measured slower.)
+constexpr int kMaskGroup = 1;   // measured: 4 tiles per block 67 us, 1 tile per block 58 us (short blocks hide the box loads)
+
 template <bool LABELS>
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(const NmsSegs sg, const float *__restrict__ cfg, unsigned long long *__restrict__ mask)
 {
-    const int seg = blockIdx.y;
+    const int seg = blockIdx.z;
     const int K = sg.K[seg % sg.L];
     const int nb = (K + 63) >> 6;
-    // decode the triangular index t -> (row block i, col block j), j >= i
-    const int t = blockIdx.x;
-    if (t >= nb * (nb + 1) / 2) return;
-    int i = (int)((2.0f * nb + 1.0f - sqrtf((2.0f * nb + 1.0f) * (2.0f * nb + 1.0f) - 8.0f * t)) * 0.5f);
-    while (i > 0 && i * (2 * nb - i + 1) / 2 > t) i--;
-    while ((i + 1) * (2 * nb - i) / 2 <= t) i++;
-    const int j = i + (t - i * (2 * nb - i + 1) / 2);
+    int i, j_begin, j_end;
+    if (kMaskGroup == 1) {
+        // triangular index t -> (row block i, column block j), j >= i: no empty blocks in the grid
+        const int t = blockIdx.x;
+        if (t >= nb * (nb + 1) / 2) return;
+        i = (int)((2.0f * nb + 1.0f - sqrtf((2.0f * nb + 1.0f) * (2.0f * nb + 1.0f) - 8.0f * t)) * 0.5f);
+        while (i > 0 && i * (2 * nb - i + 1) / 2 > t) i--;
+        while ((i + 1) * (2 * nb - i) / 2 <= t) i++;
+        j_begin = i + (t - i * (2 * nb - i + 1) / 2);
+        j_end = j_begin + 1;
+    } else {
+        i = blockIdx.x;
+        j_begin = max(i, (int)blockIdx.y * kMaskGroup); j_end = min(nb, ((int)blockIdx.y + 1) * kMaskGroup);
+        if (i >= nb || j_begin >= j_end) return;
+    }
 
     const NmsCfg c = load_nms_cfg(cfg);
     const bool zero_cond = c.inclusive ? (0.0f >= c.thr) : (0.0f > c.thr);
     const float *boxes = sg.boxes + (int64_t)seg * sg.seg_stride * sg.ld;
-    __shared__ float4 cbox[64];            // 128-bit + 32-bit broadcast loads per column (a 5-float struct costs 5 LDS)
-    __shared__ float carea[64];
-    __shared__ int32_t col_label[64];
+    __shared__ float4 cbox[2][64];         // 128-bit + 32-bit broadcast loads per column (a 5-float struct costs 5 LDS)
+    __shared__ float carea[2][64], cthr[2][64];  // area, thr * area
+    __shared__ int32_t col_label[2][64];
     const int tid = threadIdx.x;
     const int32_t *labels = (LABELS && sg.labels && !(sg.agnostic && __ldg(sg.agnostic) != 0.0f)) ? sg.labels + (int64_t)seg * sg.seg_stride : nullptr;
-    {
-        const int cidx = j * 64 + tid;
-        float4 b = make_float4(0, 0, 0, 0);
-        float area = 0.0f;
-        if (LABELS) col_label[tid] = (labels && cidx < K) ? labels[cidx] : 0;
-        if (cidx < K) {
-            const float *p = boxes + (int64_t)cidx * sg.ld;
-            b = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
-            area = mul(add(sub(b.z, b.x), c.off), add(sub(b.w, b.y), c.off));
-        }
-        cbox[tid] = b;
-        carea[tid] = area;
-    }
-    __syncthreads();
+    // "plain" box: non-negative width and height and an area the eps clamp cannot touch -- what the fast test below
+    // assumes of both boxes of a pair (NaNs fail every comparison and so are not plain either)
+    const float tiny = mul(4.0f, c.eps);
     const int ridx = i * 64 + tid;
-    if (ridx >= K) return;
-    BoxA a;
-    {
+    const bool row_ok = ridx < K;
+    BoxA a = { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
+    bool row_plain = true;
+    if (row_ok) {
         const float *p = boxes + (int64_t)ridx * sg.ld;
         a.x1 = __ldg(p); a.y1 = __ldg(p + 1); a.x2 = __ldg(p + 2); a.y2 = __ldg(p + 3);
         a.area = mul(add(sub(a.x2, a.x1), c.off), add(sub(a.y2, a.y1), c.off));
+        row_plain = (a.x2 >= a.x1) & (a.y2 >= a.y1) & (a.area >= tiny) & (a.area > 0.0f);
     }
-    const int ncol = min(64, K - j * 64);
-    const int start = (i == j) ? tid + 1 : 0;
     const bool use_labels = LABELS && labels;
-    const int32_t la = use_labels ? labels[ridx] : 0;
-    // all 64 columns, fully unrolled (constant bit positions), branch-free; columns outside [start, ncol) are masked
-    // off below; the rare pairs the division-free test cannot decide are redone exactly afterwards
-    uint32_t half[2] = { 0u, 0u }, unsure[2] = { 0u, 0u };
-#pragma unroll
-    for (int hh = 0; hh < 2; hh++) {
-        if (hh * 32 >= ncol || hh * 32 + 32 <= start) continue;
-        uint32_t acc = 0u, uns = 0u;
-#pragma unroll
-        for (int kk = 0; kk < 32; kk++) {
-            const int k = hh * 32 + kk;
-            const float4 bx = cbox[k];
-            const BoxA b = { bx.x, bx.y, bx.z, bx.w, carea[k] };
-            const NmsVote v = nms_vote(a, b, c);
-            bool sup = v.sup;
-            if (LABELS) sup = sup && (!use_labels || col_label[k] == la);
-            acc |= (sup ? 1u : 0u) << kk;
-            uns |= (v.unsure ? 1u : 0u) << kk;
+    const int32_t la = (use_labels && row_ok) ? labels[ridx] : 0;
+    // fast test only with the plain IoU of the detection configs (no legacy +1, a threshold away from 0)
+    const bool fast_cfg = c.off == 0.0f && c.thr >= 0.05f && c.thr <= 1.0f;
+    const float k1 = add(1.0f, c.thr), cb = div(3e-6f, c.thr), ta = mul(c.thr, a.area);
+
+    for (int j = j_begin; j < j_end; j++) {
+        const int buf = j & 1;
+        bool plain = row_plain;
+        {
+            const int cidx = j * 64 + tid;
+            float4 b = make_float4(0, 0, 0, 0);
+            float area = 0.0f;
+            if (LABELS) col_label[buf][tid] = (labels && cidx < K) ? labels[cidx] : 0;
+            if (cidx < K) {
+                const float *p = boxes + (int64_t)cidx * sg.ld;
+                b = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+                area = mul(add(sub(b.z, b.x), c.off), add(sub(b.w, b.y), c.off));
+                plain = plain & (b.z >= b.x) & (b.w >= b.y) & (area >= tiny) & (area > 0.0f);
+            }
+            cbox[buf][tid] = b;
+            carea[buf][tid] = area;
+            cthr[buf][tid] = mul(c.thr, area);
         }
-        half[hh] = acc;
-        unsure[hh] = uns;
-    }
+        // one barrier per tile: tile j + 2 rewrites this buffer only after the barrier of tile j + 1, which every thread
+        // reaches after it is done with tile j
+        const bool fast = !__syncthreads_or(!plain) && fast_cfg;
+        if (!row_ok) continue;
+        const int ncol = min(64, K - j * 64);
+        const int start = (i == j) ? tid + 1 : 0;
+        // all 64 columns, fully unrolled (constant bit positions), branch-free; columns outside [start, ncol) are masked
+        // off below; the rare pairs the division-free test cannot decide are redone exactly afterwards
+        uint32_t half[2] = { 0u, 0u }, unsure[2] = { 0u, 0u };
+        if (fast) {
+            // iou > thr  <=>  e = inter * (1 + thr) - thr * (area_a + area_b) > 0 in real arithmetic.  Evaluated in fp32,
+            // e is off by < 1e-6 * (area_a + area_b), and the oracle's rounded quotient moves the boundary by
+            // < 2e-7 * union, so outside the band |e| <= 3e-6 * (area_a + area_b) the sign of e decides exactly as the
+            // division does.  17 instructions per pair (the general test below: 32).  A half with any pair inside the
+            // band is redone exactly as a whole.
 #pragma unroll
-    for (int hh = 0; hh < 2; hh++) {
-        uint32_t u = unsure[hh];
-        while (u) {
-            const int kk = __ffs(u) - 1, k = hh * 32 + kk;
-            u &= u - 1;
-            const float4 bx = cbox[k];
-            const BoxA b = { bx.x, bx.y, bx.z, bx.w, carea[k] };
-            bool sup = nms_suppresses(a, b, c, zero_cond);
-            if (LABELS) sup = sup && (!use_labels || col_label[k] == la);
-            half[hh] = (half[hh] & ~(1u << kk)) | ((sup ? 1u : 0u) << kk);
+            for (int hh = 0; hh < 2; hh++) {
+                if (hh * 32 >= ncol || hh * 32 + 32 <= start) continue;
+                uint32_t acc = 0u;
+                bool close = false;
+#pragma unroll
+                for (int kk = 0; kk < 32; kk++) {
+                    const int k = hh * 32 + kk;
+                    const float4 bx = cbox[buf][k];
+                    const float w = fmaxf(sub(fminf(a.x2, bx.z), fmaxf(a.x1, bx.x)), 0.0f);
+                    const float h = fmaxf(sub(fminf(a.y2, bx.w), fmaxf(a.y1, bx.y)), 0.0f);
+                    const float sum = add(ta, cthr[buf][k]);
+                    const float e = __fmaf_rn(mul(w, h), k1, -sum), band = mul(sum, cb);
+                    bool sup = e > band;
+                    if (LABELS) sup = sup && (!use_labels || col_label[buf][k] == la);
+                    if (sup) acc |= 1u << kk;
+                    close = close || !(fabsf(e) > band);
+                }
+                half[hh] = acc;
+                unsure[hh] = close ? 0xFFFFFFFFu : 0u;
+            }
+        } else {
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                if (hh * 32 >= ncol || hh * 32 + 32 <= start) continue;
+                uint32_t acc = 0u, uns = 0u;
+#pragma unroll
+                for (int kk = 0; kk < 32; kk++) {
+                    const int k = hh * 32 + kk;
+                    const float4 bx = cbox[buf][k];
+                    const BoxA b = { bx.x, bx.y, bx.z, bx.w, carea[buf][k] };
+                    const NmsVote v = nms_vote(a, b, c);
+                    bool sup = v.sup;
+                    if (LABELS) sup = sup && (!use_labels || col_label[buf][k] == la);
+                    acc |= (sup ? 1u : 0u) << kk;
+                    uns |= (v.unsure ? 1u : 0u) << kk;
+                }
+                half[hh] = acc;
+                unsure[hh] = uns;
+            }
         }
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            uint32_t u = unsure[hh];
+            while (u) {
+                const int kk = __ffs(u) - 1, k = hh * 32 + kk;
+                u &= u - 1;
+                const float4 bx = cbox[buf][k];
+                const BoxA b = { bx.x, bx.y, bx.z, bx.w, carea[buf][k] };
+                bool sup = nms_suppresses(a, b, c, zero_cond);
+                if (LABELS) sup = sup && (!use_labels || col_label[buf][k] == la);
+                half[hh] = (half[hh] & ~(1u << kk)) | ((sup ? 1u : 0u) << kk);
+            }
+        }
+        unsigned long long bits = ((unsigned long long)half[1] << 32) | half[0];
+        const unsigned long long lo_mask = start >= 64 ? 0ull : (~0ull << start);
+        const unsigned long long hi_mask = ncol >= 64 ? ~0ull : ((1ull << ncol) - 1ull);
+        bits &= lo_mask & hi_mask;
+        mask[((int64_t)seg * sg.rows_pad + ridx) * sg.nbp + j] = bits;
     }
-    unsigned long long bits = ((unsigned long long)half[1] << 32) | half[0];
-    const unsigned long long lo_mask = start >= 64 ? 0ull : (~0ull << start);
-    const unsigned long long hi_mask = ncol >= 64 ? ~0ull : ((1ull << ncol) - 1ull);
-    bits &= lo_mask & hi_mask;
-    mask[((int64_t)seg * sg.rows_pad + ridx) * sg.nbp + j] = bits;
 }
 
 MD_DEVINL void cp_async16(void *smem, const void *gmem)
 {
     const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gmem) : "memory");
+}
+MD_DEVINL void cp_async4(void *smem, const void *gmem)
+{
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa), "l"(gmem) : "memory");
 }
 MD_DEVINL void cp_async8(void *smem, const void *gmem)
 {
@@ -456,6 +520,7 @@ nms_sweep_kernel(const NmsSegs sg, const unsigned long long *__restrict__ mask,
     __shared__ unsigned long long removed[kSweepMaxNb];      // word j of "suppressed by an earlier kept box"
     __shared__ unsigned long long kept_all[kSweepMaxNb];
     __shared__ int kept_before[kSweepMaxNb + 1];
+    __shared__ float score_sh[64 * kSweepMaxNb];
     const int seg = blockIdx.x;
     const int K = sg.K[seg % sg.L];
     const int nb = (K + 63) >> 6, nbp = sg.nbp;
@@ -481,8 +546,15 @@ nms_sweep_kernel(const NmsSegs sg, const unsigned long long *__restrict__ mask,
     };
 
     if (tid < kSweepMaxNb) removed[tid] = (init_removed && tid < nb) ? init_removed[(int64_t)seg * nbp + tid] : 0ull;
-    if (warp > 0)
+    if (warp > 0) {
+        // scores of the segment (only when the kept keys are wanted): they ride in the first cp.async group, so the
+        // epilogue finds them in shared memory instead of paying an L2 round trip per kept box
+        if (sg.kept_keys) {
+            const float *sc = sg.scores + (int64_t)seg * sg.seg_stride;
+            for (int q = htid; q < K; q += 32 * kSweepHelpers) cp_async4(&score_sh[q], sc + q);
+        }
         for (int c = 0; c < kSweepStages - 2; c++) issue(c);
+    }
     constexpr int kRowsPerWarp = 64 / kSweepHelpers;
     for (int c = 0; c < nb; c++) {
         if (warp > 0) cp_async_wait<kSweepStages - 3>();        // chunk c has landed (this thread's pieces)
@@ -550,7 +622,11 @@ nms_sweep_kernel(const NmsSegs sg, const unsigned long long *__restrict__ mask,
             const unsigned long long w = kept_all[i >> 6];
             const int b = i & 63;
             k = (w >> b) & 1ull;
-            if (k) kp[kept_before[i >> 6] + __popcll(w & ((1ull << b) - 1ull))] = i;
+            if (k) {
+                const int r = kept_before[i >> 6] + __popcll(w & ((1ull << b) - 1ull));
+                kp[r] = i;
+                if (sg.kept_keys) sg.kept_keys[(int64_t)seg * keep_stride + r] = score_key(score_sh[i]);
+            }
         }
         km[i] = k;
     }
@@ -573,8 +649,9 @@ cudaError_t run_nms(const NmsSegs &sg, int nseg, int Kmax, const float *cfg, uns
     if (nb > kSweepMaxNb) return cudaErrorInvalidValue;
     const int tiles = nb * (nb + 1) / 2;
     if (tiles > 0) {
-        if (sg.labels) nms_mask_kernel<true><<<dim3(tiles, nseg), 64, 0, s>>>(sg, cfg, mask);
-        else nms_mask_kernel<false><<<dim3(tiles, nseg), 64, 0, s>>>(sg, cfg, mask);
+        const dim3 grid = kMaskGroup == 1 ? dim3(tiles, 1, nseg) : dim3(nb, (nb + kMaskGroup - 1) / kMaskGroup, nseg);
+        if (sg.labels) nms_mask_kernel<true><<<grid, 64, 0, s>>>(sg, cfg, mask);
+        else nms_mask_kernel<false><<<grid, 64, 0, s>>>(sg, cfg, mask);
     }
     const size_t sweep_smem = kSweepSmem;
     static bool sweep_configured = false;
@@ -622,68 +699,69 @@ constexpr int kMergeSplit = 16;
 
 __global__ void __launch_bounds__(kMergeThreads)
 merge_levels_kernel(int L, int nms_pre, int max_num, const float4 *__restrict__ ws_boxes,
-                    const float *__restrict__ ws_scores, const uint8_t *__restrict__ keep_mask,
+                    const uint32_t *__restrict__ kept_keys,
                     const int32_t *__restrict__ keep_pos, const int32_t *__restrict__ count,
                     float *__restrict__ props, uint8_t *__restrict__ pmask)
 {
     extern __shared__ uint32_t kkeys[];   // [L][nms_pre] keys of the kept boxes, descending per level
-    __shared__ int cnt[kMaxLv], cum[kMaxLv + 1];
+    __shared__ int cnt[kMaxLv];
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
-    if (tid == 0) {
-        int c = 0;
-        for (int l = 0; l < L; l++) { cnt[l] = count[b * L + l]; cum[l] = c; c += cnt[l]; }
-        cum[L] = c;
-    }
+    if (tid < L) cnt[tid] = count[b * L + tid];
     __syncthreads();
-    for (int i = tid; i < L * nms_pre; i += kMergeThreads) {
-        const int l = i / nms_pre, t = i - l * nms_pre;
-        if (t < cnt[l]) {
-            const int64_t seg = (int64_t)b * L + l;
-            kkeys[i] = score_key(ws_scores[seg * nms_pre + keep_pos[seg * nms_pre + t]]);
+    // keys of the kept boxes, written in kept order by the NMS sweep (gathering them here through keep_pos -> score,
+    // once per y-block, was 80 MB of L2 sector traffic and most of this kernel's 25 us)
+    if ((nms_pre & 3) == 0) {
+        // 16-byte cp.async pieces, all in flight at once (a load-then-store loop waited one L2 round trip per piece)
+        const int q = nms_pre >> 2;
+        for (int i = tid; i < L * q; i += kMergeThreads) {
+            const int l = i / q, p4 = (i - l * q) * 4;
+            if (p4 < cnt[l]) cp_async16(kkeys + l * nms_pre + p4, kept_keys + ((int64_t)b * L + l) * nms_pre + p4);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+    } else {
+        for (int i = tid; i < L * nms_pre; i += kMergeThreads) {
+            const int l = i / nms_pre, t = i - l * nms_pre;
+            if (t < cnt[l]) kkeys[i] = kept_keys[((int64_t)b * L + l) * nms_pre + t];
         }
     }
     __syncthreads();
-    const int total_kept = cum[L];
-    const int total = L * nms_pre;   // concat index space (padded slots are never kept; see below)
-    for (int e = blockIdx.y * kMergeThreads + tid; e < total; e += kMergeSplit * kMergeThreads) {
-        const int l = e / nms_pre, i = e - l * nms_pre;
+    // one kept box per thread: entry t of level l's kept list.  Its rank inside its level is t itself; the other levels
+    // contribute a branch-free lower bound each, all in lockstep (the searches are independent)
+    int top_step = 1;
+    while (top_step * 2 <= nms_pre) top_step <<= 1;
+    for (int e = blockIdx.y * kMergeThreads + tid; e < L * nms_pre; e += kMergeSplit * kMergeThreads) {
+        const int l = e / nms_pre, t = e - l * nms_pre;
+        if (t >= cnt[l]) continue;
         const int64_t seg = (int64_t)b * L + l;
-        const bool kept = keep_mask[seg * nms_pre + i] != 0;
-        // #kept in my level at positions < i  (keep_pos is ascending)
-        int lo = 0, hi = cnt[l];
-        const int32_t *kp = keep_pos + seg * nms_pre;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (kp[mid] < i) lo = mid + 1; else hi = mid; }
-        const int before_in_level = lo;
-        int rank;
-        if (kept) {
-            const uint32_t key = score_key(ws_scores[seg * nms_pre + i]);
-            rank = before_in_level;
-            for (int l2 = 0; l2 < L; l2++) {
-                if (l2 == l) continue;
+        const int i = keep_pos[seg * nms_pre + t];               // position in the level's pre-NMS list
+        const float4 bx = ws_boxes[seg * nms_pre + i];
+        const uint32_t key = kkeys[e];
+        int pos[kMaxLv];
+#pragma unroll
+        for (int l2 = 0; l2 < kMaxLv; l2++) pos[l2] = 0;
+        for (int st = top_step; st > 0; st >>= 1) {
+#pragma unroll
+            for (int l2 = 0; l2 < kMaxLv; l2++) {
+                if (l2 >= L) break;
                 // #kept in level l2 that sort before me: key2 > key, or == when l2 < l
-                const uint32_t *kk = kkeys + l2 * nms_pre;
-                int a = 0, z = cnt[l2];
-                while (a < z) {
-                    const int mid = (a + z) >> 1;
-                    const uint32_t k2 = kk[mid];
-                    const bool before = (l2 < l) ? (k2 >= key) : (k2 > key);
-                    if (before) a = mid + 1; else z = mid;
+                const int probe = pos[l2] + st;
+                if (probe <= cnt[l2]) {
+                    const uint32_t k2 = kkeys[l2 * nms_pre + probe - 1];
+                    if ((l2 < l) ? (k2 >= key) : (k2 > key)) pos[l2] = probe;
                 }
-                rank += a;
             }
-        } else {
-            // padded slots (i >= K_l) of a level must not be counted as suppressed boxes
-            // -> caller guarantees keep_mask==0 there and we skip them via the valid-count below
-            rank = -1;
         }
-        if (kept && rank < max_num) {
-            const float4 bx = ws_boxes[seg * nms_pre + i];
+        int rank = t;
+#pragma unroll
+        for (int l2 = 0; l2 < kMaxLv; l2++)
+            if (l2 < L && l2 != l) rank += pos[l2];
+        if (rank < max_num) {
             float *o = props + ((int64_t)b * max_num + rank) * 5;
-            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = ws_scores[seg * nms_pre + i];
+            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = key_score(key);
             pmask[(int64_t)b * max_num + rank] = 1;
         }
-        (void)total_kept;
     }
 }
 
@@ -734,7 +812,7 @@ merge_suppressed_kernel(int L, int nms_pre, int max_num, const int *__restrict__
 
 // workspace layout (all per segment = b*L + l, nms_pre rows each)
 struct PropWs {
-    float4 *boxes; float *scores; int32_t *keep_pos; int32_t *count; unsigned long long *mask;
+    float4 *boxes; float *scores; int32_t *keep_pos; uint32_t *kept_keys; int32_t *count; unsigned long long *mask;
 };
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 static PropWs carve_prop_ws(void *ws, int nseg, int nms_pre, size_t *total)
@@ -745,6 +823,7 @@ static PropWs carve_prop_ws(void *ws, int nseg, int nms_pre, size_t *total)
     w.boxes = reinterpret_cast<float4 *>(p + o); o += align256((size_t)nseg * nms_pre * sizeof(float4));
     w.scores = reinterpret_cast<float *>(p + o); o += align256((size_t)nseg * nms_pre * sizeof(float));
     w.keep_pos = reinterpret_cast<int32_t *>(p + o); o += align256((size_t)nseg * nms_pre * sizeof(int32_t));
+    w.kept_keys = reinterpret_cast<uint32_t *>(p + o); o += align256((size_t)nseg * nms_pre * sizeof(uint32_t));
     w.count = reinterpret_cast<int32_t *>(p + o); o += align256((size_t)nseg * sizeof(int32_t));
     w.mask = reinterpret_cast<unsigned long long *>(p + o); o += nms_workspace_bytes(nseg, nms_pre);
     if (total) *total = o;
@@ -781,6 +860,7 @@ cudaError_t launch_proposal(const LevelSet &lv, int B, int nms_pre, int max_num,
     cudaError_t e = launch_select_sorted(PropSrc{ pl }, PropSink{ pl, w.boxes, w.scores, topk_idx }, nseg, maxN, s);
     if (e != cudaSuccess) return e;
     sg.boxes = reinterpret_cast<const float *>(w.boxes); sg.ld = 4; sg.seg_stride = nms_pre; sg.L = L;
+    sg.scores = w.scores; sg.kept_keys = w.kept_keys;
     const int nb = (nms_pre + 63) / 64;
     sg.nbp = (nb + 1) & ~1; sg.rows_pad = nb * 64;
     e = run_nms(sg, nseg, Kmax, cfg + 11, w.mask, w.keep_pos, nms_pre, keep, nms_pre, w.count, s);
@@ -793,7 +873,7 @@ cudaError_t launch_proposal(const LevelSet &lv, int B, int nms_pre, int max_num,
         configured = true;
     }
     merge_levels_kernel<<<dim3(B, kMergeSplit), kMergeThreads, smem, s>>>(
-        L, nms_pre, max_num, w.boxes, w.scores, keep, w.keep_pos, w.count, props, pmask);
+        L, nms_pre, max_num, w.boxes, w.kept_keys, w.keep_pos, w.count, props, pmask);
     merge_suppressed_kernel<<<dim3(B, kMergeSplit), kMergeThreads, 0, s>>>(
         L, nms_pre, max_num, nullptr, w.boxes, w.scores, keep, w.keep_pos, w.count, sg, props, pmask);
     return cudaGetLastError();
