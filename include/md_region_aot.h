@@ -129,6 +129,14 @@ MD_API int MdRoiAlignFwd(MD_AOT_ARGS);
  *   out: dfeat_0..dfeat_{L-1} (B,C,H_l,W_l) f32     (nparam = 3+L) */
 MD_API int MdRoiAlignBwd(MD_AOT_ARGS);
 
+/* a11, accumulating form: dfeat_l += ROIAlignGrad(dout) into tensors the caller owns and has initialised (zeros for a
+ * plain bprop; an existing gradient for gradient accumulation).  The zero-fill is 731 MB of pure DRAM writes per step
+ * at config 2; as its own node it has no producer, so a graph executor can run it beside the latency-bound Proposal
+ * chain instead of in front of the RoIAlign backward (bench.py does; --no-overlap uses MdRoiAlignBwd).
+ *   in : rois (R,5) f32 | dout (R,C,P,P) f32 | cfg f32[4+L] | acc_0..acc_{L-1} (B,C,H_l,W_l) f32 (read-modify-write)
+ *   out: done (1) int32 = 0      (nparam = 3+L+1) */
+MD_API int MdRoiAlignBwdAcc(MD_AOT_ARGS);
+
 /* Bit-exact variants: same I/O, gather kernels only (forward bit-identical to the oracle's op order;
  * used for levels/footprints the TMA path declines, and selectable by symbol because attributes cannot
  * be read on the host from a device cfg tensor). */

@@ -21,7 +21,7 @@ _DTYPE_NAMES = {
 }
 
 SYMBOLS = ("MdAnchorGrid", "MdDecodeClip", "MdDecodeLevel", "MdTopKPerLevel", "MdNms", "MdProposal",
-           "MdAssignSample", "MdAssignSampleRcnn", "MdRoiLevels", "MdRoiAlignFwd", "MdRoiAlignBwd",
+           "MdAssignSample", "MdAssignSampleRcnn", "MdRoiLevels", "MdRoiAlignFwd", "MdRoiAlignBwd", "MdRoiAlignBwdAcc",
            "MdRoiAlignFwdExact", "MdRoiAlignBwdExact",
            # the reference's own GPU symbols (iou3d_nms_kernel.cu:445-601) + the device twin of boxes_iou_nms_cpu
            "BoxesIouBevGpu", "BoxesOverlapBevGpu", "NmsGpu", "NmsNormalGpu", "BoxesIouNmsGpu",

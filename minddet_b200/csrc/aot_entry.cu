@@ -320,6 +320,29 @@ static int roialign_bwd_impl(int mode, MD_AOT_ARGS)
     return cuda_rc(md::launch_roialign_bwd(fs, (const float *)params[0], R, P, (const float *)params[2],
                                            (const float *)params[1], ws, mode, (cudaStream_t)stream));
 }
+static int roialign_bwd_acc_impl(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam < 5) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    const int L = nparam - 4;
+    md::FeatSet fs{};
+    int rc = parse_feats(L, 3, params, ndims, shapes, dtypes, &fs);     // the accumulators sit where MdRoiAlignBwd has its outputs
+    if (rc) return rc;
+    REQ(is_f32(dtypes[0]) && ndims[0] == 2 && shapes[0][1] == 5);
+    const int R = (int)shapes[0][0];
+    REQ(is_f32(dtypes[1]) && ndims[1] == 4 && shapes[1][0] == R && shapes[1][1] == fs.C && shapes[1][2] == shapes[1][3]);
+    REQ(is_f32(dtypes[2]) && numel(ndims[2], shapes[2]) >= MD_ROI_STRIDE0 + L);
+    REQ(is_i32(dtypes[nparam - 1]) && numel(ndims[nparam - 1], shapes[nparam - 1]) >= 1);
+    const int P = (int)shapes[1][2];
+    void *ws = nullptr;
+    rc = get_workspace(stream, md::roialign_workspace_bytes(R), &ws);
+    if (rc) return rc;
+    rc = cuda_rc(cudaMemsetAsync(params[nparam - 1], 0, sizeof(int32_t), (cudaStream_t)stream));
+    if (rc) return rc;
+    return cuda_rc(md::launch_roialign_bwd(fs, (const float *)params[0], R, P, (const float *)params[2],
+                                           (const float *)params[1], ws, 0, (cudaStream_t)stream, true));
+}
 
 // ---- the reference's own GPU symbols (iou3d_nms_kernel.cu:445-601), same parameter lists ------------------------
 static int bev_pairs_impl(int want_iou, MD_AOT_ARGS)
@@ -445,6 +468,7 @@ int MdYoloNms(MD_AOT_ARGS)
 
 int MdRoiAlignFwd(MD_AOT_ARGS) { return roialign_fwd_impl(0, nparam, params, ndims, shapes, dtypes, stream, extra); }
 int MdRoiAlignBwd(MD_AOT_ARGS) { return roialign_bwd_impl(0, nparam, params, ndims, shapes, dtypes, stream, extra); }
+int MdRoiAlignBwdAcc(MD_AOT_ARGS) { return roialign_bwd_acc_impl(nparam, params, ndims, shapes, dtypes, stream, extra); }
 int MdRoiAlignFwdExact(MD_AOT_ARGS) { return roialign_fwd_impl(1, nparam, params, ndims, shapes, dtypes, stream, extra); }
 int MdRoiAlignBwdExact(MD_AOT_ARGS) { return roialign_bwd_impl(1, nparam, params, ndims, shapes, dtypes, stream, extra); }
 

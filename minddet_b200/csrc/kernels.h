@@ -86,6 +86,6 @@ size_t roialign_workspace_bytes(int R);
 cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
                                 float *out, void *ws, int mode, cudaStream_t s);
 cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
-                                const float *dout, void *ws, int mode, cudaStream_t s);
+                                const float *dout, void *ws, int mode, cudaStream_t s, bool accumulate = false);
 
 }  // namespace md

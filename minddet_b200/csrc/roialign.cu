@@ -185,10 +185,10 @@ cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, in
 }
 
 cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
-                                const float *dout, void *ws, int mode, cudaStream_t s)
+                                const float *dout, void *ws, int mode, cudaStream_t s, bool accumulate)
 {
     if (P * P * 4 > kRoiMaxTaps || fs.L > kMaxLv) return cudaErrorInvalidValue;
-    for (int l = 0; l < fs.L; l++) {
+    for (int l = 0; l < fs.L && !accumulate; l++) {
         cudaError_t e = cudaMemsetAsync(fs.feat[l], 0, (size_t)fs.B * fs.C * fs.H[l] * fs.W[l] * sizeof(float), s);
         if (e != cudaSuccess) return e;
     }

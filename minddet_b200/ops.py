@@ -256,6 +256,7 @@ class SingleRoIExtractor(_Cell):
         self.cfg_values = [float(finest_scale), float(sample_num), float(roi_end_mode), 0.0] + self.strides
         self._fwd = Custom(_so("MdRoiAlignFwdExact" if exact else "MdRoiAlignFwd"), None, torch.float32)
         self._bwd = Custom(_so("MdRoiAlignBwdExact" if exact else "MdRoiAlignBwd"), None, torch.float32)
+        self._bwd_acc = None if exact else Custom(_so("MdRoiAlignBwdAcc"), lambda *s: (1,), torch.int32)
         self._lvl = Custom(_so("MdRoiLevels"), lambda r, c: (r[0],), torch.int32)
 
     def map_roi_levels(self, rois):
@@ -270,6 +271,14 @@ class SingleRoIExtractor(_Cell):
         self._bwd.out_shape = lambda *s: tuple(feat_shapes)
         out = self._bwd(rois, dout, self._cfg(self.cfg_values, rois.device))
         return out if isinstance(out, tuple) else (out,)
+
+    def _backward_into(self, rois, dout, grads):
+        """Accumulating bprop (``MdRoiAlignBwdAcc``): grads_l += ROIAlignGrad(dout); the caller has initialised ``grads``
+        (zeros for a plain bprop -- as a node of its own that zero-fill can run early, beside other work)."""
+        if self._bwd_acc is None:
+            raise RuntimeError("the exact RoIAlign variant has no accumulating backward")
+        self._bwd_acc(rois, dout, self._cfg(self.cfg_values, rois.device), *grads)
+        return tuple(grads)
 
     def construct(self, rois, *feats):
         if any(f.requires_grad for f in feats):
