@@ -54,10 +54,16 @@ constexpr int kNumBW = kMaxBW / 4;         // tensor maps per level
 constexpr int kTmaLevels = 4;
 constexpr int kMaxRowsBwd = 128;           // backward row-table capacity
 
-struct TmaMaps { CUtensorMap m[kTmaLevels * kNumBW]; };   // [level][bw/4 - 1], box = {bw, 4, CPW(bw)}
+constexpr int kMapsPerLevel = kNumBW + 1;  // + one padded map, see fwd_box_width()
+struct TmaMaps { CUtensorMap m[kTmaLevels * kMapsPerLevel]; };   // [level][bw/4 - 1], box = {bw, 4, CPW(bw)}; [level][kNumBW] = {20, 4, 8}
 
 struct __align__(16) SampleTap { int lo, hi; float wl, wh; };   // rows/cols relative to the footprint origin
 
+// Forward only: row pitch of the staged box.  With 4 lanes per channel a quarter-warp's LDS.128 covers two channels,
+// and when the channel stride 4 rows * bw * 4 B is a multiple of 128 B (bw = 8, 16) both land in the same banks: every
+// row read was a 2-way conflict (1.7x the ideal wavefronts over the kernel, which is bound by that pipe).  Four unused
+// columns of padding move the second channel to the other half of the banks.
+__host__ __device__ inline int fwd_box_width(int bw) { return (bw == 8 || bw == 16) ? bw + 4 : bw; }
 __host__ __device__ inline int lanes_per_channel(int bw) { return bw <= 16 ? 4 : (bw <= 32 ? 8 : (bw <= 64 ? 16 : 32)); }
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -248,21 +254,22 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
         return;
     }
     const int LPC = lanes_per_channel(BW), CPW = 32 / LPC, BWU = 4 * LPC + 4;
+    const int BWS = fwd_box_width(BW);                               // row pitch of the staged box (>= BW)
     const int lshift = LPC == 4 ? 2 : (LPC == 8 ? 3 : (LPC == 16 ? 4 : 5));
     const int csub = lane >> lshift, xq = lane & (LPC - 1);
     const bool col_ok = 4 * xq < BW;
     const int x_lo = sh.x_lo, y_lo = sh.y_lo, h_fp = sh.h_fp;
     const int nblk = (h_fp + 3) >> 2;
-    const int BLK = CPW * 4 * BW, SLOT = (BLK + 31) & ~31;
+    const int BLK = CPW * 4 * BWS, SLOT = (BLK + 31) & ~31;
     const int ngroups = CH / CPW;                                     // host guarantees CH % 8 == 0
     const int ng_w = (ngroups - warp + kStWarps - 1) / kStWarps;      // groups warp, warp+4, ...
     float *ring = ring_all + warp * kRingFloats;
     unsigned long long *full = sh.full[warp];
-    const CUtensorMap *map = &maps.m[g.l * kNumBW + (BW >> 2) - 1];
+    const CUtensorMap *map = &maps.m[g.l * kMapsPerLevel + (BWS == 20 && BW == 16 ? kNumBW : (BWS >> 2) - 1)];
     const int H = g.H, W = g.W;
     const float *fplane = f.feat[g.l] + ((int64_t)g.b * C + cbase) * H * W;
     const int zbase = g.b * C + cbase;
-    const int lane_off = csub * 4 * BW + 4 * xq;          // this lane's float offset inside a row block
+    const int lane_off = csub * 4 * BWS + 4 * xq;          // this lane's float offset inside a row block
 
     // one row block (BW x 4 rows x CPW channels) of channel group `grp` -> dst, completion on `bar`
     auto load_block = [&](float *dst, int grp, int j, unsigned long long *bar) {
@@ -272,8 +279,8 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
         } else {
             // elements outside the map are never used with a non-zero weight (rows/cols clamp): left unwritten
             for (int e = lane; e < BLK; e += 32) {
-                const int c = e / (4 * BW), rem = e - c * (4 * BW);
-                const int rr = rem / BW, xx = rem - rr * BW;
+                const int c = e / (4 * BWS), rem = e - c * (4 * BWS);
+                const int rr = rem / BWS, xx = rem - rr * BWS;
                 const int y = y_lo + 4 * j + rr, x = x_lo + xx;
                 if (y < H && x < W) cp_async4(dst + e, fplane + ((int64_t)(c0 + c) * H + y) * W + x);
             }
@@ -312,7 +319,7 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
         if (warp == 0 && lane < NS) {
             const SampleTap t = sh.ytab[lane];
             SampleTap o;
-            o.lo = (t.lo >> 2) * SLOT + (t.lo & 3) * BW; o.hi = (t.hi >> 2) * SLOT + (t.hi & 3) * BW; o.wl = t.wl; o.wh = t.wh;
+            o.lo = (t.lo >> 2) * SLOT + (t.lo & 3) * BWS; o.hi = (t.hi >> 2) * SLOT + (t.hi & 3) * BWS; o.wl = t.wl; o.wh = t.wh;
             yoff[lane] = o;
         }
         __syncthreads();
@@ -398,8 +405,8 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
                 int hi_slot = cur_slot;
                 if (bhi != blo) { hi_slot = cur_slot + 1; if (hi_slot == NB) hi_slot = 0; }
                 if (col_ok) {
-                    const float4 a = *reinterpret_cast<const float4 *>(ring + cur_slot * SLOT + (t.lo & 3) * BW + lane_off);
-                    const float4 b = *reinterpret_cast<const float4 *>(ring + hi_slot * SLOT + (t.hi & 3) * BW + lane_off);
+                    const float4 a = *reinterpret_cast<const float4 *>(ring + cur_slot * SLOT + (t.lo & 3) * BWS + lane_off);
+                    const float4 b = *reinterpret_cast<const float4 *>(ring + hi_slot * SLOT + (t.hi & 3) * BWS + lane_off);
                     a0 = __fmaf_rn(t.wl, a.x, __fmaf_rn(t.wh, b.x, a0));
                     a1 = __fmaf_rn(t.wl, a.y, __fmaf_rn(t.wh, b.y, a1));
                     a2 = __fmaf_rn(t.wl, a.z, __fmaf_rn(t.wh, b.z, a2));
@@ -582,7 +589,7 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
     const int ng_w = (ngroups - warp + kStWarps - 1) / kStWarps;
     float *ring = ring_all + warp * kBwdRingFloats;
     float *Gs = G_all + warp * NBUF * kGFloats;
-    const CUtensorMap *map = &maps.m[g.l * kNumBW + (BW >> 2) - 1];
+    const CUtensorMap *map = &maps.m[g.l * kMapsPerLevel + (BW >> 2) - 1];
     const int H = g.H, W = g.W;
     float *dplane = f.feat[g.l] + ((int64_t)g.b * C + cbase) * H * W;
     const float *grow = dout + ((int64_t)r * C + cbase) * PP;
@@ -749,8 +756,18 @@ static int build_maps(const FeatSet &fs, TmaMaps *out)
                 const cuuint64_t strides[2] = { (cuuint64_t)fs.W[l] * 4, (cuuint64_t)fs.W[l] * fs.H[l] * 4 };
                 const cuuint32_t box[3] = { (cuuint32_t)bw, 4u, (cuuint32_t)(32 / lanes_per_channel(bw)) };
                 const cuuint32_t estr[3] = { 1, 1, 1 };
-                ok = enc(&c.maps.m[l * kNumBW + k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, fs.feat[l], dims, strides, box, estr,
+                ok = enc(&c.maps.m[l * kMapsPerLevel + k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, fs.feat[l], dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2promo,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            }
+            if (ok) {
+                // the padded forward box for 16-column footprints: 20 columns but still 8 channels (see fwd_box_width)
+                const cuuint64_t dims[3] = { (cuuint64_t)fs.W[l], (cuuint64_t)fs.H[l], (cuuint64_t)fs.B * fs.C };
+                const cuuint64_t strides[2] = { (cuuint64_t)fs.W[l] * 4, (cuuint64_t)fs.W[l] * fs.H[l] * 4 };
+                const cuuint32_t box[3] = { 20u, 4u, 8u };
+                const cuuint32_t estr[3] = { 1, 1, 1 };
+                ok = enc(&c.maps.m[l * kMapsPerLevel + kNumBW], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, fs.feat[l], dims, strides, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2promo,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
             }
             if (ok) c.mask |= 1 << l;
