@@ -227,7 +227,11 @@ def run_b200(args):
             cur = torch.cuda.current_stream()
             fork.record(cur)
             aux.wait_event(fork)
-            with torch.cuda.stream(aux):     # (measured: started beside the RoIAlign forward instead, the step is 25 us longer)
+            if os.environ.get("MD_BENCH_DIAG_SKIP_SIDE") in ("both", "rpn"):      # diagnosis only: the chain alone (results are NOT a bench value)
+                rpn = None
+                join.record(aux)
+            else:
+              with torch.cuda.stream(aux):     # (measured: started beside the RoIAlign forward instead, the step is 25 us longer)
                 rpn = rp.rpn_targets(inp["gts"], inp["gt_valid"], anchors, avalid)
                 join.record(aux)
         nh = args.split if timers is None else 1
@@ -237,7 +241,10 @@ def run_b200(args):
             # stream beside the latency-bound Proposal chain and the backward accumulates (MdRoiAlignBwdAcc).
             zstream.wait_event(fork)
             with torch.cuda.stream(zstream):
-                zeroed = [torch.zeros_like(f) for f in inp["feats"]]
+                # (a fill confined to a few SMs -- persistent store loop on 16..64 CTAs, or cp.async.bulk from a zeroed
+                # shared-memory block -- was measured too: an SM sustains ~60 GB/s of stores, so it only gets slower)
+                zeroed = [torch.empty_like(f) if os.environ.get("MD_BENCH_DIAG_SKIP_SIDE") in ("both", "zero") else torch.zeros_like(f)
+                          for f in inp["feats"]]
                 zjoin.record(zstream)
 
         def chain(a, b):
@@ -366,6 +373,9 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1) / K
+        if os.environ.get("MD_BENCH_DIAG_SKIP_SIDE"):
+            print(f"[diag] skipped side work = {os.environ['MD_BENCH_DIAG_SKIP_SIDE']}: {ms:.4f} ms / step", file=sys.stderr, flush=True)
+            os._exit(0)
 
         # per-stage durations, live with CUDA events on the launching stream (eager, same kernels), K passes
         per = {}

@@ -8,6 +8,8 @@
 // Forward arithmetic uses explicitly rounded mul/add in the oracle's order, so the result is
 // bit-identical to oracle/region_oracle.c:o_roialign_fwd.  Backward accumulates with float atomics
 // (order is not deterministic -> FP tolerance only, as north_star allows).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "roialign_common.cuh"
 
