@@ -207,7 +207,7 @@ int MdAssignSample(MD_AOT_ARGS)
     REQ(numel(ndims[o + 7], shapes[o + 7]) == B);
     if (Sp > 2048 || Sn > 2048 || N >= (1 << 22) || G > 1024) return MD_ERR_SIZE;
     void *ws = nullptr;
-    int rc = get_workspace(stream, md::assign_workspace_bytes(B, G), &ws);
+    int rc = get_workspace(stream, md::assign_workspace_bytes(B, G, N), &ws);
     if (rc) return rc;
     return cuda_rc(md::launch_assign_sample_rpn(
         (const float *)params[0], per_image, (const uint8_t *)params[1], B, N, (const float *)params[2],
@@ -242,7 +242,7 @@ int MdAssignSampleRcnn(MD_AOT_ARGS)
         numel(ndims[o + 5], shapes[o + 5]) == (int64_t)B * S && numel(ndims[o + 7], shapes[o + 7]) == B);
     if (Sp > 2048 || Sn > 2048 || G + P >= (1 << 22) || G > 1024) return MD_ERR_SIZE;
     void *ws = nullptr;
-    int rc = get_workspace(stream, md::assign_workspace_bytes(B, G), &ws);
+    int rc = get_workspace(stream, md::assign_workspace_bytes(B, G, P), &ws);
     if (rc) return rc;
     return cuda_rc(md::launch_assign_sample_rcnn(
         (const float *)params[0], (const uint8_t *)params[1], B, P, (const float *)params[2], (const int32_t *)params[3],

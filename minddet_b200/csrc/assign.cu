@@ -4,8 +4,9 @@
 // (per-anchor argmax :90-93, per-gt max with every tie force-matched :94-103, thresholds :104-108) with
 // the IoU of pointpillars/src/core/box_np_ops.py:639-679 (iou_jit, eps=1).  The reference materialises the
 // (N x G) overlap matrix on the host per sample; here it is NEVER materialised: every thread streams the
-// (<=G) valid gts from shared memory, once to build the per-gt maxima (kernel 1) and once more to
-// label (kernel 2) -- recomputing is cheaper than a 2x4-byte-per-anchor round trip through HBM.
+// (<=G) valid gts its warp can touch from shared memory and builds the per-gt maxima and its own (max IoU,
+// arg-max) in one pass (kernel 1, 8 bytes per box kept); kernel 2 labels from those 8 bytes and walks the gts
+// again only in the few warps that hold a box good enough to be some gt's best (the force-match rule).
 // Sampling replaces npr.choice (:116-128) by "k smallest Philox keys" (oracle/CONVENTIONS.md #13) on
 // the cluster radix-select of select.cuh.
 #include "kernels.h"
@@ -97,7 +98,8 @@ MD_DEVINL uint32_t warp_hits(const GtS *sg, int ng, int base, const WarpBox &w, 
 }
 
 __global__ void __launch_bounds__(kAsThreads)
-assign_gtmax_kernel(const AsIn in, uint32_t *__restrict__ gmax /* (B,G) float bits, zeroed */)
+assign_gtmax_kernel(const AsIn in, uint32_t *__restrict__ gmax /* (B,G) float bits, zeroed */,
+                    float2 *__restrict__ best /* (B,N): every box's (max IoU, arg-max gt as int bits) for the label pass */)
 {
     extern __shared__ unsigned char smem_raw[];
     GtS *sg = reinterpret_cast<GtS *>(smem_raw);
@@ -107,25 +109,28 @@ assign_gtmax_kernel(const AsIn in, uint32_t *__restrict__ gmax /* (B,G) float bi
     const float off = __ldg(in.cfg + 3);
     for (int j = threadIdx.x; j < in.G; j += kAsThreads) smax[j] = 0u;
     const int ng = stage_gts(in, b, off, sg, &s_count);
-    if (ng == 0) return;
     const float *boxes = in.boxes + (int64_t)b * in.image_stride;
     for (int n0 = blockIdx.x * kAsThreads; n0 < in.N; n0 += gridDim.x * kAsThreads) {
         const int n = n0 + threadIdx.x;
         const bool have = n < in.N && !(in.box_valid && !in.box_valid[(int64_t)b * in.valid_stride + n]);
         const float4 a = have ? load_box(boxes + (int64_t)n * in.ld, in.ld) : make_float4(0, 0, 0, 0);
         const WarpBox wb = warp_bbox(have, a);
+        float m = 0.0f;
+        int am = 0;
         for (int base = 0; base < ng; base += 32) {
             uint32_t hits = warp_hits(sg, ng, base, wb, off);
-            while (hits) {
+            while (hits) {                                       // ascending gt order: the first of equal maxima wins
                 const int k = base + __ffs(hits) - 1;
                 hits &= hits - 1;
                 const float o = have ? iou_legacy(a, sg[k].box, sg[k].area, off) : 0.0f;
+                if (o > m) { m = o; am = sg[k].j; }
                 if (o > 0.0f) {
                     const uint32_t ob = __float_as_uint(o);      // o > 0: uint order == float order
                     if (ob > smax[k]) atomicMax(&smax[k], ob);
                 }
             }
         }
+        if (n < in.N) best[(int64_t)b * in.N + n] = make_float2(m, __int_as_float(am));
     }
     __syncthreads();
     for (int k = threadIdx.x; k < ng; k += kAsThreads)
@@ -133,8 +138,9 @@ assign_gtmax_kernel(const AsIn in, uint32_t *__restrict__ gmax /* (B,G) float bi
 }
 
 __global__ void __launch_bounds__(kAsThreads)
-assign_label_kernel(const AsIn in, const uint32_t *__restrict__ gmax, int32_t *__restrict__ assigned,
-                    int64_t assigned_stride, int assigned_offset, int32_t *__restrict__ cand_count /* (B,2) pos|neg */)
+assign_label_kernel(const AsIn in, const uint32_t *__restrict__ gmax, const float2 *__restrict__ best,
+                    int32_t *__restrict__ assigned, int64_t assigned_stride, int assigned_offset,
+                    int32_t *__restrict__ cand_count /* (B,2) pos|neg */)
 {
     extern __shared__ unsigned char smem_raw[];
     GtS *sg = reinterpret_cast<GtS *>(smem_raw);
@@ -145,27 +151,41 @@ assign_label_kernel(const AsIn in, const uint32_t *__restrict__ gmax, int32_t *_
     const float off = __ldg(in.cfg + 3);
     const int mode = (int)__ldg(in.cfg + 4);
     const int ng = stage_gts(in, b, off, sg, &s_count);
-    for (int k = threadIdx.x; k < ng; k += kAsThreads) smax[k] = __uint_as_float(gmax[(int64_t)b * in.G + sg[k].j]);
+    __shared__ uint32_t s_gmin;
+    if (threadIdx.x == 0) s_gmin = 0x7F800000u;          // +inf
     __syncthreads();
+    for (int k = threadIdx.x; k < ng; k += kAsThreads) {
+        const float gm = __uint_as_float(gmax[(int64_t)b * in.G + sg[k].j]);
+        smax[k] = gm;
+        // smallest per-gt maximum that can force a match: a box whose own best IoU is below it cannot be any gt's best
+        if (gm > 0.0f && (mode != 0 || gm >= min_pos)) atomicMin(&s_gmin, __float_as_uint(gm));   // gm > 0: uint order == float order
+    }
+    __syncthreads();
+    const float gmin = __uint_as_float(s_gmin);
     const float *boxes = in.boxes + (int64_t)b * in.image_stride;
     int32_t *out = assigned + (int64_t)b * assigned_stride + assigned_offset;
     int npos = 0, nneg = 0;                              // per-thread candidate counts (samplers need the totals)
     for (int n0 = blockIdx.x * kAsThreads; n0 < in.N; n0 += gridDim.x * kAsThreads) {
         const int n = n0 + threadIdx.x;
         const bool have = n < in.N && (!in.box_valid || in.box_valid[(int64_t)b * in.valid_stride + n]);
-        const float4 a = have ? load_box(boxes + (int64_t)n * in.ld, in.ld) : make_float4(0, 0, 0, 0);
-        const WarpBox wb = warp_bbox(have, a);
+        // (max IoU, arg-max) come from the first pass; the IoUs are only re-evaluated -- to find WHICH gt forces the
+        // match -- by the few warps that hold a box that can be some gt's best (12 bytes per box instead of a second
+        // walk over the gts: the RPN label pass went from 34 to ~8 us)
         float m = 0.0f;
         int am = 0, force = 0;
-        for (int base = 0; base < ng; base += 32) {
-            uint32_t hits = warp_hits(sg, ng, base, wb, off);
-            while (hits) {                               // ascending gt order, uniform across the warp
-                const int k = base + __ffs(hits) - 1;
-                hits &= hits - 1;
-                const float o = iou_legacy(a, sg[k].box, sg[k].area, off);
-                if (o > m) { m = o; am = sg[k].j; }
-                const float gm = smax[k];
-                if (o == gm && gm > 0.0f && (mode != 0 || gm >= min_pos)) force = sg[k].j + 1;
+        if (n < in.N) { const float2 bm = __ldg(best + (int64_t)b * in.N + n); m = bm.x; am = __float_as_int(bm.y); }
+        if (__any_sync(0xffffffffu, have && m >= gmin)) {
+            const float4 a = have ? load_box(boxes + (int64_t)n * in.ld, in.ld) : make_float4(0, 0, 0, 0);
+            const WarpBox wb = warp_bbox(have, a);
+            for (int base = 0; base < ng; base += 32) {
+                uint32_t hits = warp_hits(sg, ng, base, wb, off);
+                while (hits) {                               // ascending gt order, uniform across the warp
+                    const int k = base + __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const float o = iou_legacy(a, sg[k].box, sg[k].area, off);
+                    const float gm = smax[k];
+                    if (o == gm && gm > 0.0f && (mode != 0 || gm >= min_pos)) force = sg[k].j + 1;
+                }
             }
         }
         if (n >= in.N) continue;
@@ -407,8 +427,8 @@ __global__ void rcnn_finalize_kernel(const float *__restrict__ props5, int P_, c
 }
 
 // workspace: gmax (B,G) u32 | cand_count (B,2) i32 | list_count (B,2) i32 | lists (B,2,kListCap) u64
-struct AssignWs { uint32_t *gmax; int32_t *cand, *list_count; unsigned long long *items; size_t total; };
-static AssignWs carve_assign_ws(void *ws, int B, int G)
+struct AssignWs { uint32_t *gmax; int32_t *cand, *list_count; unsigned long long *items; float2 *best; size_t total; };
+static AssignWs carve_assign_ws(void *ws, int B, int G, int N)
 {
     AssignWs w;
     unsigned char *p = reinterpret_cast<unsigned char *>(ws);
@@ -416,10 +436,11 @@ static AssignWs carve_assign_ws(void *ws, int B, int G)
     w.gmax = reinterpret_cast<uint32_t *>(p + o); o += ((size_t)B * G * 4 + 255) & ~(size_t)255;
     w.cand = reinterpret_cast<int32_t *>(p + o); w.list_count = w.cand + B * 2; o += ((size_t)B * 4 * 4 + 255) & ~(size_t)255;
     w.items = reinterpret_cast<unsigned long long *>(p + o); o += (size_t)B * 2 * kListCap * 8;
+    w.best = reinterpret_cast<float2 *>(p + o); o += ((size_t)B * N * sizeof(float2) + 255) & ~(size_t)255;   // (max IoU, arg-max) per box
     w.total = o + 256;
     return w;
 }
-size_t assign_workspace_bytes(int B, int G) { return carve_assign_ws(nullptr, B, G).total; }
+size_t assign_workspace_bytes(int B, int G, int N) { return carve_assign_ws(nullptr, B, G, N).total; }
 
 static cudaError_t run_assign(const AsIn &in, int B, const AssignWs &w, int32_t *assigned, int64_t assigned_stride,
                               int assigned_offset, bool zero_counts, cudaStream_t s)
@@ -436,8 +457,8 @@ static cudaError_t run_assign(const AsIn &in, int B, const AssignWs &w, int32_t 
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     const size_t smem = (size_t)in.G * (sizeof(GtS) + 4) + 16;
-    assign_gtmax_kernel<<<dim3(gx, B), kAsThreads, smem, s>>>(in, w.gmax);
-    assign_label_kernel<<<dim3(gx, B), kAsThreads, smem, s>>>(in, w.gmax, assigned, assigned_stride, assigned_offset, w.cand);
+    assign_gtmax_kernel<<<dim3(gx, B), kAsThreads, smem, s>>>(in, w.gmax, w.best);
+    assign_label_kernel<<<dim3(gx, B), kAsThreads, smem, s>>>(in, w.gmax, w.best, assigned, assigned_stride, assigned_offset, w.cand);
     return cudaGetLastError();
 }
 
@@ -465,7 +486,7 @@ cudaError_t launch_assign_sample_rpn(const float *boxes, int boxes_per_image, co
 {
     if (B == 0) return cudaSuccess;
     if (N >= (1 << kSelMaxIndexBits) || Sp > kSelMaxK || Sn > kSelMaxK) return cudaErrorInvalidValue;
-    const AssignWs w = carve_assign_ws(ws, B, G);
+    const AssignWs w = carve_assign_ws(ws, B, G, N);
     AsIn in{ boxes, 4, boxes_per_image ? (int64_t)N * 4 : 0, box_valid, boxes_per_image ? (int64_t)N : 0, gts, gt_valid, G, N, cfg };
     cudaError_t e = run_assign(in, B, w, assigned, N, 0, true, s);
     if (e != cudaSuccess) return e;
@@ -487,7 +508,7 @@ cudaError_t launch_assign_sample_rcnn(const float *props5, const uint8_t *prop_m
     if (B == 0) return cudaSuccess;
     const int N = G + P, S = Sp + Sn;
     if (N >= (1 << kSelMaxIndexBits) || Sp > kSelMaxK || Sn > kSelMaxK) return cudaErrorInvalidValue;
-    const AssignWs w = carve_assign_ws(ws, B, G);
+    const AssignWs w = carve_assign_ws(ws, B, G, P);
     AsIn in{ props5, 5, (int64_t)P * 5, prop_mask, (int64_t)P, gts, gt_valid, G, P, cfg };
     cudaError_t e = cudaMemsetAsync(w.cand, 0, (size_t)B * 4 * 4, s);
     if (e != cudaSuccess) return e;

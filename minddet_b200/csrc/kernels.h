@@ -37,7 +37,7 @@ cudaError_t launch_proposal(const LevelSet &lv, int B, int nms_pre, int max_num,
                             float *props, uint8_t *pmask, int32_t *topk_idx, uint8_t *keep, cudaStream_t s);
 
 // a7/a8
-size_t assign_workspace_bytes(int B, int G);
+size_t assign_workspace_bytes(int B, int G, int N);   // N = boxes per image
 cudaError_t launch_assign_sample_rpn(const float *boxes, int boxes_per_image, const uint8_t *box_valid,
                                      int B, int N, const float *gts, const uint8_t *gt_valid, int G,
                                      const float *cfg, const int32_t *seed, void *ws, int Sp, int Sn,

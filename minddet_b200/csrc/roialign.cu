@@ -47,65 +47,71 @@ MD_DEVINL void build_taps(const RoiGeom &g, int P, int S, Tap *taps)
 constexpr int kRoiThreads = 256;
 
 __global__ void __launch_bounds__(kRoiThreads)
-roialign_fwd_gather_kernel(const RoiFeat f, const float *__restrict__ rois5, int P, int csplit,
+roialign_fwd_gather_kernel(const RoiFeat f, const float *__restrict__ rois5, int R, int P, int csplit,
                            float *__restrict__ out, const int32_t *__restrict__ only_flagged)
 {
     __shared__ Tap taps[kRoiMaxTaps];
-    const int r = blockIdx.x;
-    if (only_flagged && !only_flagged[r]) return;   // handled by the TMA kernel
-    const int S = (int)__ldg(f.cfg + 1);
-    const RoiGeom g = roi_geometry(f, rois5 + (int64_t)r * 5, P);
-    build_taps(g, P, S, taps);
-    __syncthreads();
-    const int PP = P * P, SS = S * S;
-    const float cnt = (float)SS;
-    const int cper = (f.C + csplit - 1) / csplit;
-    const int c0 = blockIdx.y * cper, c1 = min(f.C, c0 + cper);
-    const int64_t plane = (int64_t)g.H * g.W;
-    const float *fb = f.feat[g.l] + (int64_t)g.b * f.C * plane;
-    for (int o = c0 * PP + threadIdx.x; o < c1 * PP; o += kRoiThreads) {
-        const int c = o / PP, bin = o - c * PP;
-        const float *fp = fb + (int64_t)c * plane;
-        float sum = 0.0f;
-        for (int s = 0; s < SS; s++) {
-            const Tap t = taps[bin * SS + s];
-            float v = add(mul(t.w1, __ldg(fp + t.o1)), mul(t.w2, __ldg(fp + t.o2)));
-            v = add(v, mul(t.w3, __ldg(fp + t.o3)));
-            v = add(v, mul(t.w4, __ldg(fp + t.o4)));
-            sum = add(sum, v);
+    // grid.x <= R: a block walks RoIs blockIdx.x, blockIdx.x + gridDim.x, ... (as the fallback behind the TMA kernel the
+    // grid is a few blocks per SM and nearly every RoI is skipped after one flag load)
+    for (int r = blockIdx.x; r < R; r += gridDim.x) {
+        if (only_flagged && !only_flagged[r]) continue;   // handled by the TMA kernel (uniform over the block)
+        const int S = (int)__ldg(f.cfg + 1);
+        const RoiGeom g = roi_geometry(f, rois5 + (int64_t)r * 5, P);
+        build_taps(g, P, S, taps);
+        __syncthreads();
+        const int PP = P * P, SS = S * S;
+        const float cnt = (float)SS;
+        const int cper = (f.C + csplit - 1) / csplit;
+        const int c0 = blockIdx.y * cper, c1 = min(f.C, c0 + cper);
+        const int64_t plane = (int64_t)g.H * g.W;
+        const float *fb = f.feat[g.l] + (int64_t)g.b * f.C * plane;
+        for (int o = c0 * PP + threadIdx.x; o < c1 * PP; o += kRoiThreads) {
+            const int c = o / PP, bin = o - c * PP;
+            const float *fp = fb + (int64_t)c * plane;
+            float sum = 0.0f;
+            for (int s = 0; s < SS; s++) {
+                const Tap t = taps[bin * SS + s];
+                float v = add(mul(t.w1, __ldg(fp + t.o1)), mul(t.w2, __ldg(fp + t.o2)));
+                v = add(v, mul(t.w3, __ldg(fp + t.o3)));
+                v = add(v, mul(t.w4, __ldg(fp + t.o4)));
+                sum = add(sum, v);
+            }
+            out[(int64_t)r * f.C * PP + o] = div(sum, cnt);
         }
-        out[(int64_t)r * f.C * PP + o] = div(sum, cnt);
+        __syncthreads();                                   // taps are rebuilt for the next RoI
     }
 }
 
 __global__ void __launch_bounds__(kRoiThreads)
-roialign_bwd_gather_kernel(const RoiFeat f, const float *__restrict__ rois5, int P, int csplit,
+roialign_bwd_gather_kernel(const RoiFeat f, const float *__restrict__ rois5, int R, int P, int csplit,
                            const float *__restrict__ dout, const int32_t *__restrict__ only_flagged)
 {
     __shared__ Tap taps[kRoiMaxTaps];
-    const int r = blockIdx.x;
-    if (only_flagged && !only_flagged[r]) return;
-    const int S = (int)__ldg(f.cfg + 1);
-    const RoiGeom g = roi_geometry(f, rois5 + (int64_t)r * 5, P);
-    build_taps(g, P, S, taps);
-    __syncthreads();
-    const int PP = P * P, SS = S * S;
-    const float cnt = (float)SS;
-    const int cper = (f.C + csplit - 1) / csplit;
-    const int c0 = blockIdx.y * cper, c1 = min(f.C, c0 + cper);
-    const int64_t plane = (int64_t)g.H * g.W;
-    float *fb = f.feat[g.l] + (int64_t)g.b * f.C * plane;
-    for (int o = c0 * PP + threadIdx.x; o < c1 * PP; o += kRoiThreads) {
-        const int c = o / PP, bin = o - c * PP;
-        float *fp = fb + (int64_t)c * plane;
-        const float gr = div(__ldg(dout + (int64_t)r * f.C * PP + o), cnt);
-        for (int s = 0; s < SS; s++) {
-            const Tap t = taps[bin * SS + s];
-            if (t.w1 != 0.0f) atomicAdd(fp + t.o1, mul(gr, t.w1));
-            if (t.w2 != 0.0f) atomicAdd(fp + t.o2, mul(gr, t.w2));
-            if (t.w3 != 0.0f) atomicAdd(fp + t.o3, mul(gr, t.w3));
-            if (t.w4 != 0.0f) atomicAdd(fp + t.o4, mul(gr, t.w4));
+    for (int r = blockIdx.x; r < R; r += gridDim.x) {      // see roialign_fwd_gather_kernel
+        if (only_flagged && !only_flagged[r]) continue;
+        const int S = (int)__ldg(f.cfg + 1);
+        const RoiGeom g = roi_geometry(f, rois5 + (int64_t)r * 5, P);
+        build_taps(g, P, S, taps);
+        __syncthreads();
+        const int PP = P * P, SS = S * S;
+        const float cnt = (float)SS;
+        const int cper = (f.C + csplit - 1) / csplit;
+        const int c0 = blockIdx.y * cper, c1 = min(f.C, c0 + cper);
+        const int64_t plane = (int64_t)g.H * g.W;
+        float *fb = f.feat[g.l] + (int64_t)g.b * f.C * plane;
+        for (int o = c0 * PP + threadIdx.x; o < c1 * PP; o += kRoiThreads) {
+            const int c = o / PP, bin = o - c * PP;
+            float *fp = fb + (int64_t)c * plane;
+            const float gr = div(__ldg(dout + (int64_t)r * f.C * PP + o), cnt);
+            for (int s = 0; s < SS; s++) {
+                const Tap t = taps[bin * SS + s];
+                if (t.w1 != 0.0f) atomicAdd(fp + t.o1, mul(gr, t.w1));
+                if (t.w2 != 0.0f) atomicAdd(fp + t.o2, mul(gr, t.w2));
+                if (t.w3 != 0.0f) atomicAdd(fp + t.o3, mul(gr, t.w3));
+                if (t.w4 != 0.0f) atomicAdd(fp + t.o4, mul(gr, t.w4));
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -182,7 +188,7 @@ cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, in
         if (e != cudaSuccess) return e;
     }
     const int csplit = (fs.C >= 64 && !tma) ? 4 : 1;
-    roialign_fwd_gather_kernel<<<dim3(R, csplit), kRoiThreads, 0, s>>>(f, rois5, P, csplit, out, tma ? flags : nullptr);
+    roialign_fwd_gather_kernel<<<dim3(tma ? (R < 592 ? R : 592) : R, csplit), kRoiThreads, 0, s>>>(f, rois5, R, P, csplit, out, tma ? flags : nullptr);
     return cudaGetLastError();
 }
 
@@ -203,7 +209,7 @@ cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, in
         if (e != cudaSuccess) return e;
     }
     const int csplit = (fs.C >= 64 && !tma) ? 4 : 1;
-    roialign_bwd_gather_kernel<<<dim3(R, csplit), kRoiThreads, 0, s>>>(f, rois5, P, csplit, dout, tma ? flags : nullptr);
+    roialign_bwd_gather_kernel<<<dim3(tma ? (R < 592 ? R : 592) : R, csplit), kRoiThreads, 0, s>>>(f, rois5, R, P, csplit, dout, tma ? flags : nullptr);
     return cudaGetLastError();
 }
 
