@@ -76,7 +76,9 @@ MD_DEVINL float exact_exp(float x)
     return mul(p, __int_as_float((k + 127) << 23));
 }
 
-MD_DEVINL float exact_sigmoid(float x) { return div(1.0f, add(1.0f, exact_exp(-x))); }
+// 1 / y through __frcp_rn: the correctly rounded reciprocal IS the correctly rounded quotient 1.0f / y of the oracle,
+// at about half the instructions of the general __fdiv_rn sequence (the top-k evaluates 2.1 M sigmoids per step)
+MD_DEVINL float exact_sigmoid(float x) { return __frcp_rn(add(1.0f, exact_exp(-x))); }
 
 // monotone uint32 image of an fp32 value: larger float <=> larger key; -0.0 < +0.0
 MD_DEVINL uint32_t score_key(float f)
