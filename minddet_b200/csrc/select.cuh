@@ -28,7 +28,11 @@
 namespace md {
 namespace cg = cooperative_groups;
 
-constexpr int kClusterSize = 8;
+#ifndef MD_SEL_CLUSTER
+#define MD_SEL_CLUSTER 8
+#endif
+constexpr int kClusterSize = MD_SEL_CLUSTER;    // > 8 is a non-portable cluster size (opt-in below); measured with 16:
+                                                // 90 us vs 66 us for the 40 proposal segments (fewer clusters resident)
 constexpr int kSelThreads = 512;
 constexpr int kSelMaxK = 2048;            // sorted output limit per segment
 constexpr int kSelDirectMax = 1024;       // segments up to this length skip the radix passes: the leader sorts them all
@@ -618,6 +622,10 @@ cudaError_t launch_select_sorted(const Src &src, const Sink &sink, int nclusters
     if (dyn > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return e;
+        if (kClusterSize > 8) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) return e;
+        }
         configured = dyn;
     }
     kern<<<dim3(nseg * kClusterSize), dim3(kSelThreads), dyn, stream>>>(src, sink, cache);
