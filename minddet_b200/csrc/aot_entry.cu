@@ -20,7 +20,7 @@ namespace {
 
 enum { MD_OK = 0, MD_ERR_NPARAM = 1, MD_ERR_ARG = 2, MD_ERR_CUDA = 3, MD_ERR_SIZE = 4 };
 
-struct Workspace { void *ptr = nullptr; size_t bytes = 0; };
+struct Workspace { void *ptr = nullptr; size_t bytes = 0; md::SideLane lane{}; bool has_lane = false; };
 std::mutex g_ws_mutex;
 std::map<std::pair<int, void *>, Workspace> g_ws;
 
@@ -42,6 +42,32 @@ int get_workspace(void *stream, size_t bytes, void **out)
     }
     *out = w.ptr;
     return MD_OK;
+}
+
+// the (device, stream) workspace's helper stream; created on first use (not capturable: warm up first, like the scratch)
+const md::SideLane *get_side_lane(void *stream)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    Workspace &w = g_ws[std::make_pair(dev, stream)];
+    if (!w.has_lane) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing((cudaStream_t)stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+            cudaGetLastError();
+            return nullptr;                 // first use inside a capture: stay on one stream
+        }
+        md::SideLane l{};
+        if (cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        w.lane = l;
+        w.has_lane = true;
+    }
+    return &w.lane;
 }
 
 bool is_f32(const char *d) { return d && std::strcmp(d, "float32") == 0; }
@@ -178,7 +204,7 @@ int MdProposal(MD_AOT_ARGS)
     if (rc) return rc;
     return cuda_rc(md::launch_proposal(lv, B, nms_pre, max_num, (const float *)params[ic], ws, (float *)params[o0],
                                        (uint8_t *)params[o0 + 1], (int32_t *)params[o0 + 2], (uint8_t *)params[o0 + 3],
-                                       (cudaStream_t)stream));
+                                       (cudaStream_t)stream, get_side_lane(stream)));
 }
 
 int MdAssignSample(MD_AOT_ARGS)

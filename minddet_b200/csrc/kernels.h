@@ -33,8 +33,11 @@ cudaError_t launch_nms(const float *boxes, int ld, int B, int K, const float *cf
 
 // a3..a6
 size_t proposal_workspace_bytes(int B, int L, int nms_pre);
+// A helper stream with its fork / join events (owned by the per-stream workspace): lets one entry point run two of its
+// kernels side by side.  Fork-join through events, so it is also legal while the caller's stream is being captured.
+struct SideLane { cudaStream_t stream; cudaEvent_t fork, join; };
 cudaError_t launch_proposal(const LevelSet &lv, int B, int nms_pre, int max_num, const float *cfg, void *ws,
-                            float *props, uint8_t *pmask, int32_t *topk_idx, uint8_t *keep, cudaStream_t s);
+                            float *props, uint8_t *pmask, int32_t *topk_idx, uint8_t *keep, cudaStream_t s, const SideLane *side = nullptr);
 
 // a7/a8
 size_t assign_workspace_bytes(int B, int G, int N);   // N = boxes per image

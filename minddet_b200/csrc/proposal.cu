@@ -203,6 +203,7 @@ struct PropLevels {
 };
 struct PropSrc {
     PropLevels p;
+    int l0, nl;                 // this launch serves levels [l0, l0 + nl)
     struct Ctx { const float *base; int A, HW, N; bool sigmoid; };
     // One cluster per (image, level), level-major: the clusters of the finest (longest) level start first.  About 15
     // clusters of eight 139 KB CTAs are resident at a time; the hardware hands the freed slots to the next clusters.
@@ -212,7 +213,7 @@ struct PropSrc {
     {
         if (it) return -1;
         const int l = i / p.B, b = i - l * p.B;
-        return b * p.L + l;
+        return b * p.L + l0 + l;
     }
     __device__ Ctx prepare(int seg) const
     {
@@ -837,7 +838,7 @@ size_t proposal_workspace_bytes(int B, int L, int nms_pre)
 }
 
 cudaError_t launch_proposal(const LevelSet &lv, int B, int nms_pre, int max_num, const float *cfg, void *ws,
-                            float *props, uint8_t *pmask, int32_t *topk_idx, uint8_t *keep, cudaStream_t s)
+                            float *props, uint8_t *pmask, int32_t *topk_idx, uint8_t *keep, cudaStream_t s, const SideLane *side)
 {
     if (lv.L < 1 || lv.L > kMaxLv || nms_pre > kSelMaxK) return cudaErrorInvalidValue;
     const int L = lv.L, nseg = B * L;
@@ -857,7 +858,22 @@ cudaError_t launch_proposal(const LevelSet &lv, int B, int nms_pre, int max_num,
         if (N > maxN) maxN = N;
         if (pl.K[l] > Kmax) Kmax = pl.K[l];
     }
-    cudaError_t e = launch_select_sorted(PropSrc{ pl }, PropSink{ pl, w.boxes, w.scores, topk_idx }, nseg, maxN, s);
+    cudaError_t e;
+    if (side && L >= 2) {
+        // Two launches side by side: the finest level's clusters need 139 KB of shared memory per CTA (one CTA per SM,
+        // ~15 clusters resident); sized by the second level the others need 60 KB, so all of them are resident at once
+        // instead of queueing behind the big ones for three rounds.
+        int maxN1 = 0;
+        for (int l = 1; l < L; l++) maxN1 = max(maxN1, lv.A[l] * lv.H[l] * lv.W[l]);
+        e = cudaEventRecord(side->fork, s);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(side->stream, side->fork, 0);
+        if (e == cudaSuccess) e = launch_select_sorted(PropSrc{ pl, 1, L - 1 }, PropSink{ pl, w.boxes, w.scores, topk_idx }, B * (L - 1), maxN1, side->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(side->join, side->stream);
+        if (e == cudaSuccess) e = launch_select_sorted(PropSrc{ pl, 0, 1 }, PropSink{ pl, w.boxes, w.scores, topk_idx }, B, lv.A[0] * lv.H[0] * lv.W[0], s);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, side->join, 0);
+    } else {
+        e = launch_select_sorted(PropSrc{ pl, 0, L }, PropSink{ pl, w.boxes, w.scores, topk_idx }, nseg, maxN, s);
+    }
     if (e != cudaSuccess) return e;
     sg.boxes = reinterpret_cast<const float *>(w.boxes); sg.ld = 4; sg.seg_stride = nms_pre; sg.L = L;
     sg.scores = w.scores; sg.kept_keys = w.kept_keys;
