@@ -13,6 +13,7 @@ struct NmsSegs {                 // segment s -> boxes + K
     int rows_pad;                // mask rows per segment (multiple of 64)
     const int32_t *labels;       // optional (nseg, seg_stride): only boxes of equal label suppress each other ...
     const float *agnostic;       // ... unless *agnostic != 0 (device flag); both null for class-agnostic NMS
+    int l0, nl;                  // optional level subset: launch index z serves segment (z / nl) * L + l0 + z % nl (nl == 0: z)
     const float *scores;         // optional (nseg, seg_stride) with kept_keys: the sweep also writes the monotone keys of
     uint32_t *kept_keys;         // the kept boxes' scores, in kept order, (nseg, keep_stride) -- the cross-level merge's input
 };

@@ -326,6 +326,8 @@ MD_DEVINL bool nms_suppresses(const BoxA &a, const BoxA &b, const NmsCfg &c, boo
     return c.inclusive ? (iou >= c.thr) : (iou > c.thr);
 }
 
+MD_DEVINL int nms_segment(const NmsSegs &sg, int z) { return sg.nl ? (z / sg.nl) * sg.L + sg.l0 + z % sg.nl : z; }
+
 // grid: (tile, 1, segment) over the upper triangle of 64 x 64 tiles; 64 threads: thread r owns row box r of the tile.
 // (kMaskGroup > 1: grid (row block, group of column blocks, segment) and a block walks its group with double-buffered
 // column boxes -- kept for reference, measured slower.)
@@ -335,7 +337,7 @@ template <bool LABELS>
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(const NmsSegs sg, const float *__restrict__ cfg, unsigned long long *__restrict__ mask)
 {
-    const int seg = blockIdx.z;
+    const int seg = nms_segment(sg, blockIdx.z);
     const int K = sg.K[seg % sg.L];
     const int nb = (K + 63) >> 6;
     int i, j_begin, j_end;
@@ -522,7 +524,7 @@ nms_sweep_kernel(const NmsSegs sg, const unsigned long long *__restrict__ mask,
     __shared__ unsigned long long kept_all[kSweepMaxNb];
     __shared__ int kept_before[kSweepMaxNb + 1];
     __shared__ float score_sh[64 * kSweepMaxNb];
-    const int seg = blockIdx.x;
+    const int seg = nms_segment(sg, blockIdx.x);
     const int K = sg.K[seg % sg.L];
     const int nb = (K + 63) >> 6, nbp = sg.nbp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -858,11 +860,18 @@ cudaError_t launch_proposal(const LevelSet &lv, int B, int nms_pre, int max_num,
         if (N > maxN) maxN = N;
         if (pl.K[l] > Kmax) Kmax = pl.K[l];
     }
+    sg.boxes = reinterpret_cast<const float *>(w.boxes); sg.ld = 4; sg.seg_stride = nms_pre; sg.L = L;
+    sg.scores = w.scores; sg.kept_keys = w.kept_keys;
+    const int nb = (nms_pre + 63) / 64;
+    sg.nbp = (nb + 1) & ~1; sg.rows_pad = nb * 64;
     cudaError_t e;
     if (side && L >= 2) {
-        // Two launches side by side: the finest level's clusters need 139 KB of shared memory per CTA (one CTA per SM,
-        // ~15 clusters resident); sized by the second level the others need 60 KB, so all of them are resident at once
-        // instead of queueing behind the big ones for three rounds.
+        // Two top-k launches side by side: the finest level's clusters need 139 KB of shared memory per CTA (one CTA per
+        // SM, ~15 clusters resident); sized by the second level the others need 60 KB, so all of them are resident at once
+        // instead of queueing behind the big ones for three rounds.  (Also measured: the NMS mask + sweep per lane as well,
+        // joined in front of the merge -- the stage alone drops from 311 to 282 us, but inside the step, where the RPN
+        // targets and the gradient zero-fill already run beside this chain, the step gets 8 us longer.  The kernels keep
+        // the level-subset addressing, NmsSegs::l0 / nl.)
         int maxN1 = 0;
         for (int l = 1; l < L; l++) maxN1 = max(maxN1, lv.A[l] * lv.H[l] * lv.W[l]);
         e = cudaEventRecord(side->fork, s);
@@ -871,15 +880,11 @@ cudaError_t launch_proposal(const LevelSet &lv, int B, int nms_pre, int max_num,
         if (e == cudaSuccess) e = cudaEventRecord(side->join, side->stream);
         if (e == cudaSuccess) e = launch_select_sorted(PropSrc{ pl, 0, 1 }, PropSink{ pl, w.boxes, w.scores, topk_idx }, B, lv.A[0] * lv.H[0] * lv.W[0], s);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(s, side->join, 0);
+        if (e == cudaSuccess) e = run_nms(sg, nseg, Kmax, cfg + 11, w.mask, w.keep_pos, nms_pre, keep, nms_pre, w.count, s);
     } else {
         e = launch_select_sorted(PropSrc{ pl, 0, L }, PropSink{ pl, w.boxes, w.scores, topk_idx }, nseg, maxN, s);
+        if (e == cudaSuccess) e = run_nms(sg, nseg, Kmax, cfg + 11, w.mask, w.keep_pos, nms_pre, keep, nms_pre, w.count, s);
     }
-    if (e != cudaSuccess) return e;
-    sg.boxes = reinterpret_cast<const float *>(w.boxes); sg.ld = 4; sg.seg_stride = nms_pre; sg.L = L;
-    sg.scores = w.scores; sg.kept_keys = w.kept_keys;
-    const int nb = (nms_pre + 63) / 64;
-    sg.nbp = (nb + 1) & ~1; sg.rows_pad = nb * 64;
-    e = run_nms(sg, nseg, Kmax, cfg + 11, w.mask, w.keep_pos, nms_pre, keep, nms_pre, w.count, s);
     if (e != cudaSuccess) return e;
     const size_t smem = (size_t)L * nms_pre * sizeof(uint32_t);
     static bool configured = false;
