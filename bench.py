@@ -205,7 +205,7 @@ def run_b200(args):
     h2d_bytes = pipeline.input_bytes(host)
     side = torch.cuda.Stream(priority=-1)     # the chain; the zero-fill stream below keeps the default (lower) priority,
     aux = torch.cuda.Stream(priority=-1)      # so its blocks fill SMs the chain leaves idle instead of queueing ahead of it
-    zstream, zjoin = torch.cuda.Stream(), torch.cuda.Event()
+    zstream, zjoin, zfork = torch.cuda.Stream(), torch.cuda.Event(), torch.cuda.Event()
     fork, join = torch.cuda.Event(), torch.cuda.Event()
     group_streams = [torch.cuda.Stream() for _ in range(max(0, args.split - 1))]
     group_join = [torch.cuda.Event() for _ in range(max(0, args.split - 1))]
@@ -231,27 +231,31 @@ def run_b200(args):
                 rpn = None
                 join.record(aux)
             else:
-              with torch.cuda.stream(aux):     # (measured: started beside the RoIAlign forward instead, the step is 25 us longer)
+              with torch.cuda.stream(aux):     # (measured: started after Proposal or beside the RoIAlign forward instead, the step is 10 / 25 us longer)
                 rpn = rp.rpn_targets(inp["gts"], inp["gt_valid"], anchors, avalid)
                 join.record(aux)
         nh = args.split if timers is None else 1
         zeroed = None
-        if overlap and nh == 1:
-            # The RoIAlign gradient's zero-fill (731 MB of DRAM writes, ~115 us) has no producer: it runs on its own
-            # stream beside the latency-bound Proposal chain and the backward accumulates (MdRoiAlignBwdAcc).
-            zstream.wait_event(fork)
-            with torch.cuda.stream(zstream):
-                # (a fill confined to a few SMs -- persistent store loop on 16..64 CTAs, or cp.async.bulk from a zeroed
-                # shared-memory block -- was measured too: an SM sustains ~60 GB/s of stores, so it only gets slower)
-                zeroed = [torch.empty_like(f) if os.environ.get("MD_BENCH_DIAG_SKIP_SIDE") in ("both", "zero") else torch.zeros_like(f)
-                          for f in inp["feats"]]
-                zjoin.record(zstream)
 
         def chain(a, b):
             """Proposal -> RCNN targets -> RoIAlign fwd -> bwd for images [a, b) on the current stream"""
             sl = lambda xs: [x[a:b] for x in xs]
             feats_h = sl(inp["feats"])
             props, pmask = rp.proposal(sl(inp["cls_scores"]), sl(inp["bbox_preds"]))
+            nonlocal zeroed
+            if overlap and nh == 1:
+                # The RoIAlign gradient's zero-fill (731 MB of DRAM writes, ~105 us) has no producer: it runs on its own
+                # (lower-priority) stream and the backward accumulates (MdRoiAlignBwdAcc).  Started here, beside the RCNN
+                # targets and the head of the RoIAlign forward, not at the top of the step: the Proposal kernels share
+                # the SMs badly with a kernel that wants every SM's store bandwidth (measured: 1.008 -> 0.999 ms, and
+                # 0.985 ms with Proposal's own two lanes, which only pay off without the fill beside them; started after
+                # the RCNN targets instead: 0.997 ms).
+                zfork.record(torch.cuda.current_stream())
+                zstream.wait_event(zfork)
+                with torch.cuda.stream(zstream):
+                    zeroed = [torch.empty_like(f) if os.environ.get("MD_BENCH_DIAG_SKIP_SIDE") in ("both", "zero") else torch.zeros_like(f)
+                              for f in inp["feats"]]
+                    zjoin.record(zstream)
             if nh == 1:
                 mark("proposal")
                 nonlocal_rpn()

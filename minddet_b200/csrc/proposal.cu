@@ -10,6 +10,8 @@
 //     (image, level), chunk-by-chunk with a warp-wide OR fixed point, zero host round trips.
 //   * graph order top-k -> gather -> NMS -> gather-keep: center_head.py:435-459.
 // Semantics: oracle/CONVENTIONS.md #1-8, #17; oracle/region_oracle.c (o_topk, o_nms, o_proposal_image).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "nms.cuh"
 #include "select.cuh"
@@ -866,21 +868,33 @@ cudaError_t launch_proposal(const LevelSet &lv, int B, int nms_pre, int max_num,
     sg.nbp = (nb + 1) & ~1; sg.rows_pad = nb * 64;
     cudaError_t e;
     if (side && L >= 2) {
-        // Two top-k launches side by side: the finest level's clusters need 139 KB of shared memory per CTA (one CTA per
-        // SM, ~15 clusters resident); sized by the second level the others need 60 KB, so all of them are resident at once
-        // instead of queueing behind the big ones for three rounds.  (Also measured: the NMS mask + sweep per lane as well,
-        // joined in front of the merge -- the stage alone drops from 311 to 282 us, but inside the step, where the RPN
-        // targets and the gradient zero-fill already run beside this chain, the step gets 8 us longer.  The kernels keep
-        // the level-subset addressing, NmsSegs::l0 / nl.)
+        // Two lanes side by side, joined in front of the merge: the finest level on the caller's stream, the other
+        // levels on the workspace's helper stream, each lane top-k -> NMS mask -> NMS sweep.
+        //  * top-k: the finest level's clusters need 139 KB of shared memory per CTA (one CTA per SM, ~15 clusters
+        //    resident); sized by the second level the others need 60 KB, so all of them are resident at once instead of
+        //    queueing behind the big ones for three rounds;
+        //  * the other levels finish their top-k first, and their (issue-bound) mask kernel then fills the SMs the
+        //    (latency-bound) level-0 top-k leaves mostly idle.
+        // Measured inside the step (bench.py): 1.008 -> 0.991 ms provided nothing DRAM-heavy runs beside this chain (with
+        // the gradient zero-fill started at the top of the step the lanes made it 12 us longer).
         int maxN1 = 0;
         for (int l = 1; l < L; l++) maxN1 = max(maxN1, lv.A[l] * lv.H[l] * lv.W[l]);
         e = cudaEventRecord(side->fork, s);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(side->stream, side->fork, 0);
+        // the NMS mask + sweep per lane too (MD_PROP_NMS_LANES=0: one NMS launch for all levels after the join)
+        static const bool nms_lanes = !(getenv("MD_PROP_NMS_LANES") && getenv("MD_PROP_NMS_LANES")[0] == '0');
+        int Kmax1 = 0;
+        for (int l = 1; l < L; l++) Kmax1 = max(Kmax1, pl.K[l]);
+        NmsSegs sg1 = sg, sg0 = sg;
+        sg1.l0 = 1; sg1.nl = L - 1;
+        sg0.l0 = 0; sg0.nl = 1;
         if (e == cudaSuccess) e = launch_select_sorted(PropSrc{ pl, 1, L - 1 }, PropSink{ pl, w.boxes, w.scores, topk_idx }, B * (L - 1), maxN1, side->stream);
+        if (e == cudaSuccess && nms_lanes) e = run_nms(sg1, B * (L - 1), Kmax1, cfg + 11, w.mask, w.keep_pos, nms_pre, keep, nms_pre, w.count, side->stream);
         if (e == cudaSuccess) e = cudaEventRecord(side->join, side->stream);
         if (e == cudaSuccess) e = launch_select_sorted(PropSrc{ pl, 0, 1 }, PropSink{ pl, w.boxes, w.scores, topk_idx }, B, lv.A[0] * lv.H[0] * lv.W[0], s);
+        if (e == cudaSuccess && nms_lanes) e = run_nms(sg0, B, pl.K[0], cfg + 11, w.mask, w.keep_pos, nms_pre, keep, nms_pre, w.count, s);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(s, side->join, 0);
-        if (e == cudaSuccess) e = run_nms(sg, nseg, Kmax, cfg + 11, w.mask, w.keep_pos, nms_pre, keep, nms_pre, w.count, s);
+        if (e == cudaSuccess && !nms_lanes) e = run_nms(sg, nseg, Kmax, cfg + 11, w.mask, w.keep_pos, nms_pre, keep, nms_pre, w.count, s);
     } else {
         e = launch_select_sorted(PropSrc{ pl, 0, L }, PropSink{ pl, w.boxes, w.scores, topk_idx }, nseg, maxN, s);
         if (e == cudaSuccess) e = run_nms(sg, nseg, Kmax, cfg + 11, w.mask, w.keep_pos, nms_pre, keep, nms_pre, w.count, s);
