@@ -702,10 +702,54 @@ cudaError_t launch_nms(const float *boxes, int ld, int B, int K, const float *cf
 constexpr int kMergeThreads = 512;
 constexpr int kMergeSplit = 16;
 
+// suppressed boxes: rank = total_kept + (#suppressed valid boxes before me in concat order)
+// (second half of merge_levels_kernel: same grid, disjoint output ranks)
+__device__ void merge_suppressed(int L, int nms_pre, int max_num,
+                                 const float4 *__restrict__ ws_boxes, const float *__restrict__ ws_scores,
+                                 const uint8_t *__restrict__ keep_mask, const int32_t *__restrict__ keep_pos,
+                                 const int32_t *__restrict__ count, const NmsSegs &sg,
+                                 float *__restrict__ props, uint8_t *__restrict__ pmask)
+{
+    __shared__ int cnt[kMaxLv], cumk[kMaxLv + 1], cumv[kMaxLv + 1];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        int c = 0, v = 0;
+        for (int l = 0; l < L; l++) { cnt[l] = count[b * L + l]; cumk[l] = c; c += cnt[l]; cumv[l] = v; v += sg.K[l]; }
+        cumk[L] = c; cumv[L] = v;
+    }
+    __syncthreads();
+    const int total_kept = cumk[L], total_valid = cumv[L];
+    for (int e = blockIdx.y * kMergeThreads + tid; e < L * nms_pre && total_kept < max_num; e += kMergeSplit * kMergeThreads) {
+        const int l = e / nms_pre, i = e - l * nms_pre;
+        if (i >= sg.K[l]) continue;
+        const int64_t seg = (int64_t)b * L + l;
+        if (keep_mask[seg * nms_pre + i]) continue;
+        int lo = 0, hi = cnt[l];
+        const int32_t *kp = keep_pos + seg * nms_pre;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (kp[mid] < i) lo = mid + 1; else hi = mid; }
+        const int concat = cumv[l] + i;
+        const int kept_before = cumk[l] + lo;
+        const int rank = total_kept + (concat - kept_before);
+        if (rank < max_num) {
+            const float4 bx = ws_boxes[seg * nms_pre + i];
+            float *o = props + ((int64_t)b * max_num + rank) * 5;
+            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = ws_scores[seg * nms_pre + i];
+            pmask[(int64_t)b * max_num + rank] = 0;
+        }
+    }
+    // zero padding when fewer than max_num boxes exist at all
+    for (int r = total_valid + blockIdx.y * kMergeThreads + tid; r < max_num; r += kMergeSplit * kMergeThreads) {
+        float *o = props + ((int64_t)b * max_num + r) * 5;
+        o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f;
+        pmask[(int64_t)b * max_num + r] = 0;
+    }
+}
+
 __global__ void __launch_bounds__(kMergeThreads)
 merge_levels_kernel(int L, int nms_pre, int max_num, const float4 *__restrict__ ws_boxes,
                     const uint32_t *__restrict__ kept_keys,
                     const int32_t *__restrict__ keep_pos, const int32_t *__restrict__ count,
+                    const float *__restrict__ ws_scores, const uint8_t *__restrict__ keep_mask, const NmsSegs sg,
                     float *__restrict__ props, uint8_t *__restrict__ pmask)
 {
     extern __shared__ uint32_t kkeys[];   // [L][nms_pre] keys of the kept boxes, descending per level
@@ -768,51 +812,7 @@ merge_levels_kernel(int L, int nms_pre, int max_num, const float4 *__restrict__ 
             pmask[(int64_t)b * max_num + rank] = 1;
         }
     }
-}
-
-// suppressed boxes: rank = total_kept + (#suppressed valid boxes before me in concat order)
-__global__ void __launch_bounds__(kMergeThreads)
-merge_suppressed_kernel(int L, int nms_pre, int max_num, const int *__restrict__ Kl_dev_unused,
-                        const float4 *__restrict__ ws_boxes, const float *__restrict__ ws_scores,
-                        const uint8_t *__restrict__ keep_mask, const int32_t *__restrict__ keep_pos,
-                        const int32_t *__restrict__ count, const NmsSegs sg,
-                        float *__restrict__ props, uint8_t *__restrict__ pmask)
-{
-    (void)Kl_dev_unused;
-    __shared__ int cnt[kMaxLv], cumk[kMaxLv + 1], cumv[kMaxLv + 1];
-    const int b = blockIdx.x, tid = threadIdx.x;
-    if (tid == 0) {
-        int c = 0, v = 0;
-        for (int l = 0; l < L; l++) { cnt[l] = count[b * L + l]; cumk[l] = c; c += cnt[l]; cumv[l] = v; v += sg.K[l]; }
-        cumk[L] = c; cumv[L] = v;
-    }
-    __syncthreads();
-    const int total_kept = cumk[L], total_valid = cumv[L];
-    if (total_kept >= max_num) return;   // no room for suppressed boxes
-    for (int e = blockIdx.y * kMergeThreads + tid; e < L * nms_pre; e += kMergeSplit * kMergeThreads) {
-        const int l = e / nms_pre, i = e - l * nms_pre;
-        if (i >= sg.K[l]) continue;
-        const int64_t seg = (int64_t)b * L + l;
-        if (keep_mask[seg * nms_pre + i]) continue;
-        int lo = 0, hi = cnt[l];
-        const int32_t *kp = keep_pos + seg * nms_pre;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (kp[mid] < i) lo = mid + 1; else hi = mid; }
-        const int concat = cumv[l] + i;
-        const int kept_before = cumk[l] + lo;
-        const int rank = total_kept + (concat - kept_before);
-        if (rank < max_num) {
-            const float4 bx = ws_boxes[seg * nms_pre + i];
-            float *o = props + ((int64_t)b * max_num + rank) * 5;
-            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = ws_scores[seg * nms_pre + i];
-            pmask[(int64_t)b * max_num + rank] = 0;
-        }
-    }
-    // zero padding when fewer than max_num boxes exist at all
-    for (int r = total_valid + blockIdx.y * kMergeThreads + tid; r < max_num; r += kMergeSplit * kMergeThreads) {
-        float *o = props + ((int64_t)b * max_num + r) * 5;
-        o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f;
-        pmask[(int64_t)b * max_num + r] = 0;
-    }
+    merge_suppressed(L, nms_pre, max_num, ws_boxes, ws_scores, keep_mask, keep_pos, count, sg, props, pmask);
 }
 
 // workspace layout (all per segment = b*L + l, nms_pre rows each)
@@ -908,9 +908,7 @@ cudaError_t launch_proposal(const LevelSet &lv, int B, int nms_pre, int max_num,
         configured = true;
     }
     merge_levels_kernel<<<dim3(B, kMergeSplit), kMergeThreads, smem, s>>>(
-        L, nms_pre, max_num, w.boxes, w.kept_keys, w.keep_pos, w.count, props, pmask);
-    merge_suppressed_kernel<<<dim3(B, kMergeSplit), kMergeThreads, 0, s>>>(
-        L, nms_pre, max_num, nullptr, w.boxes, w.scores, keep, w.keep_pos, w.count, sg, props, pmask);
+        L, nms_pre, max_num, w.boxes, w.kept_keys, w.keep_pos, w.count, w.scores, keep, sg, props, pmask);
     return cudaGetLastError();
 }
 

@@ -8,7 +8,7 @@ import torch
 from . import synth
 from .ops import (AnchorGenerator, BboxAssignSample, BboxAssignSampleForRcnn, Proposal, SingleRoIExtractor)
 
-KERNELS_PER_STEP = 22   # select, nms_mask, nms_sweep, merge x2 | gtmax, label, prefilter, select(list), select(full scan,
+KERNELS_PER_STEP = 24   # 2 lanes x (select, nms_mask, nms_sweep), merge | gtmax, label, prefilter, select(list), select(full scan,
                         # returns at once), finalize | gt_head, gtmax, label, prefilter, select x2, finalize |
                         # roialign fwd (stream + gather for declined RoIs) | roialign bwd (stream + gather);
                         # the cudaMemsetAsync nodes of a step (dX zero-fill, small counters) are not counted
