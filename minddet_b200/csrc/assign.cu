@@ -232,10 +232,15 @@ __global__ void rcnn_gt_head_kernel(const uint8_t *__restrict__ gt_valid, int B,
 constexpr int kListCap = 8192;
 struct SampleLists { unsigned long long *items; int32_t *count; const int32_t *cand_count; };   // per (image, kind)
 
-MD_DEVINL uint32_t sample_threshold(int ncand)
+// Keys above the threshold are dropped.  Aim for ~2 * want survivors (want is > 8 sigma below that mean, and a list that
+// still ends up short is detected and redone by the full scan): the list then fits the select's direct path (<= 1024
+// entries: one sort, no radix passes) instead of carrying up to kListCap entries through four passes.
+MD_DEVINL uint32_t sample_threshold(int ncand, int want)
 {
-    if (ncand <= kListCap) return 0xFFFFFFFFu;
-    return (uint32_t)((((unsigned long long)(kListCap / 2)) << 32) / (unsigned long long)ncand);
+    int target = 2 * want;
+    target = target < 256 ? 256 : (target > kListCap / 2 ? kListCap / 2 : target);
+    if (ncand <= target) return 0xFFFFFFFFu;
+    return (uint32_t)((((unsigned long long)target) << 32) / (unsigned long long)ncand);
 }
 MD_DEVINL bool list_is_exact(const SampleLists &L, int seg, int want)
 {
@@ -244,8 +249,8 @@ MD_DEVINL bool list_is_exact(const SampleLists &L, int seg, int want)
 }
 
 __global__ void __launch_bounds__(256)
-sample_prefilter_kernel(const int32_t *__restrict__ assigned, int N, uint32_t stream_base, const int32_t *__restrict__ seed,
-                        const float *__restrict__ cfg, const SampleLists L)
+sample_prefilter_kernel(const int32_t *__restrict__ assigned, int N, int Sp, int Sn, uint32_t stream_base,
+                        const int32_t *__restrict__ seed, const float *__restrict__ cfg, const SampleLists L)
 {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     if (__ldg(cfg + 14) != 0.0f) {                       // MD_AS_FORCE_FULL: mark both lists overflowed -> full-scan select
@@ -253,7 +258,7 @@ sample_prefilter_kernel(const int32_t *__restrict__ assigned, int N, uint32_t st
         return;
     }
     const uint32_t s0 = (uint32_t)__ldg(seed), s1 = (uint32_t)__ldg(seed + 1);
-    const uint32_t thr_pos = sample_threshold(L.cand_count[b * 2]), thr_neg = sample_threshold(L.cand_count[b * 2 + 1]);
+    const uint32_t thr_pos = sample_threshold(L.cand_count[b * 2], Sp), thr_neg = sample_threshold(L.cand_count[b * 2 + 1], Sn);
     const int32_t *a = assigned + (int64_t)b * N;
     for (int n0 = blockIdx.x * 256; n0 < N; n0 += gridDim.x * 256) {
         const int n = n0 + threadIdx.x;
@@ -471,7 +476,7 @@ static cudaError_t run_samplers(const int32_t *assigned, int B, int N, int Sp, i
     int gx = (N + 255) / 256;
     const int cap = (148 * 8 + B - 1) / B;
     if (gx > cap) gx = cap;
-    sample_prefilter_kernel<<<dim3(gx, B), 256, 0, s>>>(assigned, N, stream_base, seed, cfg, L);
+    sample_prefilter_kernel<<<dim3(gx, B), 256, 0, s>>>(assigned, N, Sp, Sn, stream_base, seed, cfg, L);
     cudaError_t e = launch_select_sorted(ListSrc{ L, Sp, Sn, B }, sink, 2 * B, kListCap, s);
     if (e != cudaSuccess) return e;
     return launch_select_sorted(SampleSrc{ assigned, N, Sp, Sn, stream_base, seed, B, L }, sink, 2 * B, N, s);
