@@ -528,7 +528,7 @@ def run_b200(args):
             "clocks": sampler.summary(),
             "e2e": {"value": world * BATCH / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms},
-            "gpu_launches": (18 * args.split + 6) * K,   # per image group: proposal 7 (2 lanes x (select, nms mask, nms sweep) + merge) + rcnn targets 7 + RoIAlign fwd 2 + bwd 2; rpn targets 6
+            "gpu_launches": (17 * args.split + 6) * K,   # per image group: proposal 7 (2 lanes x (select, nms mask, nms sweep) + merge) + rcnn targets 6 + RoIAlign fwd 2 + bwd 2; rpn targets 6
             "nccl_collectives_per_step": 1 if world > 1 else 0,
             "roofline": roofline, "stage_ms": stage_ms, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

@@ -99,7 +99,9 @@ MD_DEVINL uint32_t warp_hits(const GtS *sg, int ng, int base, const WarpBox &w, 
 
 __global__ void __launch_bounds__(kAsThreads)
 assign_gtmax_kernel(const AsIn in, uint32_t *__restrict__ gmax /* (B,G) float bits, zeroed */,
-                    float2 *__restrict__ best /* (B,N): every box's (max IoU, arg-max gt as int bits) for the label pass */)
+                    float2 *__restrict__ best /* (B,N): every box's (max IoU, arg-max gt as int bits) for the label pass */,
+                    int32_t *__restrict__ head_assigned /* nullable: RCNN flavour, the gts-as-proposals head of `assigned` */,
+                    int64_t head_stride, int32_t *__restrict__ head_cand)
 {
     extern __shared__ unsigned char smem_raw[];
     GtS *sg = reinterpret_cast<GtS *>(smem_raw);
@@ -108,6 +110,19 @@ assign_gtmax_kernel(const AsIn in, uint32_t *__restrict__ gmax /* (B,G) float bi
     const int b = blockIdx.y;
     const float off = __ldg(in.cfg + 3);
     for (int j = threadIdx.x; j < in.G; j += kAsThreads) smax[j] = 0u;
+    if (head_assigned && blockIdx.x == 0) {
+        // gts-as-proposals head of the RCNN candidate list: a valid gt is assigned to itself and is a positive candidate
+        // of its own image (it used to be a kernel of its own)
+        int nv = 0;
+        for (int j = threadIdx.x; j < in.G; j += kAsThreads) {
+            const bool v = !in.gt_valid || in.gt_valid[(int64_t)b * in.G + j];
+            head_assigned[(int64_t)b * head_stride + j] = v ? j + 1 : -1;
+            nv += v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, o);
+        if ((threadIdx.x & 31) == 0 && nv) atomicAdd(head_cand + b * 2, nv);
+    }
     const int ng = stage_gts(in, b, off, sg, &s_count);
     const float *boxes = in.boxes + (int64_t)b * in.image_stride;
     for (int n0 = blockIdx.x * kAsThreads; n0 < in.N; n0 += gridDim.x * kAsThreads) {
@@ -209,18 +224,6 @@ assign_label_kernel(const AsIn in, const uint32_t *__restrict__ gmax, const floa
         if (npos) atomicAdd(cand_count + b * 2, npos);
         if (nneg) atomicAdd(cand_count + b * 2 + 1, nneg);
     }
-}
-
-// gts-as-proposals head of the RCNN candidate list
-__global__ void rcnn_gt_head_kernel(const uint8_t *__restrict__ gt_valid, int B, int G, int32_t *__restrict__ assigned,
-                                    int64_t assigned_stride, int32_t *__restrict__ cand_count)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * G) return;
-    const int b = i / G, j = i - b * G;
-    const bool v = !gt_valid || gt_valid[i];
-    assigned[(int64_t)b * assigned_stride + j] = v ? j + 1 : -1;
-    if (v) atomicAdd(cand_count + b * 2, 1);             // a valid gt is a positive candidate of its own image
 }
 
 // ---- fast path of the samplers ------------------------------------------------------------------------------
@@ -448,7 +451,7 @@ static AssignWs carve_assign_ws(void *ws, int B, int G, int N)
 size_t assign_workspace_bytes(int B, int G, int N) { return carve_assign_ws(nullptr, B, G, N).total; }
 
 static cudaError_t run_assign(const AsIn &in, int B, const AssignWs &w, int32_t *assigned, int64_t assigned_stride,
-                              int assigned_offset, bool zero_counts, cudaStream_t s)
+                              int assigned_offset, bool zero_counts, cudaStream_t s, bool gt_head = false)
 {
     if (in.G > kAsMaxG) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(w.gmax, 0, (size_t)B * in.G * 4, s);
@@ -462,7 +465,7 @@ static cudaError_t run_assign(const AsIn &in, int B, const AssignWs &w, int32_t 
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     const size_t smem = (size_t)in.G * (sizeof(GtS) + 4) + 16;
-    assign_gtmax_kernel<<<dim3(gx, B), kAsThreads, smem, s>>>(in, w.gmax, w.best);
+    assign_gtmax_kernel<<<dim3(gx, B), kAsThreads, smem, s>>>(in, w.gmax, w.best, gt_head ? assigned : nullptr, assigned_stride, w.cand);
     assign_label_kernel<<<dim3(gx, B), kAsThreads, smem, s>>>(in, w.gmax, w.best, assigned, assigned_stride, assigned_offset, w.cand);
     return cudaGetLastError();
 }
@@ -517,8 +520,7 @@ cudaError_t launch_assign_sample_rcnn(const float *props5, const uint8_t *prop_m
     AsIn in{ props5, 5, (int64_t)P * 5, prop_mask, (int64_t)P, gts, gt_valid, G, P, cfg };
     cudaError_t e = cudaMemsetAsync(w.cand, 0, (size_t)B * 4 * 4, s);
     if (e != cudaSuccess) return e;
-    if (G > 0) rcnn_gt_head_kernel<<<(B * G + 255) / 256, 256, 0, s>>>(gt_valid, B, G, assigned, N, w.cand);
-    e = run_assign(in, B, w, assigned, N, G, false, s);
+    e = run_assign(in, B, w, assigned, N, G, false, s, G > 0);
     if (e != cudaSuccess) return e;
     SampleSink sink{ sel_idx, sel_idx + Sp, Sp, Sn, S, S, w.cand };
     e = run_samplers(assigned, B, N, Sp, Sn, 2u, seed, cfg, w, sink, s);

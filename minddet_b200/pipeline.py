@@ -8,8 +8,8 @@ import torch
 from . import synth
 from .ops import (AnchorGenerator, BboxAssignSample, BboxAssignSampleForRcnn, Proposal, SingleRoIExtractor)
 
-KERNELS_PER_STEP = 24   # 2 lanes x (select, nms_mask, nms_sweep), merge | gtmax, label, prefilter, select(list), select(full scan,
-                        # returns at once), finalize | gt_head, gtmax, label, prefilter, select x2, finalize |
+KERNELS_PER_STEP = 23   # 2 lanes x (select, nms_mask, nms_sweep), merge | gtmax, label, prefilter, select(list), select(full scan,
+                        # returns at once), finalize | gtmax (+ gt head), label, prefilter, select x2, finalize |
                         # roialign fwd (stream + gather for declined RoIs) | roialign bwd (stream + gather);
                         # the cudaMemsetAsync nodes of a step (dX zero-fill, small counters) are not counted
 
