@@ -111,3 +111,42 @@ def test_proposal_fewer_anchors_than_nms_pre():
     cfg = O.proposal_cfg(32, 32, nms_pre=100, max_num=64)
     ref = O.proposal_image([(logits[l][0], deltas[l][0], bases[l], strides[l]) for l in range(2)], cfg)
     assert np.array_equal(props[0].cpu().numpy(), ref["props"]) and np.array_equal(pmask[0].cpu().numpy().astype(np.uint8), ref["mask"])
+
+
+def test_proposal_single_level_takes_the_one_lane_path():
+    """L = 1: no helper stream, one top-k + NMS launch (the two-lane split needs at least two levels)."""
+    shapes, strides = [(25, 42)], (16,)
+    bases = synth.base_anchor_sets(strides)
+    logits, deltas = synth.rpn_head_outputs(2, shapes, 3, 11)
+    prop = Proposal((400, 672), strides, bases, nms_pre=300, max_num=200)
+    props, pmask = prop([dev(x) for x in logits], [dev(x) for x in deltas])
+    cfg = O.proposal_cfg(400, 672, nms_pre=300, max_num=200)
+    for b in range(2):
+        ref = O.proposal_image([(logits[0][b], deltas[0][b], bases[0], strides[0])], cfg)
+        assert np.array_equal(props[b].cpu().numpy(), ref["props"])
+        assert np.array_equal(pmask[b].cpu().numpy().astype(np.uint8), ref["mask"])
+
+
+def test_proposal_two_lanes_inside_a_cuda_graph():
+    """MdProposal forks onto the workspace's helper stream and joins back with events: the same call must be capturable
+    (the bench replays it inside a CUDA graph) and the replay must reproduce the eager result bit for bit."""
+    shapes, strides = [(50, 84), (25, 42), (13, 21)], (8, 16, 32)
+    bases = synth.base_anchor_sets(strides)
+    logits, deltas = synth.rpn_head_outputs(2, shapes, 3, 12)
+    prop = Proposal((400, 672), strides, bases, nms_pre=1000, max_num=1000)
+    ls, ds = [dev(x) for x in logits], [dev(x) for x in deltas]
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        eager_props, eager_mask = prop(ls, ds)          # warm-up on the capture stream: workspace + helper stream exist
+        side.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            g_props, g_mask = prop(ls, ds)
+        g_props.zero_()
+        g_mask.zero_()
+        graph.replay()
+        side.synchronize()
+    assert torch.equal(g_props, eager_props) and torch.equal(g_mask, eager_mask)
+    cfg = O.proposal_cfg(400, 672, nms_pre=1000, max_num=1000)
+    ref = O.proposal_image([(logits[l][0], deltas[l][0], bases[l], strides[l]) for l in range(3)], cfg)
+    assert np.array_equal(g_props[0].cpu().numpy(), ref["props"])
