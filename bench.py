@@ -30,7 +30,7 @@ METRIC = "Faster R-CNN RPN+RoI region path throughput"
 UNIT = "img/s"
 BATCH = 8
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the stream kernels (ncu --set full, profiles/r1_roialign_ncu.md)
-NCU_TRAFFIC = {"roialign_fwd": 849e6, "roialign_bwd": 1260e6}     # r1 v6: 652.7+190.5 MB / 791.4+469.1 MB (profiles/r1_roialign_ncu_v6.txt)
+NCU_TRAFFIC = {"roialign_fwd": 849e6, "roialign_bwd": 1260e6}     # fwd r1 v7: 656.7+192.2 MB (profiles/r1_roialign_fwd_ncu_v7.txt); bwd r1 v6: 791.4+469.1 MB (profiles/r1_roialign_ncu_v6.txt)
 WORKLOAD = ("configs[1]: Faster R-CNN R50-FPN region path, batch 8/GPU, 800x1344, 5 levels (268569 anchors), "
             "2000 pre-NMS/level, NMS 0.7, max_num 2000, G<=128 gts, 512 sampled RoIs, 256-ch 7x7 RoIAlign fwd+bwd")
 
