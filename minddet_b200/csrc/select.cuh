@@ -11,8 +11,14 @@
 //   * per-CTA totals are exchanged through DISTRIBUTED SHARED MEMORY (cluster.map_shared_rank),
 //   * the pass loop stops as soon as the threshold bin holds exactly the number still needed
 //     (normally after the 4 key digits; the index digits only run when a tie straddles K).
-// Selected composites are appended to the leader CTA's shared memory through DSMEM atomics, the
-// leader bitonic-sorts them (<= 2048) and calls Sink::emit(seg, rank, comp) in sorted order.
+// Every CTA then collects ITS winners into its own shared memory (two sweeps over the cached keys: count, block scan,
+// write), sorts them (shuffle-based bitonic sort, ~K/8 entries per CTA), and after one cluster barrier pulls the other
+// CTAs' sorted lists over DSMEM: a composite's final rank is its position in its own list plus the lower bounds in
+// the other seven, so the owner calls Sink::emit(seg, rank, comp) itself -- sort, ranking and emit are spread over the
+// cluster.  Segments with N <= kSelSoloMax and K <= kSelSoloMaxK are served by the leader alone ("solo": the other
+// CTAs exit at once, no cluster barrier); segments with N <= kSelDirectMax skip the radix passes (one sort).
+// Pass 0 of Srcs with raw_ptr()/from_raw() pulls the whole slice in with cp.async first.  -DMD_SEL_TIMING builds print
+// the cycles of every phase of the first cluster's leader.
 //
 // Semantics == oracle o_topk / o_sample (oracle/CONVENTIONS.md #4, #13).  Reference idiom being
 // replaced: ops.TopK(sorted=True) at centerpoint/det3d_ms/models/bbox_heads/center_head.py:435 and
