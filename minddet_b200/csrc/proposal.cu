@@ -6,8 +6,11 @@
 //     iou3d_nms_kernel.cu:361-405 -- same 64x64 tile -> one u64 word layout, but only the upper
 //     triangle is launched (the reference's early-out is commented out, :376) ...
 //   * ... and the host-side serial reduce (:571-593: cudaMalloc, blocking D2H of N*ceil(N/64)*8 bytes,
-//     CPU sweep, H2D) is replaced by nms_sweep_kernel: the greedy sweep runs on the device, one warp per
-//     (image, level), chunk-by-chunk with a warp-wide OR fixed point, zero host round trips.
+//     CPU sweep, H2D) is replaced by nms_sweep_kernel: the greedy sweep runs on the device, one CTA per
+//     (image, level) -- a resolver warp walking the 64-box chunks with a warp-wide OR fixed point, helper warps
+//     streaming the mask in and folding the kept rows -- zero host round trips.
+//   * launch_proposal runs two lanes side by side (finest level | the other levels: top-k -> mask -> sweep each) on the
+//     caller's stream and the workspace's helper stream, joined in front of the cross-level merge.
 //   * graph order top-k -> gather -> NMS -> gather-keep: center_head.py:435-459.
 // Semantics: oracle/CONVENTIONS.md #1-8, #17; oracle/region_oracle.c (o_topk, o_nms, o_proposal_image).
 #include <cstdlib>
