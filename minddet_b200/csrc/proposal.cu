@@ -879,7 +879,9 @@ cudaError_t launch_proposal(const LevelSet &lv, int B, int nms_pre, int max_num,
         //  * the other levels finish their top-k first, and their (issue-bound) mask kernel then fills the SMs the
         //    (latency-bound) level-0 top-k leaves mostly idle.
         // Measured inside the step (bench.py): 1.008 -> 0.991 ms provided nothing DRAM-heavy runs beside this chain (with
-        // the gradient zero-fill started at the top of the step the lanes made it 12 us longer).
+        // the gradient zero-fill started at the top of the step the lanes made it 12 us longer).  Also measured: the
+        // caller's lane taking the second level's NMS as well (it finishes its top-k later but has less NMS work):
+        // MdProposal 147 -> 158 us, step +13 us -- two issue-bound mask kernels side by side only slow each other.
         int maxN1 = 0;
         for (int l = 1; l < L; l++) maxN1 = max(maxN1, lv.A[l] * lv.H[l] * lv.W[l]);
         e = cudaEventRecord(side->fork, s);
