@@ -203,8 +203,9 @@ def run_b200(args):
     rp = pipeline.RegionPath(seed=0)
     host = pipeline.make_inputs(BATCH, seed=0xD37 + rank, pin=True)
     h2d_bytes = pipeline.input_bytes(host)
-    side = torch.cuda.Stream(priority=-1)     # the chain; the zero-fill stream below keeps the default (lower) priority,
-    aux = torch.cuda.Stream(priority=-1)      # so its blocks fill SMs the chain leaves idle instead of queueing ahead of it
+    side = torch.cuda.Stream(priority=-1)     # the chain.  The RPN-target and zero-fill streams below keep the default (lower)
+    aux = torch.cuda.Stream()                 # priority: their blocks fill SMs the chain leaves idle instead of queueing ahead of
+                                              # it (measured, RPN targets at the chain's priority: 0.984 vs 0.967 ms per step)
     zstream, zjoin, zfork = torch.cuda.Stream(), torch.cuda.Event(), torch.cuda.Event()
     fork, join = torch.cuda.Event(), torch.cuda.Event()
     group_streams = [torch.cuda.Stream() for _ in range(max(0, args.split - 1))]

@@ -58,7 +58,9 @@ const md::SideLane *get_side_lane(void *stream)
             return nullptr;                 // first use inside a capture: stay on one stream
         }
         md::SideLane l{};
-        if (cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        int prio = 0;                       // the helper lane is part of the caller's chain: same scheduling priority
+        if (cudaStreamGetPriority((cudaStream_t)stream, &prio) != cudaSuccess) { cudaGetLastError(); prio = 0; }
+        if (cudaStreamCreateWithPriority(&l.stream, cudaStreamNonBlocking, prio) != cudaSuccess ||
             cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) {
             cudaGetLastError();
