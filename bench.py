@@ -203,9 +203,12 @@ def run_b200(args):
     rp = pipeline.RegionPath(seed=0)
     host = pipeline.make_inputs(BATCH, seed=0xD37 + rank, pin=True)
     h2d_bytes = pipeline.input_bytes(host)
-    side = torch.cuda.Stream(priority=-1)     # the chain.  The RPN-target and zero-fill streams below keep the default (lower)
-    aux = torch.cuda.Stream()                 # priority: their blocks fill SMs the chain leaves idle instead of queueing ahead of
-                                              # it (measured, RPN targets at the chain's priority: 0.984 vs 0.967 ms per step)
+    # Three priority levels (the device offers 0 .. -3; out-of-range values are clamped): the chain highest, the RPN
+    # targets below it, the zero-fill lowest -- side work fills the SMs the chain leaves idle instead of queueing ahead of
+    # it.  Measured per step: all equal 1.039 ms; RPN targets at the chain's priority 0.984; chain > (RPN = fill) 0.967;
+    # chain > RPN > fill 0.960.
+    side = torch.cuda.Stream(priority=-2)
+    aux = torch.cuda.Stream(priority=-1)
     zstream, zjoin, zfork = torch.cuda.Stream(), torch.cuda.Event(), torch.cuda.Event()
     fork, join = torch.cuda.Event(), torch.cuda.Event()
     group_streams = [torch.cuda.Stream() for _ in range(max(0, args.split - 1))]
