@@ -18,8 +18,13 @@
  *   Float attributes travel as a trailing 1-D float32 `cfg` INPUT TENSOR that is read on the device
  *   (the reference passes its NMS threshold the same way, iou_gpu.py:57, iou3d_nms_kernel.cu:500);
  *   integer attributes travel in the output shapes.  No dynamic output shapes: fixed size + mask/count.
- * Return value: 0 success; 1 wrong nparam; 2 bad dtype/shape; 3 CUDA error; 4 unsupported size.
+ * Return value: 0 success; 1 wrong nparam; 2 bad dtype/shape; 3 CUDA error; 4 unsupported size;
+ *   5 the op needs to allocate (first call on this stream, or a bigger shape than any before) while the stream is being
+ *   captured into a CUDA graph -- run it once eagerly (or in graph mode's warm-up) first.
  *   (the reference returns 1 on wrong nparam, iou-bev-nms-org.cpp:238, and 0 on success, :282.)
+ * Workspace lifetime: scratch blocks are never freed or moved while the library is loaded (growth retires the old block
+ *   but keeps it mapped), so a captured CUDA graph stays valid whatever is called afterwards.  The device used is the one
+ *   current on the calling thread (MindSpore binds one device per process): make the tensors' device current.
  * There is NO CPU fallback: without a CUDA device every entry returns 3.
  *
  * cfg slot tables: the MD_CFG_* enums below.

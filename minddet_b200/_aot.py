@@ -27,7 +27,8 @@ SYMBOLS = ("MdAnchorGrid", "MdDecodeClip", "MdDecodeLevel", "MdTopKPerLevel", "M
            "BoxesIouBevGpu", "BoxesOverlapBevGpu", "NmsGpu", "NmsNormalGpu", "BoxesIouNmsGpu",
            "MdYoloDecode", "MdYoloNms", "MdMaskTargets", "MdEncode", "MdRcnnPostProcess")
 
-ERRORS = {1: "wrong nparam", 2: "bad dtype/shape", 3: "CUDA error", 4: "unsupported size"}
+ERRORS = {1: "wrong nparam", 2: "bad dtype/shape", 3: "CUDA error", 4: "unsupported size",
+          5: "workspace must grow while the stream is being captured (run the op once eagerly first)"}
 
 _lib = None
 
@@ -74,9 +75,13 @@ def call_aot(symbol, inputs, outputs, stream=None, lib=None):
     shape_arrays = [(ctypes.c_int64 * max(1, t.dim()))(*t.shape) for t in tensors]
     shapes = (ctypes.POINTER(ctypes.c_int64) * n)(*[ctypes.cast(a, ctypes.POINTER(ctypes.c_int64)) for a in shape_arrays])
     dtypes = (ctypes.c_char_p * n)(*[_DTYPE_NAMES[t.dtype].encode() for t in tensors])
+    dev = tensors[0].device
+    if any(t.device != dev for t in tensors):
+        raise AotError(f"{symbol}: all tensors must live on one device")
     if stream is None:
-        stream = torch.cuda.current_stream(tensors[0].device).cuda_stream
-    rc = getattr(lib, symbol)(n, params, ndims, shapes, dtypes, ctypes.c_void_p(stream), None)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):          # the library keys its workspace on the CURRENT device (as MindSpore binds it)
+        rc = getattr(lib, symbol)(n, params, ndims, shapes, dtypes, ctypes.c_void_p(stream), None)
     if rc != 0:
         raise AotError(f"{symbol} returned {rc} ({ERRORS.get(rc, 'unknown')})")
     return outputs

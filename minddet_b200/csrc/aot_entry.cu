@@ -6,45 +6,77 @@
 //   * work is enqueued on the stream MindSpore passes and never synchronised (the reference
 //     cudaStreamSynchronize()s it and launches on the default stream, :448-449);
 //   * no libtorch (the reference wraps raw pointers as at::Tensor, ms_ext.cpp:14-27);
-//   * scratch comes from a per-(device,stream) grow-only workspace, not cudaMalloc/cudaFree per call (:510-517);
+//   * scratch comes from a per-(device,stream) grow-only workspace that is never freed or moved while the library is
+//     loaded (safe under CUDA-graph replay), not cudaMalloc/cudaFree per call (:510-517);
 //   * errors are returned, never exit()ed (:32-40).
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <utility>
+#include <vector>
 
 #include "../../include/md_region_aot.h"
 #include "kernels.h"
 
 namespace {
 
-enum { MD_OK = 0, MD_ERR_NPARAM = 1, MD_ERR_ARG = 2, MD_ERR_CUDA = 3, MD_ERR_SIZE = 4 };
+enum { MD_OK = 0, MD_ERR_NPARAM = 1, MD_ERR_ARG = 2, MD_ERR_CUDA = 3, MD_ERR_SIZE = 4, MD_ERR_CAPTURE = 5 };
 
-struct Workspace { void *ptr = nullptr; size_t bytes = 0; md::SideLane lane{}; bool has_lane = false; };
+// Per-(device, stream) state: scratch block, a small zero-initialised control block (work tickets the kernels re-arm
+// themselves), the helper lane.  Graph-safe by construction:
+//   * a block is NEVER freed or moved while the library is loaded: growth allocates a bigger block and retires the old
+//     one (kept until MdShutdown), so a CUDA graph captured earlier keeps replaying against valid memory;
+//   * nothing is allocated or created while the stream is being captured (cudaMalloc / cudaStreamCreate are not
+//     capturable): the call returns MD_ERR_CAPTURE (5) instead -- run the op once, or MdReserve(), before capturing.
+struct Workspace {
+    void *ptr = nullptr; size_t bytes = 0;
+    int *ctl = nullptr;
+    std::vector<void *> retired;
+    md::SideLane lane{}; bool has_lane = false;
+};
 std::mutex g_ws_mutex;
 std::map<std::pair<int, void *>, Workspace> g_ws;
 
-// Grow-only scratch keyed by (device, stream).  Growth frees the old block with cudaFree, which
-// waits for the device, so no kernel that still uses it can be in flight.  (Warm up before capturing
-// a CUDA graph: allocation is not capturable.)
-int get_workspace(void *stream, size_t bytes, void **out)
+bool capturing(void *stream)
+{
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing((cudaStream_t)stream, &st) != cudaSuccess) { cudaGetLastError(); return false; }
+    return st != cudaStreamCaptureStatusNone;
+}
+
+// The device is the one the framework made current for this call (MindSpore binds one device per process / executor
+// thread); tensors of another device are a caller error.
+int get_workspace(void *stream, size_t bytes, void **out, int **ctl = nullptr)
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return MD_ERR_CUDA;
     std::lock_guard<std::mutex> lock(g_ws_mutex);
     Workspace &w = g_ws[std::make_pair(dev, stream)];
-    if (w.bytes < bytes) {
-        if (w.ptr) cudaFree(w.ptr);
-        w.ptr = nullptr; w.bytes = 0;
-        const size_t want = bytes + bytes / 4 + 4096;
-        if (cudaMalloc(&w.ptr, want) != cudaSuccess) { cudaGetLastError(); return MD_ERR_CUDA; }
-        w.bytes = want;
+    if (w.bytes < bytes || !w.ctl) {
+        if (capturing(stream)) return MD_ERR_CAPTURE;
+        if (!w.ctl) {
+            if (cudaMalloc(reinterpret_cast<void **>(&w.ctl), md::MD_CTL_INTS * sizeof(int)) != cudaSuccess ||
+                cudaMemset(w.ctl, 0, md::MD_CTL_INTS * sizeof(int)) != cudaSuccess) {
+                cudaGetLastError();
+                w.ctl = nullptr;
+                return MD_ERR_CUDA;
+            }
+        }
+        if (w.bytes < bytes) {
+            const size_t want = (bytes > 2 * w.bytes ? bytes : 2 * w.bytes) + 4096;
+            void *p = nullptr;
+            if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return MD_ERR_CUDA; }
+            if (w.ptr) w.retired.push_back(w.ptr);
+            w.ptr = p; w.bytes = want;
+        }
     }
     *out = w.ptr;
+    if (ctl) *ctl = w.ctl;
     return MD_OK;
 }
 
-// the (device, stream) workspace's helper stream; created on first use (not capturable: warm up first, like the scratch)
+// the (device, stream) helper stream; created at the first non-capturing touch.  Inside a capture that meets no lane the
+// op runs on one stream (same results, a little slower) -- never an error.
 const md::SideLane *get_side_lane(void *stream)
 {
     int dev = 0;
@@ -52,11 +84,7 @@ const md::SideLane *get_side_lane(void *stream)
     std::lock_guard<std::mutex> lock(g_ws_mutex);
     Workspace &w = g_ws[std::make_pair(dev, stream)];
     if (!w.has_lane) {
-        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-        if (cudaStreamIsCapturing((cudaStream_t)stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
-            cudaGetLastError();
-            return nullptr;                 // first use inside a capture: stay on one stream
-        }
+        if (capturing(stream)) return nullptr;
         md::SideLane l{};
         int prio = 0;                       // the helper lane is part of the caller's chain: same scheduling priority
         if (cudaStreamGetPriority((cudaStream_t)stream, &prio) != cudaSuccess) { cudaGetLastError(); prio = 0; }
@@ -322,10 +350,11 @@ static int roialign_fwd_impl(int mode, MD_AOT_ARGS)
     REQ(is_f32(dtypes[io]) && ndims[io] == 4 && shapes[io][0] == R && shapes[io][1] == fs.C && shapes[io][2] == shapes[io][3]);
     const int P = (int)shapes[io][2];
     void *ws = nullptr;
-    rc = get_workspace(stream, md::roialign_workspace_bytes(R), &ws);
+    int *ctl = nullptr;
+    rc = get_workspace(stream, md::roialign_workspace_bytes(R), &ws, &ctl);
     if (rc) return rc;
     return cuda_rc(md::launch_roialign_fwd(fs, (const float *)params[0], R, P, (const float *)params[ic],
-                                           (float *)params[io], ws, mode, (cudaStream_t)stream));
+                                           (float *)params[io], ws, ctl, mode, (cudaStream_t)stream));
 }
 
 static int roialign_bwd_impl(int mode, MD_AOT_ARGS)
@@ -343,10 +372,11 @@ static int roialign_bwd_impl(int mode, MD_AOT_ARGS)
     REQ(is_f32(dtypes[2]) && numel(ndims[2], shapes[2]) >= MD_ROI_STRIDE0 + L);
     const int P = (int)shapes[1][2];
     void *ws = nullptr;
-    rc = get_workspace(stream, md::roialign_workspace_bytes(R), &ws);
+    int *ctl = nullptr;
+    rc = get_workspace(stream, md::roialign_workspace_bytes(R), &ws, &ctl);
     if (rc) return rc;
     return cuda_rc(md::launch_roialign_bwd(fs, (const float *)params[0], R, P, (const float *)params[2],
-                                           (const float *)params[1], ws, mode, (cudaStream_t)stream));
+                                           (const float *)params[1], ws, ctl, mode, (cudaStream_t)stream));
 }
 static int roialign_bwd_acc_impl(MD_AOT_ARGS)
 {
@@ -364,12 +394,13 @@ static int roialign_bwd_acc_impl(MD_AOT_ARGS)
     REQ(is_i32(dtypes[nparam - 1]) && numel(ndims[nparam - 1], shapes[nparam - 1]) >= 1);
     const int P = (int)shapes[1][2];
     void *ws = nullptr;
-    rc = get_workspace(stream, md::roialign_workspace_bytes(R), &ws);
+    int *ctl = nullptr;
+    rc = get_workspace(stream, md::roialign_workspace_bytes(R), &ws, &ctl);
     if (rc) return rc;
     rc = cuda_rc(cudaMemsetAsync(params[nparam - 1], 0, sizeof(int32_t), (cudaStream_t)stream));
     if (rc) return rc;
     return cuda_rc(md::launch_roialign_bwd(fs, (const float *)params[0], R, P, (const float *)params[2],
-                                           (const float *)params[1], ws, 0, (cudaStream_t)stream, true));
+                                           (const float *)params[1], ws, ctl, 0, (cudaStream_t)stream, true));
 }
 
 // ---- the reference's own GPU symbols (iou3d_nms_kernel.cu:445-601), same parameter lists ------------------------

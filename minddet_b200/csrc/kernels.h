@@ -86,9 +86,12 @@ cudaError_t launch_mask_targets(const uint8_t *masks, int B, int G, int H, int W
 cudaError_t launch_roi_levels(const float *rois5, int R, const float *cfg, int32_t *out, cudaStream_t s);
 size_t roialign_workspace_bytes(int R);
 // mode (cfg slot MD_ROI_MODE): 0 = TMA separable kernels (+ gather for RoIs they decline), 1 = gather only
+// ctl: the (device, stream) control block (zero-initialised ints that persist between calls; the channel-lane kernels keep
+// their work tickets in ctl[MD_CTL_ROI_FWD ..] / ctl[MD_CTL_ROI_BWD ..] and re-arm them before they exit)
+enum { MD_CTL_ROI_FWD = 0, MD_CTL_ROI_BWD = 8, MD_CTL_INTS = 1024 };
 cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
-                                float *out, void *ws, int mode, cudaStream_t s);
+                                float *out, void *ws, int *ctl, int mode, cudaStream_t s);
 cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
-                                const float *dout, void *ws, int mode, cudaStream_t s, bool accumulate = false);
+                                const float *dout, void *ws, int *ctl, int mode, cudaStream_t s, bool accumulate = false);
 
 }  // namespace md

@@ -57,12 +57,16 @@ roialign_fwd_gather_kernel(const RoiFeat f, const float *__restrict__ rois5, int
         if (only_flagged && !only_flagged[r]) continue;   // handled by the TMA kernel (uniform over the block)
         const int S = (int)__ldg(f.cfg + 1);
         const RoiGeom g = roi_geometry(f, rois5 + (int64_t)r * 5, P);
-        build_taps(g, P, S, taps);
-        __syncthreads();
         const int PP = P * P, SS = S * S;
-        const float cnt = (float)SS;
         const int cper = (f.C + csplit - 1) / csplit;
         const int c0 = blockIdx.y * cper, c1 = min(f.C, c0 + cper);
+        if (!g.ok || S < 1 || PP * SS > kRoiMaxTaps) {     // bad batch index / sample count the tap table cannot hold: zeros
+            for (int o = c0 * PP + threadIdx.x; o < c1 * PP; o += kRoiThreads) out[(int64_t)r * f.C * PP + o] = 0.0f;
+            continue;
+        }
+        build_taps(g, P, S, taps);
+        __syncthreads();
+        const float cnt = (float)SS;
         const int64_t plane = (int64_t)g.H * g.W;
         const float *fb = f.feat[g.l] + (int64_t)g.b * f.C * plane;
         for (int o = c0 * PP + threadIdx.x; o < c1 * PP; o += kRoiThreads) {
@@ -91,9 +95,10 @@ roialign_bwd_gather_kernel(const RoiFeat f, const float *__restrict__ rois5, int
         if (only_flagged && !only_flagged[r]) continue;
         const int S = (int)__ldg(f.cfg + 1);
         const RoiGeom g = roi_geometry(f, rois5 + (int64_t)r * 5, P);
+        const int PP = P * P, SS = S * S;
+        if (!g.ok || S < 1 || PP * SS > kRoiMaxTaps) continue;   // bad batch index / oversized tap table: no gradient
         build_taps(g, P, S, taps);
         __syncthreads();
-        const int PP = P * P, SS = S * S;
         const float cnt = (float)SS;
         const int cper = (f.C + csplit - 1) / csplit;
         const int c0 = blockIdx.y * cper, c1 = min(f.C, c0 + cper);
@@ -171,12 +176,17 @@ cudaError_t launch_roialign_fwd_tma(const FeatSet &fs, const RoiFeat &f, const f
                                     float *out, int32_t *fallback_flag, cudaStream_t s, bool *launched);
 cudaError_t launch_roialign_bwd_tma(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P,
                                     const float *dout, int32_t *fallback_flag, cudaStream_t s, bool *launched);
+// roialign_cl.cu: channel-per-lane kernels (7x7, C % 32 == 0); RoIs they decline are flagged for the gather kernels
+cudaError_t launch_roialign_fwd_cl(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, float *out,
+                                   int32_t *fallback_flag, int *ctr, cudaStream_t s, bool *launched);
+cudaError_t launch_roialign_bwd_cl(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, const float *dout,
+                                   int32_t *fallback_flag, int *ctr, cudaStream_t s, bool *launched);
 
 size_t roialign_workspace_bytes(int R) { return (size_t)R * sizeof(int32_t) + 256; }
 
 // mode: 0 = TMA separable kernel + gather for the RoIs it declines (default); 1 = gather only (bit-exact fwd)
 cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
-                                float *out, void *ws, int mode, cudaStream_t s)
+                                float *out, void *ws, int *ctl, int mode, cudaStream_t s)
 {
     if (R == 0) return cudaSuccess;
     if (P * P * 4 > kRoiMaxTaps || fs.L > kMaxLv) return cudaErrorInvalidValue;
@@ -184,7 +194,10 @@ cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, in
     int32_t *flags = reinterpret_cast<int32_t *>(ws);
     bool tma = false;
     if (mode == 0 && flags) {
-        cudaError_t e = launch_roialign_fwd_tma(fs, f, rois5, R, P, out, flags, s, &tma);
+        cudaError_t e = cudaSuccess;
+        if (ctl) e = launch_roialign_fwd_cl(fs, f, rois5, R, P, out, flags, ctl + MD_CTL_ROI_FWD, s, &tma);
+        if (e != cudaSuccess) return e;
+        if (!tma) e = launch_roialign_fwd_tma(fs, f, rois5, R, P, out, flags, s, &tma);
         if (e != cudaSuccess) return e;
     }
     const int csplit = (fs.C >= 64 && !tma) ? 4 : 1;
@@ -193,7 +206,7 @@ cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, in
 }
 
 cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
-                                const float *dout, void *ws, int mode, cudaStream_t s, bool accumulate)
+                                const float *dout, void *ws, int *ctl, int mode, cudaStream_t s, bool accumulate)
 {
     if (P * P * 4 > kRoiMaxTaps || fs.L > kMaxLv) return cudaErrorInvalidValue;
     for (int l = 0; l < fs.L && !accumulate; l++) {
@@ -205,7 +218,10 @@ cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, in
     int32_t *flags = reinterpret_cast<int32_t *>(ws);
     bool tma = false;
     if (mode == 0 && flags) {
-        cudaError_t e = launch_roialign_bwd_tma(fs, f, rois5, R, P, dout, flags, s, &tma);
+        cudaError_t e = cudaSuccess;
+        if (ctl) e = launch_roialign_bwd_cl(fs, f, rois5, R, P, dout, flags, ctl + MD_CTL_ROI_BWD, s, &tma);
+        if (e != cudaSuccess) return e;
+        if (!tma) e = launch_roialign_bwd_tma(fs, f, rois5, R, P, dout, flags, s, &tma);
         if (e != cudaSuccess) return e;
     }
     const int csplit = (fs.C >= 64 && !tma) ? 4 : 1;

@@ -46,7 +46,7 @@ MD_DEVINL Tap make_tap(float y, float x, int H, int W)
     return t;
 }
 
-struct RoiGeom { int b, l, H, W; float sw, sh, bw, bh; };
+struct RoiGeom { int b, l, H, W; float sw, sh, bw, bh; bool ok; };   // ok: batch index inside [0, B) (CONVENTIONS #23)
 
 MD_DEVINL RoiGeom roi_geometry(const RoiFeat &f, const float *__restrict__ roi, int P)
 {
@@ -54,7 +54,9 @@ MD_DEVINL RoiGeom roi_geometry(const RoiFeat &f, const float *__restrict__ roi, 
     float r[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) r[k] = __ldg(roi + 1 + k);
-    g.b = (int)__ldg(roi);
+    const float bf = __ldg(roi);
+    g.ok = bf >= 0.0f && bf < (float)f.B;          // false for NaN too
+    g.b = g.ok ? (int)bf : 0;
     g.l = roi_level_of(r, __ldg(f.cfg + 0), f.L);
     g.H = f.H[g.l]; g.W = f.W[g.l];
     const float scale = div(1.0f, __ldg(f.cfg + 4 + g.l));
@@ -72,5 +74,34 @@ MD_DEVINL float sample_coord(float start, float bin, int p, int i, int S)
     return add(base, o);
 }
 
+
+// ---- 1-D sample -> (low index, high index, low weight, high weight, valid); mirrors make_tap ----------
+MD_DEVINL bool sample_1d(float v, int extent, int &lo, int &hi, float &wl, float &wh)
+{
+    if (v < -1.0f || v > (float)extent) return false;
+    if (v <= 0.0f) v = 0.0f;
+    lo = (int)v;
+    if (lo >= extent - 1) { hi = lo = extent - 1; v = (float)lo; } else hi = lo + 1;
+    wh = sub(v, (float)lo);
+    wl = sub(1.0f, wh);
+    return true;
+}
+
+
+// CTA -> (RoI, channel chunk).  Blocks are ordered (segment of `seg` consecutive RoIs, chunk, RoI in segment)
+// so that the CTAs resident at any time read the SAME channel planes of (normally) one image: every
+// feature byte is then fetched from HBM once and re-used out of L2 by all RoIs that overlap it.
+struct WorkItem { int r, chunk; };
+MD_DEVINL WorkItem work_item(int bid, int R, int seg, int nchunk)
+{
+    const int per_seg = seg * nchunk;
+    const int sidx = bid / per_seg, base = sidx * seg;
+    const int seg_len = min(seg, R - base);
+    const int rem = bid - sidx * per_seg;
+    WorkItem w;
+    w.chunk = rem / seg_len;
+    w.r = base + (rem - w.chunk * seg_len);
+    return w;
+}
 
 }  // namespace md

@@ -34,6 +34,8 @@
 
 #include "kernels.h"
 #include "roialign_common.cuh"
+#include "tma_host.h"
+#include "tma_ptx.cuh"
 
 namespace md {
 
@@ -65,63 +67,6 @@ struct __align__(16) SampleTap { int lo, hi; float wl, wh; };   // rows/cols rel
 // columns of padding move the second channel to the other half of the banks.
 __host__ __device__ inline int fwd_box_width(int bw) { return (bw == 8 || bw == 16) ? bw + 4 : bw; }
 __host__ __device__ inline int lanes_per_channel(int bw) { return bw <= 16 ? 4 : (bw <= 32 ? 8 : (bw <= 64 ? 16 : 32)); }
-
-// ---- PTX wrappers -----------------------------------------------------------------------------------
-MD_DEVINL uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-MD_DEVINL void mbar_init(unsigned long long *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-MD_DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-MD_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-MD_DEVINL void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-MD_DEVINL void mbar_wait(unsigned long long *bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    const uint32_t a = smem_u32(bar);
-    while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
-    }
-}
-MD_DEVINL void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
-}
-MD_DEVINL void tma_reduce_add_3d(const CUtensorMap *map, int x, int y, int z, const void *src)
-{
-    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 :: "l"(map), "r"(smem_u32(src)), "r"(x), "r"(y), "r"(z) : "memory");
-}
-MD_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> MD_DEVINL void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
-template <int N> MD_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
-MD_DEVINL void cp_async4(void *smem, const void *gmem)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(smem)), "l"(gmem) : "memory");
-}
-MD_DEVINL void cp_async_mbar_arrive(unsigned long long *bar)
-{
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-MD_DEVINL void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> MD_DEVINL void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
-
-// ---- 1-D sample -> (low index, high index, low weight, high weight, valid); mirrors make_tap ----------
-MD_DEVINL bool sample_1d(float v, int extent, int &lo, int &hi, float &wl, float &wh)
-{
-    if (v < -1.0f || v > (float)extent) return false;
-    if (v <= 0.0f) v = 0.0f;
-    lo = (int)v;
-    if (lo >= extent - 1) { hi = lo = extent - 1; v = (float)lo; } else hi = lo + 1;
-    wh = sub(v, (float)lo);
-    wl = sub(1.0f, wh);
-    return true;
-}
 
 // ---- per-RoI prologue: sample tables and footprint --------------------------------------------------
 template <int P>
@@ -173,22 +118,6 @@ MD_DEVINL void build_tables(StreamShared<P> &sh, const RoiGeom &g)
 // =====================================================================================================
 // forward
 // =====================================================================================================
-// CTA -> (RoI, channel chunk).  Blocks are ordered (segment of `seg` consecutive RoIs, chunk, RoI in segment)
-// so that the CTAs resident at any time read the SAME channel planes of (normally) one image: every
-// feature byte is then fetched from HBM once and re-used out of L2 by all RoIs that overlap it.
-struct WorkItem { int r, chunk; };
-MD_DEVINL WorkItem work_item(int bid, int R, int seg, int nchunk)
-{
-    const int per_seg = seg * nchunk;
-    const int sidx = bid / per_seg, base = sidx * seg;
-    const int seg_len = min(seg, R - base);
-    const int rem = bid - sidx * per_seg;
-    WorkItem w;
-    w.chunk = rem / seg_len;
-    w.r = base + (rem - w.chunk * seg_len);
-    return w;
-}
-
 // step 2 of the forward: U[cs][p][BWU] (smem) -> Out[cs][p][q].  lane = (channel-in-round, q); the lane's four
 // column taps stay in registers, rows advance by an immediate (BWU is a template parameter).
 template <int P, int BWU>
@@ -249,7 +178,7 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
     }
     if (flag_writer) fallback_flag[r] = 0;
     float *orow = out + ((int64_t)r * C + cbase) * PP;
-    if (!sh.any_x || !sh.any_y) {                                   // every sample is out of range -> zeros
+    if (!g.ok || !sh.any_x || !sh.any_y) {                          // bad batch index, or every sample out of range -> zeros
         for (int i = tid; i < CH * PP; i += kStThreads) orow[i] = 0.0f;
         return;
     }
@@ -515,7 +444,7 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
         if (flag_writer) fallback_flag[r] = 1;
         return;
     }
-    if (!sh.any_x || !sh.any_y) {                                   // no sample in range -> no gradient
+    if (!g.ok || !sh.any_x || !sh.any_y) {                          // bad batch index / no sample in range -> no gradient
         if (flag_writer) fallback_flag[r] = 0;
         return;
     }
@@ -698,11 +627,7 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
 // =====================================================================================================
 // host: tensor maps (one per (level, box width)); small LRU keyed by (pointers, dims)
 // =====================================================================================================
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode()
+EncodeTiledFn get_encode()
 {
     static EncodeTiledFn fn = nullptr;
     static std::once_flag once;

@@ -646,10 +646,13 @@ O_API void o_roialign_fwd(int L, const float *const *feats, const int *H_, const
                           const float *scale_, int B, int C, const float *rois5, int64_t R,
                           const int32_t *lvl_in, float finest, int P, int S, float end_mode, float *out)
 {
-    (void)B;
     Tap *taps = (Tap *)malloc(sizeof(Tap) * (size_t)P * P * S * S);
     for (int64_t r = 0; r < R; r++) {
         const float *roi = rois5 + r * 5;
+        if (!(roi[0] >= 0.0f && roi[0] < (float)B)) {   /* CONVENTIONS #23: batch index out of range (or NaN) -> zeros */
+            memset(out + (int64_t)r * C * P * P, 0, sizeof(float) * (size_t)C * P * P);
+            continue;
+        }
         int b = (int)roi[0];
         int l = lvl_in ? lvl_in[r] : roi_level(roi + 1, finest, L);
         int H = H_[l], W = W_[l];
@@ -691,10 +694,10 @@ O_API void o_roialign_bwd(int L, float *const *dfeats, const int *H_, const int 
                           const int32_t *lvl_in, float finest, int P, int S, float end_mode,
                           const float *dout)
 {
-    (void)B;
     Tap *taps = (Tap *)malloc(sizeof(Tap) * (size_t)P * P * S * S);
     for (int64_t r = 0; r < R; r++) {
         const float *roi = rois5 + r * 5;
+        if (!(roi[0] >= 0.0f && roi[0] < (float)B)) continue;   /* CONVENTIONS #23: no gradient */
         int b = (int)roi[0];
         int l = lvl_in ? lvl_in[r] : roi_level(roi + 1, finest, L);
         int H = H_[l], W = W_[l];

@@ -312,7 +312,7 @@ def test_roi_levels_bit_exact():
 
 
 @pytest.mark.parametrize("exact", [False, True])
-@pytest.mark.parametrize("P,S,C", [(7, 2, 16), (14, 2, 8), (7, 1, 4), (7, 2, 37)])
+@pytest.mark.parametrize("P,S,C", [(7, 2, 16), (14, 2, 8), (7, 1, 4), (7, 2, 37), (7, 2, 64)])
 def test_roialign_fwd_bwd_vs_oracle(P, S, C, exact):
     rng = np.random.default_rng(42)
     B = 2
@@ -328,6 +328,12 @@ def test_roialign_fwd_bwd_vs_oracle(P, S, C, exact):
     rois[5, 1:] = [5, 100, 1300, 130]     # wide and flat -> wider than the largest TMA box (gather path)
     rois[6, 1:] = [-500, -500, -300, -300]  # entirely outside: every sample invalid -> zeros
     rois[7, 1:] = [1342, 798, 1400, 900]
+    rois[8, 1:] = [300, 300, 301, 301]    # one-pixel RoI: every bin on the same two rows / columns (dense row weights)
+    rois[9, 1:] = [40, 40, 67, 67]        # bin size exactly 1 feature pixel on level 0: samples on x.25 / x.75
+    rois[10, 1:] = [64, 64, 175, 175]     # sqrt(area) = 112: first RoI of level 1
+    rois[11, 1:] = [10, 10, 450, 120]     # 110 columns on level 1 (3 column chunks of the channel-lane kernel)
+    rois[12, 0] = -1                       # batch index out of range: no data (zeros forward, nothing backward)
+    rois[13, 0] = B
     ext = SingleRoIExtractor(P, S, strides, 56, exact=exact)
     ft = [dev(f).requires_grad_(True) for f in feats]
     out = ext(dev(rois), *ft)
