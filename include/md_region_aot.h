@@ -103,16 +103,22 @@ MD_API int MdNms(MD_AOT_ARGS);
  *   (nparam = 3L+1+4; nms_pre and max_num are read from the output shapes) */
 MD_API int MdProposal(MD_AOT_ARGS);
 
+/* Sampling randomness (a8, both flavours): seed = {seed_lo, seed_hi} or {seed_lo, seed_hi, step}.  The sample is the
+ * k candidates with the smallest Philox-4x32-10 keys, counter (candidate, stream, image, step), key (seed_lo, seed_hi).
+ * With the 3-word form the op INCREMENTS seed[2] on the device when its samplers are done, so the next call -- or the
+ * next replay of a captured CUDA graph -- draws a fresh sample (the reference draws fresh npr.choice samples per call,
+ * pointpillars/src/core/target_assigner.py:116-128).  Keep that tensor alive between calls (a Parameter / buffer); the
+ * 2-word form means step 0 for ever (reproducible single calls).  oracle/CONVENTIONS.md #13, #24. */
 /* a7/a8  BboxAssignSample (RPN flavour)
  *   in : boxes (N,4) [shared by the batch] or (B,N,4) f32 | box_valid (N)/(B,N) uint8/bool
- *        | gts (B,G,4) f32 | gt_valid (B,G) uint8/bool | cfg f32[16] = MD_CFG_ASSIGN | seed int32[2]
+ *        | gts (B,G,4) f32 | gt_valid (B,G) uint8/bool | cfg f32[16] = MD_CFG_ASSIGN | seed int32[2 or 3]
  *   out: assigned (B,N) int32 | pos_idx (B,Sp) int32 | pos_valid (B,Sp) uint8 | neg_idx (B,Sn) int32
  *        | neg_valid (B,Sn) uint8 | pos_gt (B,Sp) int32 | pos_target (B,Sp,4) f32 | num_pos (B) int32 */
 MD_API int MdAssignSample(MD_AOT_ARGS);
 
 /* a8  BboxAssignSampleForRcnn (gts are prepended to the proposals as candidates)
  *   in : proposals (B,P,5) f32 | prop_mask (B,P) uint8/bool | gts (B,G,4) f32 | gt_labels (B,G) int32
- *        | gt_valid (B,G) uint8/bool | cfg f32[16] = MD_CFG_ASSIGN | seed int32[2]
+ *        | gt_valid (B,G) uint8/bool | cfg f32[16] = MD_CFG_ASSIGN | seed int32[2 or 3]
  *   out: rois (B,S,5) f32 [batch,x1,y1,x2,y2] | deltas (B,S,4) f32 | labels (B,S) int32
  *        | mask (B,S) uint8 | assigned (B,G+P) int32 | sel_idx (B,S) int32 | pos_gt (B,Sp) int32
  *        | num_pos (B) int32          (S = Sp+Sn; Sp is read from pos_gt's shape) */

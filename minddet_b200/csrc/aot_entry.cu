@@ -267,7 +267,7 @@ int MdAssignSample(MD_AOT_ARGS)
     if (rc) return rc;
     return cuda_rc(md::launch_assign_sample_rpn(
         (const float *)params[0], per_image, (const uint8_t *)params[1], B, N, (const float *)params[2],
-        (const uint8_t *)params[3], G, (const float *)params[4], (const int32_t *)params[5], ws, Sp, Sn,
+        (const uint8_t *)params[3], G, (const float *)params[4], (const int32_t *)params[5], (int)numel(ndims[5], shapes[5]), ws, Sp, Sn,
         (int32_t *)params[o], (int32_t *)params[o + 1], (uint8_t *)params[o + 2], (int32_t *)params[o + 3],
         (uint8_t *)params[o + 4], (int32_t *)params[o + 5], (float *)params[o + 6], (int32_t *)params[o + 7],
         (cudaStream_t)stream));
@@ -302,7 +302,7 @@ int MdAssignSampleRcnn(MD_AOT_ARGS)
     if (rc) return rc;
     return cuda_rc(md::launch_assign_sample_rcnn(
         (const float *)params[0], (const uint8_t *)params[1], B, P, (const float *)params[2], (const int32_t *)params[3],
-        (const uint8_t *)params[4], G, (const float *)params[5], (const int32_t *)params[6], ws, Sp, Sn,
+        (const uint8_t *)params[4], G, (const float *)params[5], (const int32_t *)params[6], (int)numel(ndims[6], shapes[6]), ws, Sp, Sn,
         (float *)params[o], (float *)params[o + 1], (int32_t *)params[o + 2], (uint8_t *)params[o + 3],
         (int32_t *)params[o + 4], (int32_t *)params[o + 5], (int32_t *)params[o + 6], (int32_t *)params[o + 7],
         (cudaStream_t)stream));
@@ -500,7 +500,7 @@ int MdYoloDecode(MD_AOT_ARGS)
     REQ(ndims[0] == 3 && shapes[0][1] > 64 && ndims[2] == 3 && shapes[2][0] == shapes[0][0] && shapes[2][1] == shapes[0][2] && shapes[2][2] == 6);
     REQ(numel(ndims[1], shapes[1]) >= 4);
     return cuda_rc(md::launch_yolo_decode((const float *)params[0], (int)shapes[0][0], (int)shapes[0][1], (int)shapes[0][2],
-                                          (const float *)params[1], (float *)params[2], (cudaStream_t)stream));
+                                          (const float *)params[1], (int)numel(ndims[1], shapes[1]), (float *)params[2], (cudaStream_t)stream));
 }
 
 int MdYoloNms(MD_AOT_ARGS)

@@ -253,14 +253,14 @@ MD_DEVINL bool list_is_exact(const SampleLists &L, int seg, int want)
 
 __global__ void __launch_bounds__(256)
 sample_prefilter_kernel(const int32_t *__restrict__ assigned, int N, int Sp, int Sn, uint32_t stream_base,
-                        const int32_t *__restrict__ seed, const float *__restrict__ cfg, const SampleLists L)
+                        const int32_t *__restrict__ seed, int has_step, const float *__restrict__ cfg, const SampleLists L)
 {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     if (__ldg(cfg + 14) != 0.0f) {                       // MD_AS_FORCE_FULL: mark both lists overflowed -> full-scan select
         if (blockIdx.x == 0 && threadIdx.x < 2) L.count[b * 2 + threadIdx.x] = kListCap + 1;
         return;
     }
-    const uint32_t s0 = (uint32_t)__ldg(seed), s1 = (uint32_t)__ldg(seed + 1);
+    const uint32_t s0 = (uint32_t)seed[0], s1 = (uint32_t)seed[1], step = has_step ? (uint32_t)seed[2] : 0u;
     const uint32_t thr_pos = sample_threshold(L.cand_count[b * 2], Sp), thr_neg = sample_threshold(L.cand_count[b * 2 + 1], Sn);
     const int32_t *a = assigned + (int64_t)b * N;
     for (int n0 = blockIdx.x * 256; n0 < N; n0 += gridDim.x * 256) {
@@ -271,7 +271,7 @@ sample_prefilter_kernel(const int32_t *__restrict__ assigned, int N, int Sp, int
             const int32_t v = __ldg(a + n);
             kind = v > 0 ? 0 : (v == 0 ? 1 : -1);
             if (kind >= 0) {
-                r = philox_key((uint32_t)n, stream_base + kind, (uint32_t)b, s0, s1);
+                r = philox_key((uint32_t)n, stream_base + kind, (uint32_t)b, s0, s1, step);
                 if (r > (kind ? thr_neg : thr_pos)) kind = -1;
             }
         }
@@ -308,15 +308,15 @@ struct ListSrc {
 
 // ---- sampling on the cluster radix-select -------------------------------------------------------------
 struct SampleSrc {
-    const int32_t *assigned; int N; int Sp, Sn; uint32_t stream_base; const int32_t *seed; int nimg; SampleLists L;
-    struct Ctx { const int32_t *base; int kind; uint32_t image, seed_lo, seed_hi; bool on; };
+    const int32_t *assigned; int N; int Sp, Sn; uint32_t stream_base; const int32_t *seed; int has_step; int nimg; SampleLists L;
+    struct Ctx { const int32_t *base; int kind; uint32_t image, seed_lo, seed_hi, step; bool on; };
     // negatives (odd segments, ~all anchors are candidates) first, positives after
     __device__ int segment_of(int i, int it) const { return it ? -1 : (i < nimg ? 2 * i + 1 : 2 * (i - nimg)); }
     __device__ Ctx prepare(int seg) const
     {
         const int b = seg >> 1;
-        return Ctx{ assigned + (int64_t)b * N, seg & 1, (uint32_t)b, (uint32_t)__ldg(seed), (uint32_t)__ldg(seed + 1),
-                    !list_is_exact(L, seg, (seg & 1) ? Sn : Sp) };
+        return Ctx{ assigned + (int64_t)b * N, seg & 1, (uint32_t)b, (uint32_t)seed[0], (uint32_t)seed[1],
+                    has_step ? (uint32_t)seed[2] : 0u, !list_is_exact(L, seg, (seg & 1) ? Sn : Sp) };
     }
     __device__ bool active(const Ctx &c) const { return c.on; }      // full scan only for segments the list path declined
     __device__ int length(const Ctx &) const { return N; }
@@ -327,7 +327,7 @@ struct SampleSrc {
         const int32_t a = __ldg(c.base + m);
         const bool cand = c.kind ? (a == 0) : (a > 0);
         if (!cand) return false;
-        key = ~philox_key((uint32_t)m, stream_base + c.kind, c.image, c.seed_lo, c.seed_hi);
+        key = ~philox_key((uint32_t)m, stream_base + c.kind, c.image, c.seed_lo, c.seed_hi, c.step);
         return true;
     }
 };
@@ -354,9 +354,10 @@ __global__ void rpn_finalize_kernel(const AsIn in, int Sp, int Sn, const int32_t
                                     const int32_t *__restrict__ assigned, int32_t *__restrict__ pos_idx,
                                     uint8_t *__restrict__ pos_valid, int32_t *__restrict__ neg_idx,
                                     uint8_t *__restrict__ neg_valid, int32_t *__restrict__ pos_gt,
-                                    float4 *__restrict__ pos_target, int32_t *__restrict__ num_pos_out)
+                                    float4 *__restrict__ pos_target, int32_t *__restrict__ num_pos_out, int32_t *step)
 {
     const int b = blockIdx.x;
+    if (step && b == 0 && threadIdx.x == 0) *step += 1;          // the samplers of this call are done: next call, next draw
     const int P = cand_count[b * 2], Q = cand_count[b * 2 + 1];
     const int num_total = (int)__ldg(in.cfg + 5);
     const int num_pos = min(P, Sp);
@@ -397,8 +398,9 @@ __global__ void rcnn_finalize_kernel(const float *__restrict__ props5, int P_, c
                                      const int32_t *__restrict__ assigned, int32_t *__restrict__ sel_idx,
                                      float *__restrict__ rois5, float4 *__restrict__ deltas,
                                      int32_t *__restrict__ labels, uint8_t *__restrict__ mask,
-                                     int32_t *__restrict__ pos_gt, int32_t *__restrict__ num_pos_out)
+                                     int32_t *__restrict__ pos_gt, int32_t *__restrict__ num_pos_out, int32_t *step)
 {
+    if (step && blockIdx.x == 0 && threadIdx.x == 0) *step += 1;   // the samplers of this call are done: next call, next draw
     const int b = blockIdx.x;
     const int S = Sp + Sn, N = G + P_;
     const int Pc = cand_count[b * 2], Qc = cand_count[b * 2 + 1];
@@ -473,21 +475,21 @@ static cudaError_t run_assign(const AsIn &in, int B, const AssignWs &w, int32_t 
 // list fast path, then the full-scan select for the segments it declined (normally none: both kernels of the
 // second launch return at once)
 static cudaError_t run_samplers(const int32_t *assigned, int B, int N, int Sp, int Sn, uint32_t stream_base,
-                                const int32_t *seed, const float *cfg, const AssignWs &w, const SampleSink &sink, cudaStream_t s)
+                                const int32_t *seed, int has_step, const float *cfg, const AssignWs &w, const SampleSink &sink, cudaStream_t s)
 {
     SampleLists L{ w.items, w.list_count, w.cand };
     int gx = (N + 255) / 256;
     const int cap = (148 * 8 + B - 1) / B;
     if (gx > cap) gx = cap;
-    sample_prefilter_kernel<<<dim3(gx, B), 256, 0, s>>>(assigned, N, Sp, Sn, stream_base, seed, cfg, L);
+    sample_prefilter_kernel<<<dim3(gx, B), 256, 0, s>>>(assigned, N, Sp, Sn, stream_base, seed, has_step, cfg, L);
     cudaError_t e = launch_select_sorted(ListSrc{ L, Sp, Sn, B }, sink, 2 * B, kListCap, s);
     if (e != cudaSuccess) return e;
-    return launch_select_sorted(SampleSrc{ assigned, N, Sp, Sn, stream_base, seed, B, L }, sink, 2 * B, N, s);
+    return launch_select_sorted(SampleSrc{ assigned, N, Sp, Sn, stream_base, seed, has_step, B, L }, sink, 2 * B, N, s);
 }
 
 cudaError_t launch_assign_sample_rpn(const float *boxes, int boxes_per_image, const uint8_t *box_valid,
                                      int B, int N, const float *gts, const uint8_t *gt_valid, int G,
-                                     const float *cfg, const int32_t *seed, void *ws, int Sp, int Sn,
+                                     const float *cfg, const int32_t *seed, int seed_len, void *ws, int Sp, int Sn,
                                      int32_t *assigned, int32_t *pos_idx, uint8_t *pos_valid, int32_t *neg_idx,
                                      uint8_t *neg_valid, int32_t *pos_gt, float *pos_target, int32_t *num_pos,
                                      cudaStream_t s)
@@ -499,16 +501,17 @@ cudaError_t launch_assign_sample_rpn(const float *boxes, int boxes_per_image, co
     cudaError_t e = run_assign(in, B, w, assigned, N, 0, true, s);
     if (e != cudaSuccess) return e;
     SampleSink sink{ pos_idx, neg_idx, Sp, Sn, Sp, Sn, w.cand };
-    e = run_samplers(assigned, B, N, Sp, Sn, 0u, seed, cfg, w, sink, s);
+    e = run_samplers(assigned, B, N, Sp, Sn, 0u, seed, seed_len >= 3, cfg, w, sink, s);
     if (e != cudaSuccess) return e;
     rpn_finalize_kernel<<<B, 256, 0, s>>>(in, Sp, Sn, w.cand, assigned, pos_idx, pos_valid, neg_idx, neg_valid,
-                                          pos_gt, reinterpret_cast<float4 *>(pos_target), num_pos);
+                                          pos_gt, reinterpret_cast<float4 *>(pos_target), num_pos,
+                                          seed_len >= 3 ? const_cast<int32_t *>(seed) + 2 : nullptr);
     return cudaGetLastError();
 }
 
 cudaError_t launch_assign_sample_rcnn(const float *props5, const uint8_t *prop_mask, int B, int P,
                                       const float *gts, const int32_t *gt_labels, const uint8_t *gt_valid, int G,
-                                      const float *cfg, const int32_t *seed, void *ws, int Sp, int Sn,
+                                      const float *cfg, const int32_t *seed, int seed_len, void *ws, int Sp, int Sn,
                                       float *rois5, float *deltas, int32_t *labels, uint8_t *mask,
                                       int32_t *assigned, int32_t *sel_idx, int32_t *pos_gt, int32_t *num_pos,
                                       cudaStream_t s)
@@ -523,10 +526,11 @@ cudaError_t launch_assign_sample_rcnn(const float *props5, const uint8_t *prop_m
     e = run_assign(in, B, w, assigned, N, G, false, s, G > 0);
     if (e != cudaSuccess) return e;
     SampleSink sink{ sel_idx, sel_idx + Sp, Sp, Sn, S, S, w.cand };
-    e = run_samplers(assigned, B, N, Sp, Sn, 2u, seed, cfg, w, sink, s);
+    e = run_samplers(assigned, B, N, Sp, Sn, 2u, seed, seed_len >= 3, cfg, w, sink, s);
     if (e != cudaSuccess) return e;
     rcnn_finalize_kernel<<<B, 256, 0, s>>>(props5, P, gts, gt_labels, G, cfg, Sp, Sn, w.cand, assigned, sel_idx,
-                                           rois5, reinterpret_cast<float4 *>(deltas), labels, mask, pos_gt, num_pos);
+                                           rois5, reinterpret_cast<float4 *>(deltas), labels, mask, pos_gt, num_pos,
+                                           seed_len >= 3 ? const_cast<int32_t *>(seed) + 2 : nullptr);
     return cudaGetLastError();
 }
 

@@ -92,10 +92,10 @@ MD_DEVINL float key_score(uint32_t k)
     return __uint_as_float(b);
 }
 
-// ---- Philox-4x32-10, counter (n, stream, image, 0), key = 64-bit seed; returns word 0 -----------
-MD_DEVINL uint32_t philox_key(uint32_t n, uint32_t stream, uint32_t image, uint32_t seed_lo, uint32_t seed_hi)
+// ---- Philox-4x32-10, counter (n, stream, image, step), key = 64-bit seed; returns word 0 -----------
+MD_DEVINL uint32_t philox_key(uint32_t n, uint32_t stream, uint32_t image, uint32_t seed_lo, uint32_t seed_hi, uint32_t step = 0u)
 {
-    uint32_t c0 = n, c1 = stream, c2 = image, c3 = 0u;
+    uint32_t c0 = n, c1 = stream, c2 = image, c3 = step;
     uint32_t k0 = seed_lo, k1 = seed_hi;
 #pragma unroll
     for (int r = 0; r < 10; r++) {

@@ -39,17 +39,18 @@ struct SideLane { cudaStream_t stream; cudaEvent_t fork, join; };
 cudaError_t launch_proposal(const LevelSet &lv, int B, int nms_pre, int max_num, const float *cfg, void *ws,
                             float *props, uint8_t *pmask, int32_t *topk_idx, uint8_t *keep, cudaStream_t s, const SideLane *side = nullptr);
 
-// a7/a8
+// a7/a8.  seed = {seed_lo, seed_hi[, step]}: with seed_len >= 3 the Philox counter carries seed[2] and the op increments it
+// on the device when its samplers are done (a replayed CUDA graph draws a fresh sample every replay)
 size_t assign_workspace_bytes(int B, int G, int N);   // N = boxes per image
 cudaError_t launch_assign_sample_rpn(const float *boxes, int boxes_per_image, const uint8_t *box_valid,
                                      int B, int N, const float *gts, const uint8_t *gt_valid, int G,
-                                     const float *cfg, const int32_t *seed, void *ws, int Sp, int Sn,
+                                     const float *cfg, const int32_t *seed, int seed_len, void *ws, int Sp, int Sn,
                                      int32_t *assigned, int32_t *pos_idx, uint8_t *pos_valid, int32_t *neg_idx,
                                      uint8_t *neg_valid, int32_t *pos_gt, float *pos_target, int32_t *num_pos,
                                      cudaStream_t s);
 cudaError_t launch_assign_sample_rcnn(const float *props5, const uint8_t *prop_mask, int B, int P,
                                       const float *gts, const int32_t *gt_labels, const uint8_t *gt_valid, int G,
-                                      const float *cfg, const int32_t *seed, void *ws, int Sp, int Sn,
+                                      const float *cfg, const int32_t *seed, int seed_len, void *ws, int Sp, int Sn,
                                       float *rois5, float *deltas, int32_t *labels, uint8_t *mask,
                                       int32_t *assigned, int32_t *sel_idx, int32_t *pos_gt, int32_t *num_pos,
                                       cudaStream_t s);
@@ -62,7 +63,7 @@ cudaError_t launch_bev_nms(const float *boxes, int n, const float *thr, int mode
                            int32_t *num_out, cudaStream_t s);
 
 // "next" row 1: YOLOv8 post-process (yolo.cu); reg_max = 16
-cudaError_t launch_yolo_decode(const float *pred, int B, int C, int A, const float *cfg, float *dets, cudaStream_t s);
+cudaError_t launch_yolo_decode(const float *pred, int B, int C, int A, const float *cfg, int cfg_len, float *dets, cudaStream_t s);
 size_t yolo_nms_workspace_bytes(int B, int nms_pre);
 cudaError_t launch_yolo_nms(const float *dets, int B, int A, const float *cfg, void *ws, int nms_pre, int max_det,
                             float *out, int32_t *keep_idx, int32_t *num_out, int32_t *cand_idx, cudaStream_t s);

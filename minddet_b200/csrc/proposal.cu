@@ -662,11 +662,9 @@ cudaError_t run_nms(const NmsSegs &sg, int nseg, int Kmax, const float *cfg, uns
         else nms_mask_kernel<false><<<grid, 64, 0, s>>>(sg, cfg, mask);
     }
     const size_t sweep_smem = kSweepSmem;
-    static bool sweep_configured = false;
-    if (!sweep_configured) {
+    {   // the attribute is per DEVICE and the value is a constant: set it on every launch (no process-wide "done" flag)
         cudaError_t e = cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem);
         if (e != cudaSuccess) return e;
-        sweep_configured = true;
     }
     nms_sweep_kernel<<<nseg, kSweepThreads, sweep_smem, s>>>(sg, mask, nullptr, keep_pos, keep_stride, keep_mask, mask_stride, count);
     return cudaGetLastError();
@@ -906,11 +904,9 @@ cudaError_t launch_proposal(const LevelSet &lv, int B, int nms_pre, int max_num,
     }
     if (e != cudaSuccess) return e;
     const size_t smem = (size_t)L * nms_pre * sizeof(uint32_t);
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
+    if (smem > 48 * 1024) {      // per device, constant value: set on every launch that needs it
         e = cudaFuncSetAttribute(merge_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     merge_levels_kernel<<<dim3(B, kMergeSplit), kMergeThreads, smem, s>>>(
         L, nms_pre, max_num, w.boxes, w.kept_keys, w.keep_pos, w.count, w.scores, keep, sg, props, pmask);

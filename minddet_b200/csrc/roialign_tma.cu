@@ -731,12 +731,10 @@ template <int P>
 static cudaError_t launch_fwd(const TmaMaps &maps, const RoiFeat &f, int mask, const float *rois5, int R, float *out,
                               int32_t *flag, cudaStream_t s)
 {
-    static bool configured = false;
     auto kern = roialign_fwd_stream_kernel<P>;
-    if (!configured) {
+    {   // per device, constant value: set on every launch
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<P>());
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     const int nchunk = chunks_for(f.C);
     kern<<<R * nchunk, kStThreads, fwd_smem<P>(), s>>>(maps, f, mask, rois5, R, kSegRois, nchunk, out, flag);
@@ -760,12 +758,10 @@ template <int P>
 static cudaError_t launch_bwd(const TmaMaps &maps, const RoiFeat &f, int mask, const float *rois5, int R, const float *dout,
                               int32_t *flag, cudaStream_t s)
 {
-    static bool configured = false;
     auto kern = roialign_bwd_stream_kernel<P>;
-    if (!configured) {
+    {   // per device, constant value: set on every launch
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<P>());
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     const int nchunk = chunks_for(f.C);
     kern<<<R * nchunk, kStThreads, bwd_smem<P>(), s>>>(maps, f, mask, rois5, R, kSegRois, nchunk, dout, flag);

@@ -624,15 +624,16 @@ cudaError_t launch_select_sorted(const Src &src, const Sink &sink, int nclusters
     int cache = per <= kSelMaxCacheElems ? per : 0;   // 0 -> recompute keys every pass
     cache = (cache + 31) & ~31;
     const size_t dyn = sizeof(SelShared) + (size_t)(cache + cache / 32 + 8) * sizeof(uint32_t);
-    static size_t configured = 0;   // per instantiation
-    if (dyn > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    {
+        // The attribute is per DEVICE, so a process-wide "already configured" flag is wrong on a second GPU and racy between
+        // host threads.  Always allow the largest slice this kernel can ask for: a constant, identical from every caller.
+        constexpr size_t kMaxDyn = sizeof(SelShared) + (size_t)(kSelMaxCacheElems + 32 + kSelMaxCacheElems / 32 + 8) * sizeof(uint32_t);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dyn > kMaxDyn ? dyn : kMaxDyn));
         if (e != cudaSuccess) return e;
         if (kClusterSize > 8) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             if (e != cudaSuccess) return e;
         }
-        configured = dyn;
     }
     kern<<<dim3(nseg * kClusterSize), dim3(kSelThreads), dyn, stream>>>(src, sink, cache);
     return cudaGetLastError();

@@ -23,10 +23,11 @@ constexpr int kYoloMaxLevels = 8;
 
 struct YoloLevels { int n, start[kYoloMaxLevels + 1], W[kYoloMaxLevels]; float stride[kYoloMaxLevels]; };
 
-MD_DEVINL YoloLevels load_levels(const float *__restrict__ cfg)
+// cfg_len = floats the caller's cfg tensor really holds: the level count read from cfg[0] is clamped to what fits
+MD_DEVINL YoloLevels load_levels(const float *__restrict__ cfg, int cfg_len)
 {
     YoloLevels lv;
-    lv.n = min((int)__ldg(cfg), kYoloMaxLevels);
+    lv.n = max(0, min(min((int)__ldg(cfg), kYoloMaxLevels), (cfg_len - 1) / 3));
     int s = 0;
     for (int l = 0; l < lv.n; l++) {
         const int H = (int)__ldg(cfg + 1 + 3 * l);
@@ -57,11 +58,11 @@ MD_DEVINL float dfl_expectation(const float (&x)[kRegMax])
 
 template <int V>   // anchors per thread: 4 (128-bit path) or 1
 __global__ void __launch_bounds__(kYoloThreads)
-yolo_decode_kernel(const float *__restrict__ pred, int B, int A, int nc, int tiles_per_image, const float *__restrict__ cfg,
+yolo_decode_kernel(const float *__restrict__ pred, int B, int A, int nc, int tiles_per_image, const float *__restrict__ cfg, int cfg_len,
                    float *__restrict__ dets)
 {
     __shared__ YoloLevels lv;                 // dynamic level lookup per anchor: keep it out of local memory
-    if (threadIdx.x == 0) lv = load_levels(cfg);
+    if (threadIdx.x == 0) lv = load_levels(cfg, cfg_len);
     __syncthreads();
     // persistent: the grid is one full wave (148 x resident CTAs); tiles = (image, 128*V anchors) are strided
     for (int tile = blockIdx.x; tile < tiles_per_image * B; tile += gridDim.x) {
@@ -144,7 +145,7 @@ yolo_decode_kernel(const float *__restrict__ pred, int B, int A, int nc, int til
     }
 }
 
-cudaError_t launch_yolo_decode(const float *pred, int B, int C, int A, const float *cfg, float *dets, cudaStream_t s)
+cudaError_t launch_yolo_decode(const float *pred, int B, int C, int A, const float *cfg, int cfg_len, float *dets, cudaStream_t s)
 {
     const int nc = C - 4 * kRegMax;
     if (nc < 1) return cudaErrorInvalidValue;
@@ -164,7 +165,7 @@ cudaError_t launch_yolo_decode(const float *pred, int B, int C, int A, const flo
     const int tiles_per_image = (A + per - 1) / per;
     const long long tiles = (long long)tiles_per_image * B;
     const int grid = (int)(tiles < 148LL * resident[V] ? tiles : 148LL * resident[V]);
-    kern<<<grid, kYoloThreads, 0, s>>>(pred, B, A, nc, tiles_per_image, cfg, dets);
+    kern<<<grid, kYoloThreads, 0, s>>>(pred, B, A, nc, tiles_per_image, cfg, cfg_len, dets);
     return cudaGetLastError();
 }
 

@@ -172,6 +172,16 @@ class Proposal(_Cell):
         return props, mask
 
 
+def _seed_values(seed, advance):
+    """int32 seed tensor of the samplers: {seed_lo, seed_hi[, step]}.  With ``advance`` (default) the tensor has the third
+    word: the op uses it as the per-call Philox counter and increments it ON THE DEVICE after every call, so consecutive
+    calls -- and consecutive replays of a captured CUDA graph -- draw fresh samples, like the reference's per-call
+    ``npr.choice`` (pointpillars/src/core/target_assigner.py:116-128).  ``advance=False`` freezes the draw (tests)."""
+    s = int(seed) & 0xFFFFFFFFFFFFFFFF
+    v = [np.int32(np.uint32(s & 0xFFFFFFFF)).item(), np.int32(np.uint32(s >> 32)).item()]
+    return v + [0] if advance else v
+
+
 class BboxAssignSample(_Cell):
     """a7/a8, RPN flavour.  ``construct(gt_bboxes, gt_valids, bboxes, valid_mask)``.
 
@@ -180,15 +190,18 @@ class BboxAssignSample(_Cell):
 
     def __init__(self, pos_iou_thr=0.7, neg_iou_thr=0.3, min_pos_iou=0.3, num_expected_pos=128,
                  num_expected_neg=256, num_expected_total=256, means=(0.0, 0.0, 0.0, 0.0), stds=(1.0, 1.0, 1.0, 1.0),
-                 seed=0, iou_offset=1.0, mode=0, force_full_scan=False):
+                 seed=0, iou_offset=1.0, mode=0, force_full_scan=False, advance=True):
         self.Sp, self.Sn = num_expected_pos, num_expected_neg
         self.cfg_values = [float(pos_iou_thr), float(neg_iou_thr), float(min_pos_iou), float(iou_offset), float(mode),
                            float(num_expected_total)] + [float(m) for m in means] + [float(s) for s in stds] + [
                                1.0 if force_full_scan else 0.0, 0.0]
-        s = int(seed) & 0xFFFFFFFFFFFFFFFF
-        self.seed_values = [np.int32(np.uint32(s & 0xFFFFFFFF)).item(), np.int32(np.uint32(s >> 32)).item()]
+        self.seed_values = _seed_values(seed, advance)
         self._op = Custom(_so("MdAssignSample"), None,
                           (torch.int32, torch.int32, torch.bool, torch.int32, torch.bool, torch.int32, torch.float32, torch.int32))
+
+    def seed_tensor(self, device):
+        """the persistent device tensor {seed_lo, seed_hi[, step]}; ``seed_tensor(dev)[2]`` is the step the NEXT call uses"""
+        return self._cfg(self.seed_values, device, torch.int32)
 
     def construct(self, gt_bboxes, gt_valids, bboxes, valid_mask):
         B, G = gt_bboxes.shape[:2]
@@ -208,15 +221,18 @@ class BboxAssignSampleForRcnn(_Cell):
 
     def __init__(self, pos_iou_thr=0.5, neg_iou_thr=0.5, min_pos_iou=0.5, num_expected_pos=128,
                  num_expected_neg=384, num_expected_total=512, means=(0.0, 0.0, 0.0, 0.0), stds=(0.1, 0.1, 0.2, 0.2),
-                 seed=0, iou_offset=1.0, mode=0, force_full_scan=False):
+                 seed=0, iou_offset=1.0, mode=0, force_full_scan=False, advance=True):
         self.Sp, self.Sn = num_expected_pos, num_expected_neg
         self.cfg_values = [float(pos_iou_thr), float(neg_iou_thr), float(min_pos_iou), float(iou_offset), float(mode),
                            float(num_expected_total)] + [float(m) for m in means] + [float(s) for s in stds] + [
                                1.0 if force_full_scan else 0.0, 0.0]
-        s = int(seed) & 0xFFFFFFFFFFFFFFFF
-        self.seed_values = [np.int32(np.uint32(s & 0xFFFFFFFF)).item(), np.int32(np.uint32(s >> 32)).item()]
+        self.seed_values = _seed_values(seed, advance)
         self._op = Custom(_so("MdAssignSampleRcnn"), None,
                           (torch.float32, torch.float32, torch.int32, torch.bool, torch.int32, torch.int32, torch.int32, torch.int32))
+
+    def seed_tensor(self, device):
+        """the persistent device tensor {seed_lo, seed_hi[, step]}; ``seed_tensor(dev)[2]`` is the step the NEXT call uses"""
+        return self._cfg(self.seed_values, device, torch.int32)
 
     def construct(self, gt_bboxes, gt_labels, proposal_mask, proposals, gt_valids):
         B, G = gt_bboxes.shape[:2]

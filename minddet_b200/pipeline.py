@@ -17,14 +17,14 @@ KERNELS_PER_STEP = 23   # 2 lanes x (select, nms_mask, nms_sweep), merge | gtmax
 class RegionPath:
     def __init__(self, img_shape=(synth.IMG_H, synth.IMG_W), strides=synth.STRIDES, roi_levels=4,
                  nms_pre=2000, max_num=2000, nms_thr=0.7, roi_pos=128, roi_neg=384, roi_total=512,
-                 out_size=7, sample_num=2, seed=0, device="cuda"):
+                 out_size=7, sample_num=2, seed=0, device="cuda", advance=True):
         self.img_shape, self.strides, self.device = img_shape, tuple(strides), device
         self.shapes = synth.level_shapes(img_shape[0], img_shape[1], strides)
         self.bases = synth.base_anchor_sets(strides)
         self.generators = [AnchorGenerator(s, [8], [0.5, 1.0, 2.0]) for s in strides]
         self.proposal = Proposal(img_shape, strides, self.bases, nms_pre=nms_pre, max_num=max_num, nms_thr=nms_thr)
-        self.rpn_targets = BboxAssignSample(0.7, 0.3, 0.3, 128, 256, 256, seed=seed)
-        self.rcnn_targets = BboxAssignSampleForRcnn(0.5, 0.5, 0.5, roi_pos, roi_neg, roi_total, seed=seed)
+        self.rpn_targets = BboxAssignSample(0.7, 0.3, 0.3, 128, 256, 256, seed=seed, advance=advance)
+        self.rcnn_targets = BboxAssignSampleForRcnn(0.5, 0.5, 0.5, roi_pos, roi_neg, roi_total, seed=seed, advance=advance)
         self.extractor = SingleRoIExtractor(out_size, sample_num, strides[:roi_levels], 56)
         self.roi_levels = roi_levels
         self._anchors = None

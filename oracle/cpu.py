@@ -39,6 +39,7 @@ def lib():
         _lib.o_philox_key.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]
         _lib.o_nms.restype = C.c_int
         _lib.o_sample.restype = C.c_int64
+        _lib.o_sample_step.restype = C.c_int64
         _lib.o_proposal_image.restype = C.c_int
         _lib.o_assign_sample_rpn.restype = C.c_int
         _lib.o_assign_sample_rcnn.restype = C.c_int
@@ -64,7 +65,7 @@ class AssignCfg(C.Structure):
     _fields_ = [("pos_thr", C.c_float), ("neg_thr", C.c_float), ("min_pos_iou", C.c_float),
                 ("iou_off", C.c_float), ("mode", C.c_int), ("pos_slots", C.c_int),
                 ("neg_slots", C.c_int), ("num_total", C.c_int), ("means", C.c_float * 4),
-                ("stds", C.c_float * 4), ("seed", C.c_uint64)]
+                ("stds", C.c_float * 4), ("seed", C.c_uint64), ("step", C.c_uint32), ("pad_", C.c_uint32)]
 
 
 class RegionCfg(C.Structure):
@@ -86,10 +87,10 @@ def proposal_cfg(img_h, img_w, nms_pre=2000, max_num=2000, nms_thr=0.7, means=(0
 
 
 def assign_cfg(pos_thr, neg_thr, min_pos_iou, pos_slots, neg_slots, num_total, means=(0, 0, 0, 0),
-               stds=(1, 1, 1, 1), seed=0, iou_off=1.0, mode=0):
+               stds=(1, 1, 1, 1), seed=0, iou_off=1.0, mode=0, step=0):
     c = AssignCfg()
     c.pos_thr, c.neg_thr, c.min_pos_iou, c.iou_off, c.mode = pos_thr, neg_thr, min_pos_iou, iou_off, mode
-    c.pos_slots, c.neg_slots, c.num_total, c.seed = pos_slots, neg_slots, num_total, seed
+    c.pos_slots, c.neg_slots, c.num_total, c.seed, c.step = pos_slots, neg_slots, num_total, seed, step
     c.means[:] = list(means)
     c.stds[:] = list(stds)
     return c
@@ -227,11 +228,11 @@ def assign(boxes, gts, pos_thr, neg_thr, min_pos_iou, valid=None, gt_valid=None,
     return a, m, am
 
 
-def sample(assigned, want_positive, stream, image, seed, k_slots):
+def sample(assigned, want_positive, stream, image, seed, k_slots, step=0):
     assigned = np.ascontiguousarray(assigned, np.int32)
     out = np.empty(k_slots, np.int32)
-    c = lib().o_sample(_p(assigned, i32p), C.c_int64(assigned.size), int(want_positive), C.c_uint32(stream),
-                       C.c_uint32(image), C.c_uint64(seed), k_slots, _p(out, i32p))
+    c = lib().o_sample_step(_p(assigned, i32p), C.c_int64(assigned.size), int(want_positive), C.c_uint32(stream),
+                            C.c_uint32(image), C.c_uint64(seed), C.c_uint32(step), k_slots, _p(out, i32p))
     return out, int(c)
 
 

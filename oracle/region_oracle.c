@@ -92,15 +92,19 @@ static inline void philox_round(uint32_t c[4], uint32_t k0, uint32_t k1)
     uint32_t n3 = (uint32_t)p0;
     c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
 }
-O_API uint32_t o_philox_key(uint32_t n, uint32_t stream, uint32_t image, uint64_t seed)
+O_API uint32_t o_philox_key_step(uint32_t n, uint32_t stream, uint32_t image, uint32_t step, uint64_t seed)
 {
-    uint32_t c[4] = { n, stream, image, 0u };
+    uint32_t c[4] = { n, stream, image, step };                 /* CONVENTIONS #24 */
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     for (int r = 0; r < 10; r++) {
         philox_round(c, k0, k1);
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     return c[0];
+}
+O_API uint32_t o_philox_key(uint32_t n, uint32_t stream, uint32_t image, uint64_t seed)
+{
+    return o_philox_key_step(n, stream, image, 0u, seed);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -475,15 +479,15 @@ O_API void o_assign(const float *boxes, const uint8_t *valid, int64_t N, const f
 }
 
 /* sampling (CONVENTIONS #13): the k candidates with smallest (rkey, n), ascending. returns #cands */
-O_API int64_t o_sample(const int32_t *assigned, int64_t N, int want_positive, uint32_t stream,
-                       uint32_t image, uint64_t seed, int k_slots, int32_t *out_idx)
+O_API int64_t o_sample_step(const int32_t *assigned, int64_t N, int want_positive, uint32_t stream,
+                            uint32_t image, uint64_t seed, uint32_t step, int k_slots, int32_t *out_idx)
 {
     uint64_t *v = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(N > 0 ? N : 1));
     int64_t c = 0;
     for (int64_t n = 0; n < N; n++) {
         int is = want_positive ? (assigned[n] > 0) : (assigned[n] == 0);
         if (!is) continue;
-        uint32_t rk = o_philox_key((uint32_t)n, stream, image, seed);
+        uint32_t rk = o_philox_key_step((uint32_t)n, stream, image, step, seed);
         /* select_largest picks the largest: invert so that smallest (rkey,n) is largest */
         v[c++] = ~(((uint64_t)rk << 32) | (uint64_t)(uint32_t)n);
     }
@@ -495,12 +499,20 @@ O_API int64_t o_sample(const int32_t *assigned, int64_t N, int want_positive, ui
     return c;
 }
 
+O_API int64_t o_sample(const int32_t *assigned, int64_t N, int want_positive, uint32_t stream,
+                       uint32_t image, uint64_t seed, int k_slots, int32_t *out_idx)
+{
+    return o_sample_step(assigned, N, want_positive, stream, image, seed, 0u, k_slots, out_idx);
+}
+
 typedef struct {
     float pos_thr, neg_thr, min_pos_iou, iou_off;
     int mode;
     int pos_slots, neg_slots, num_total;
     float means[4], stds[4];
     uint64_t seed;
+    uint32_t step;      /* CONVENTIONS #24: per-call counter, 4th Philox counter word */
+    uint32_t pad_;
 } OAssignCfg;
 
 /*
@@ -516,8 +528,8 @@ O_API int o_assign_sample_rpn(const float *anchors, const uint8_t *valid, int64_
 {
     o_assign(anchors, valid, N, gts, gt_valid, G, cfg->pos_thr, cfg->neg_thr, cfg->min_pos_iou,
              cfg->iou_off, cfg->mode, assigned, NULL, NULL);
-    int64_t P = o_sample(assigned, N, 1, 0u, image, cfg->seed, cfg->pos_slots, pos_idx);
-    int64_t Q = o_sample(assigned, N, 0, 1u, image, cfg->seed, cfg->neg_slots, neg_idx);
+    int64_t P = o_sample_step(assigned, N, 1, 0u, image, cfg->seed, cfg->step, cfg->pos_slots, pos_idx);
+    int64_t Q = o_sample_step(assigned, N, 0, 1u, image, cfg->seed, cfg->step, cfg->neg_slots, neg_idx);
     int num_pos = (int)(P < cfg->pos_slots ? P : cfg->pos_slots);
     int64_t nneg = cfg->num_total - num_pos;
     if (nneg > Q) nneg = Q;
@@ -556,8 +568,8 @@ O_API int o_assign_sample_rcnn(const float *props, const uint8_t *prop_valid, in
     o_assign(props, prop_valid, P_, gts, gt_valid, G, cfg->pos_thr, cfg->neg_thr, cfg->min_pos_iou,
              cfg->iou_off, cfg->mode, assigned + G, NULL, NULL);
     int S = cfg->pos_slots + cfg->neg_slots;
-    int64_t Pc = o_sample(assigned, N, 1, 2u, image, cfg->seed, cfg->pos_slots, sel_idx);
-    int64_t Qc = o_sample(assigned, N, 0, 3u, image, cfg->seed, cfg->neg_slots, sel_idx + cfg->pos_slots);
+    int64_t Pc = o_sample_step(assigned, N, 1, 2u, image, cfg->seed, cfg->step, cfg->pos_slots, sel_idx);
+    int64_t Qc = o_sample_step(assigned, N, 0, 3u, image, cfg->seed, cfg->step, cfg->neg_slots, sel_idx + cfg->pos_slots);
     int num_pos = (int)(Pc < cfg->pos_slots ? Pc : cfg->pos_slots);
     int64_t nneg = cfg->num_total - num_pos;
     if (nneg > Qc) nneg = Qc;
