@@ -1,16 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- img/s of the Faster R-CNN region path (BASELINE.json metric) on N B200s.
 
-One "step" = one pass of the whole hot path (Proposal -> RPN targets -> RCNN targets -> RoIAlign fwd
--> RoIAlign bwd) over one batch of 8 synthetic 800x1344 images per GPU (config 2 of BASELINE.json;
-images are sharded across GPUs, weak scaling, plus one NCCL all-gather of the top-100 proposals per
-image when N > 1).
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|4|5]     own arm  (CUDA, through the aot C-ABI)
+  python bench.py --impl reference [...]                                   CPU arm  (oracle port, every host core busy)
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]          own arm  (CUDA, through the aot C-ABI)
-  python bench.py --impl reference [...]                        CPU arm  (oracle port of the path, all host cores)
+--config 2 (default) = BASELINE.json configs[1]: one "step" = Proposal -> RPN targets -> RCNN targets -> RoIAlign fwd ->
+  RoIAlign bwd over 8 synthetic 800x1344 images per GPU (images sharded across GPUs, weak scaling; with N > 1 one NCCL
+  all-gather of the top-100 proposals per image).  --global-batch 64 makes it configs[2] literally (64/N images per GPU,
+  strong scaling); the default multi-GPU line also carries that measurement as `global64`.
+--config 4 = configs[3] (Mask R-CNN): the same step + 14x14 mask RoIAlign fwd/bwd on the <=128 positive RoIs per image
+  and the 28x28 mask-target crop.
+--config 5 = configs[4]: YOLOv8 640x640 batch 64 post-process (DFL decode of 8400 anchors + class-aware NMS).
 
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` includes pinned-host ->
-device copies of every input and a device -> host read of the step's compact results every step.
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (CUDA events, max over ranks); `e2e` includes the
+pinned-host -> device copy of every input and a device -> host read of a token sample of the results every step.
+After the timed region every rank compares what it just computed with the CPU oracle on its own inputs
+(`parity_checked`); a mismatch is a non-zero exit.
 """
 import argparse
 import json
@@ -28,11 +33,16 @@ if ROOT not in sys.path:
 
 METRIC = "Faster R-CNN RPN+RoI region path throughput"
 UNIT = "img/s"
-BATCH = 8
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the stream kernels (ncu --set full, profiles/r1_roialign_ncu.md)
-NCU_TRAFFIC = {"roialign_fwd": 849e6, "roialign_bwd": 1260e6}     # fwd r1 v7: 656.7+192.2 MB (profiles/r1_roialign_fwd_ncu_v7.txt); bwd r1 v6: 791.4+469.1 MB (profiles/r1_roialign_ncu_v6.txt)
-WORKLOAD = ("configs[1]: Faster R-CNN R50-FPN region path, batch 8/GPU, 800x1344, 5 levels (268569 anchors), "
-            "2000 pre-NMS/level, NMS 0.7, max_num 2000, G<=128 gts, 512 sampled RoIs, 256-ch 7x7 RoIAlign fwd+bwd")
+BATCH = 8            # images per GPU (weak scaling); --global-batch overrides it
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels (ncu --set full, profiles/README.md)
+NCU_TRAFFIC = {"roialign_fwd": 849e6, "roialign_bwd": 1260e6, "yolo_decode": None}
+WORKLOADS = {
+    2: ("configs[1]: Faster R-CNN R50-FPN region path, batch 8/GPU, 800x1344, 5 levels (268569 anchors), "
+        "2000 pre-NMS/level, NMS 0.7, max_num 2000, G<=128 gts, 512 sampled RoIs, 256-ch 7x7 RoIAlign fwd+bwd"),
+    4: ("configs[3]: Mask R-CNN R50-FPN region path = configs[1] + 14x14 mask RoIAlign fwd+bwd on the <=128 positive "
+        "RoIs per image + 28x28 mask-target crop, batch 8/GPU"),
+    5: "configs[4]: YOLOv8 640x640 batch 64/GPU post-process: DFL decode of 8400 anchors x 80 classes + class-aware NMS",
+}
 
 
 def peaks():
@@ -40,6 +50,14 @@ def peaks():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def config_dict(args, world, batch):
+    """identical for both arms (the driver compares them)"""
+    return {"workload": WORKLOADS[args.config], "global_batch": world * batch, "images_per_gpu": batch,
+            "parallelism": f"image-sharded dp{world}", "scaling": "strong" if args.global_batch else "weak",
+            "l2": "inputs larger than L2 (731 MB of features per step vs 126 MB L2)" if args.config != 5
+                  else "two 310 MB prediction tensors used alternately (> 126 MB L2)"}
 
 
 class ClockSampler(threading.Thread):
@@ -56,7 +74,6 @@ class ClockSampler(threading.Thread):
         try:
             import pynvml
             pynvml.nvmlInit()
-            # CUDA_VISIBLE_DEVICES may remap indices: resolve through the PCI address of the CUDA device when torch exposes it
             import torch
             pr = torch.cuda.get_device_properties(index)
             try:
@@ -101,6 +118,42 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+ORIG_AFFINITY = None
+
+
+def restore_affinity():
+    if ORIG_AFFINITY is not None:
+        try:
+            os.sched_setaffinity(0, ORIG_AFFINITY)
+        except Exception:
+            pass
+
+
+def bind_to_gpu_numa_node(local):
+    """e2e is an H2D stream of ~1 GB per step per rank: bind the process (and so the first-touch pages of its pinned staging
+    buffers) to the CPUs of the GPU's NUMA node before anything is allocated.  Returns a description for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": None, "bound": False, "why": "the platform reports no NUMA node for the GPU"}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return {"numa_node": node, "bound": False, "why": "no allowed CPU on that node"}
+        global ORIG_AFFINITY
+        ORIG_AFFINITY = os.sched_getaffinity(0)
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "bound": True, "cpus": len(allowed)}
+    except Exception as e:                                       # never fatal: it is a placement hint
+        return {"numa_node": None, "bound": False, "why": type(e).__name__}
+
+
 # ------------------------------------------------------------------------------------------------
 def footprint_bytes(rois, levels_hw, strides, C, P=7, S=2, finest=56.0):
     """Exact union-of-footprints (bytes) the RoIAlign of `rois` must read / the backward must update:
@@ -132,51 +185,264 @@ def footprint_bytes(rois, levels_hw, strides, C, P=7, S=2, finest=56.0):
     return total
 
 
+def region_cfg(O, rpn_step=0, rcnn_step=0):
+    c = O.RegionCfg()
+    c.prop = O.proposal_cfg(800, 1344, nms_pre=2000, max_num=2000)
+    c.rpn = O.assign_cfg(0.7, 0.3, 0.3, 128, 256, 256, seed=0, step=rpn_step)
+    c.rcnn = O.assign_cfg(0.5, 0.5, 0.5, 128, 384, 512, stds=(0.1, 0.1, 0.2, 0.2), seed=0, step=rcnn_step)
+    c.finest_scale, c.roi_P, c.roi_S, c.roi_end_mode, c.num_roi_levels, c.do_backward = 56.0, 7, 2, 0.0, 4, 1
+    return c
+
+
+def oracle_region_path(O, host, cfg, nthreads):
+    from minddet_b200 import synth
+    return O.region_path_batch([x.numpy() for x in host["cls_scores"]], [x.numpy() for x in host["bbox_preds"]],
+                               synth.base_anchor_sets(), synth.STRIDES, [x.numpy() for x in host["feats"]], host["gts"].numpy(),
+                               host["gt_labels"].numpy(), host["gt_valid"].numpy().astype(np.uint8), cfg,
+                               dout=host["dout"].numpy(), nthreads=nthreads)
+
+
+def cpu_region_throughput(min_seconds, max_reps=64):
+    """The oracle port of the whole path on EVERY host core: cores // 8 concurrent passes over the same 8 images, each pass
+    image-parallel on 8 pthreads (ctypes releases the GIL).  Returns (img/s, cores, threads_busy, description)."""
+    import oracle as O
+    from minddet_b200 import pipeline
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    nimg = 8
+    inp = pipeline.make_inputs(nimg, seed=0xD37)
+    cfg = region_cfg(O)
+    ncalls = max(1, cores // nimg)
+    per_call = max(1, min(nimg, cores // ncalls))
+    oracle_region_path(O, inp, cfg, per_call)                    # warm-up (page faults, thread start)
+    done, lock, t0 = [0], threading.Lock(), time.perf_counter()
+
+    def worker():
+        while True:
+            oracle_region_path(O, inp, cfg, per_call)
+            with lock:
+                done[0] += 1
+                if time.perf_counter() - t0 >= min_seconds or done[0] >= max_reps:
+                    return
+
+    th = [threading.Thread(target=worker) for _ in range(ncalls)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    busy = ncalls * per_call
+    return (done[0] * nimg / dt, cores, busy,
+            f"{done[0]} passes over {nimg} images of the same workload in {dt:.1f} s: {ncalls} concurrent passes x {per_call} pthreads "
+            f"(one image per thread) = {busy} of {cores} host cores busy; oracle/region_oracle.c port -- the reference has no "
+            f"code for this path and MindSpore is absent")
+
+
+def cpu_yolo_throughput(min_seconds):
+    import oracle as O
+    from concurrent.futures import ThreadPoolExecutor
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    shapes, strides = [(80, 80), (40, 40), (20, 20)], (8, 16, 32)
+    A = sum(h * w for h, w in shapes)
+    rng = np.random.default_rng(0)
+    preds = rng.normal(0, 1, (cores, 144, A)).astype(np.float32)
+    preds[:, 64:] -= 5.0
+
+    def one(i):
+        d = O.yolo_decode(preds[i], shapes, strides)
+        O.yolo_nms(d, 0.25, 2048, 0.7, False, 300)
+
+    one(0)
+    reps, t0 = 0, time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        while time.perf_counter() - t0 < min_seconds:
+            list(ex.map(one, range(cores)))
+            reps += 1
+    dt = time.perf_counter() - t0
+    return (reps * cores / dt, cores, cores,
+            f"{reps} passes over {cores} images ({dt:.1f} s), one image per thread on {cores} host threads; oracle port of decode + NMS")
+
+
 def run_reference(args):
-    """CPU arm: the oracle port of the whole path (oracle/region_oracle.c), image-parallel over all
-    host cores, on a bounded sample of the same workload."""
+    """CPU arm: the oracle port of the path, all host cores busy, on a bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle as O
-    from minddet_b200 import pipeline, synth
-    cores = os.cpu_count() or 1
-    nimg = max(1, min(BATCH, cores))
-    inp = pipeline.make_inputs(nimg, seed=0xD37)
-    cfg = region_cfg(O)
-    shapes = synth.level_shapes()
-    bases = synth.base_anchor_sets()
-
-    def one():
-        t0 = time.perf_counter()
-        O.region_path_batch([x.numpy() for x in inp["cls_scores"]], [x.numpy() for x in inp["bbox_preds"]], bases,
-                            synth.STRIDES, [x.numpy() for x in inp["feats"]], inp["gts"].numpy(), inp["gt_labels"].numpy(),
-                            inp["gt_valid"].numpy().astype(np.uint8), cfg, dout=inp["dout"].numpy(), nthreads=cores)
-        return time.perf_counter() - t0
-
-    for _ in range(min(args.warmup, 2)):
-        one()
-    steps = max(1, min(args.steps, 20))
-    dt = sum(one() for _ in range(steps)) / steps
-    val = nimg / dt
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"{nimg} images per step"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{nimg} images of the same workload per step, {cores} pthreads (one image per task); "
-                                       "oracle/region_oracle.c port -- the reference has no code for this path and MindSpore is absent"},
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    batch = (args.global_batch // world) if args.global_batch else (64 if args.config == 5 else BATCH)
+    steps, warm = max(1, min(args.steps, 20)), min(args.warmup, 2)
+    budget = float(np.clip(1.0 * steps, 10.0, 30.0))
+    if args.config == 5:
+        val, cores, busy, sample = cpu_yolo_throughput(budget)
+    else:
+        val, cores, busy, sample = cpu_region_throughput(budget)
+        if args.config == 4:
+            sample += " (the mask branch is not in the CPU pass: this over-states the CPU arm)"
+    line = {"impl": "reference", "metric": METRIC if args.config != 5 else "YOLOv8 post-process throughput", "value": val, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": batch / val * 1e3, "higher_is_better": True,
+            "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, world, batch),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "threads_busy": busy, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def region_cfg(O):
-    c = O.RegionCfg()
-    c.prop = O.proposal_cfg(800, 1344, nms_pre=2000, max_num=2000)
-    c.rpn = O.assign_cfg(0.7, 0.3, 0.3, 128, 256, 256, seed=0)
-    c.rcnn = O.assign_cfg(0.5, 0.5, 0.5, 128, 384, 512, stds=(0.1, 0.1, 0.2, 0.2), seed=0)
-    c.finest_scale, c.roi_P, c.roi_S, c.roi_end_mode, c.num_roi_levels, c.do_backward = 56.0, 7, 2, 0.0, 4, 1
-    return c
+# ------------------------------------------------------------------------------------------------
+def count_graph_kernels(graph):
+    """kernel nodes of a captured torch CUDA graph (our launches per replay), or None when the build cannot tell"""
+    try:
+        from cuda.bindings import runtime as rt
+    except Exception:
+        try:
+            from cuda import cudart as rt
+        except Exception:
+            return None
+    try:
+        raw = graph.raw_cuda_graph()
+        g = rt.cudaGraph_t(int(raw))
+        err, _, n = rt.cudaGraphGetNodes(g, 0)
+        if int(err) != 0 or n == 0:
+            return None
+        err, nodes, n = rt.cudaGraphGetNodes(g, n)
+        k = 0
+        for nd in nodes[:n]:
+            err, ty = rt.cudaGraphNodeGetType(nd)
+            if int(err) == 0 and ty == rt.cudaGraphNodeType.cudaGraphNodeTypeKernel:
+                k += 1
+        return k
+    except Exception:
+        return None
+
+
+def new_graph():
+    import torch
+    try:
+        return torch.cuda.CUDAGraph(keep_graph=True)             # keeps the cudaGraph_t so that its nodes can be counted
+    except TypeError:
+        return torch.cuda.CUDAGraph()
+
+
+def parity_check_region(O, out, host, rp, cores):
+    """What the LAST replay left in the output tensors vs the oracle on this rank's own inputs (and the sampler steps that
+    replay used).  Integer outputs bit-exact, RoIAlign forward 1e-5 (+1e-6), backward 1e-5 of the gradient scale."""
+    import torch
+    torch.cuda.synchronize()
+    rpn_step = int(rp.rpn_targets.seed_tensor("cuda")[2]) - 1
+    rcnn_step = int(rp.rcnn_targets.seed_tensor("cuda")[2]) - 1
+    h = out["halves"][0]
+    ref = oracle_region_path(O, host, region_cfg(O, rpn_step, rcnn_step), cores)
+    g = lambda t: t.detach().cpu().numpy()
+    bad = []
+
+    def eq(name, a, b):
+        if not np.array_equal(a, b):
+            bad.append(name)
+    eq("props", g(h["props"]), ref["props"])
+    eq("pmask", g(h["pmask"]).astype(np.uint8), ref["pmask"])
+    eq("rpn_assigned", g(out["rpn"]["assigned"]), ref["rpn_assigned"])
+    eq("rpn_pos_idx", g(out["rpn"]["pos_idx"]), ref["rpn_pos_idx"])
+    eq("rpn_neg_idx", g(out["rpn"]["neg_idx"]), ref["rpn_neg_idx"])
+    eq("roi_boxes", g(h["rcnn"]["rois"])[:, :, 1:], ref["rois"][:, :, 1:])
+    eq("roi_labels", g(h["rcnn"]["labels"]), ref["roi_labels"])
+    eq("roi_mask", g(h["rcnn"]["mask"]).astype(np.uint8), ref["roi_mask"])
+    eq("roi_levels", g(rp.extractor.map_roi_levels(h["rois"])), O.roi_levels(ref["rois"].reshape(-1, 5), 56.0, 4))
+    fp = 0.0
+    a, b = g(h["roi_feats"]), ref["roi_feats"]
+    err = np.abs(a - b)
+    fp = max(fp, float((err / (np.abs(b) + 1e-1)).max()))
+    if not np.allclose(a, b, rtol=1e-5, atol=1e-6):
+        bad.append("roi_feats")
+    for l in range(4):
+        a, b = g(h["dfeats"][l]), ref["dfeats"][l]
+        scale = max(1.0, float(np.abs(b).max()))
+        e = float(np.abs(a - b).max()) / scale
+        fp = max(fp, e)
+        if e > 1e-5:
+            bad.append(f"dfeats{l}")
+    return bad, fp
+
+
+def nms_latency(rp, dev, iters=20):
+    """BASELINE metric "NMS us/image": MdNms (mask + sweep) on score-sorted decoded boxes, 5 segments of 2000 per image.
+    B = 8 amortised and the B = 1 latency."""
+    import torch
+    from minddet_b200 import NMSWithMask, TopKPerLevel, BoundingBoxDecode
+    dec = BoundingBoxDecode((800, 1344))
+    topk = TopKPerLevel(2000, apply_sigmoid=True)
+    rows = []
+    for l in list(range(4)) + [0]:                      # the coarsest level has only 819 anchors: level 0 stands in for it
+        sc, idx = topk(dev["cls_scores"][l])
+        boxes = dec.decode_level(dev["bbox_preds"][l], rp.proposal._bases(sc.device)[l], float(rp.strides[l]))
+        sel = torch.gather(boxes, 1, idx.long()[..., None].expand(-1, -1, 4))
+        rows.append(torch.cat([sel, sc[..., None]], 2))
+    allb = torch.stack(rows, 1).contiguous()            # (B, 5, 2000, 5)
+    nms = NMSWithMask(0.7)
+    res = {}
+    for name, t in (("b8", allb.reshape(-1, 2000, 5)), ("b1", allb[:1].reshape(-1, 2000, 5).contiguous())):
+        for _ in range(3):
+            nms(t)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            nms(t)
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = e0.elapsed_time(e1) / iters * 1e3
+    nimg = allb.shape[0]
+    return {"nms_us_per_image": res["b8"] / nimg, "nms_us_b1_latency": res["b1"], "boxes_per_level": 2000, "levels": 5,
+            "batch": nimg, "note": "MdNms (bitmask + on-device sweep) on the step's own score-sorted decoded boxes; "
+                                   "per-image figure = time of the B=%d call / %d; b1 = one image alone (5 segments)" % (nimg, nimg)}
+
+
+def global64_measure(world, rank, K, W):
+    """configs[2] literally: batch 64 image-sharded across the N GPUs (64/N images per GPU), device-resident, CUDA graph.
+    Inputs are generated on the device (timing only; parity is checked on the main workload)."""
+    import torch
+    import torch.distributed as dist
+    from minddet_b200 import pipeline, synth
+    if 64 % world:
+        return None
+    b = 64 // world
+    g = torch.Generator(device="cuda").manual_seed(0xD37 + rank)
+    shapes = synth.level_shapes()
+    inp = dict(
+        cls_scores=[torch.randn(b, 3, h, w, device="cuda", generator=g) * 2.0 - 4.0 for h, w in shapes],
+        bbox_preds=[torch.randn(b, 12, h, w, device="cuda", generator=g) * 0.15 for h, w in shapes],
+        feats=[torch.rand(b, 256, h, w, device="cuda", generator=g) * 2 - 1 for h, w in shapes[:4]],
+        dout=torch.rand(b * 512, 256, 7, 7, device="cuda", generator=g) * 2 - 1)
+    gts, labels, valid = synth.gt_boxes(b, G=128, seed=0xD37 + rank)
+    inp.update(gts=torch.from_numpy(gts).cuda(), gt_labels=torch.from_numpy(labels).cuda(), gt_valid=torch.from_numpy(valid.astype(bool)).cuda())
+    rp = pipeline.RegionPath(seed=0)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        run = lambda: rp.step(inp["cls_scores"], inp["bbox_preds"], inp["feats"], inp["gts"], inp["gt_labels"], inp["gt_valid"], inp["dout"])
+        for _ in range(2):
+            run()
+        st.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=st):
+            run()
+        for _ in range(max(1, W)):
+            graph.replay()
+        st.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    del inp, graph
+    torch.cuda.empty_cache()
+    return {"workload": "configs[2]: batch 64 image-sharded, %d images per GPU" % b, "value": 64 / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms, "images_per_gpu": b, "scaling": "strong", "data": "synthetic (generated on the device), in-line streams"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -191,6 +457,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the region path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     saved_stdout = None
     if world > 1:
         # NCCL prints "NCCL version ..." on stdout when it first connects; keep stdout for the ONE JSON line
@@ -198,10 +465,34 @@ def run_b200(args):
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.config == 5:
+        return run_yolo(args, world, rank, local, saved_stdout)
     W, K = max(3, args.warmup), max(1, args.steps)
+    batch = BATCH
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must be a multiple of the number of GPUs")
+        batch = args.global_batch // world
+    mask_branch = args.config == 4
 
     rp = pipeline.RegionPath(seed=0)
-    host = pipeline.make_inputs(BATCH, seed=0xD37 + rank, pin=True)
+    seed = 0xD37 if args.same_seed else 0xD37 + rank
+    host = pipeline.make_inputs(batch, seed=seed, pin=True)
+    if mask_branch:
+        from minddet_b200 import MaskTargets, SingleRoIExtractor
+        mext = SingleRoIExtractor(14, 2, synth.STRIDES[:4], 56)
+        mtarget = MaskTargets(28, 2)
+        rng = np.random.default_rng(seed + 9)
+        GM = 32                                                   # synth.gt_boxes draws at most 32 valid gts per image
+        gtb = host["gts"].numpy()
+        masks = np.zeros((batch, GM, synth.IMG_H, synth.IMG_W), np.uint8)
+        for b in range(batch):
+            for gi in range(GM):
+                x1, y1, x2, y2 = [int(v) for v in gtb[b, gi]]
+                if x2 > x1 and y2 > y1:
+                    masks[b, gi, y1:y2 + 1, x1:x2 + 1] = 1        # box-shaped instance masks (uint8, 275 MB per 8 images)
+        host["gt_masks"] = torch.from_numpy(masks).pin_memory()
+        host["dout_mask"] = torch.from_numpy(rng.uniform(-1, 1, (batch * 128, 256, 14, 14)).astype(np.float32)).pin_memory()
     h2d_bytes = pipeline.input_bytes(host)
     # Three priority levels (the device offers 0 .. -3; out-of-range values are clamped): the chain highest, the RPN
     # targets below it, the zero-fill lowest -- side work fills the SMs the chain leaves idle instead of queueing ahead of
@@ -211,9 +502,6 @@ def run_b200(args):
     aux = torch.cuda.Stream(priority=-1)
     zstream, zjoin, zfork = torch.cuda.Stream(), torch.cuda.Event(), torch.cuda.Event()
     fork, join = torch.cuda.Event(), torch.cuda.Event()
-    group_streams = [torch.cuda.Stream() for _ in range(max(0, args.split - 1))]
-    group_join = [torch.cuda.Event() for _ in range(max(0, args.split - 1))]
-    gfork = torch.cuda.Event()
     from minddet_b200 import shard
 
     def step(inp, timers=None):
@@ -225,91 +513,58 @@ def run_b200(args):
         mark("start")
         anchors, avalid = rp.anchors()
         overlap = timers is None and not args.no_overlap
+        rpn = None
         if overlap:
             # RPN target assignment depends only on anchors + gts, not on the proposals: it runs on a second stream
             # beside the (latency-bound) Proposal chain, as any graph executor is free to do; joined below
             cur = torch.cuda.current_stream()
             fork.record(cur)
             aux.wait_event(fork)
-            if os.environ.get("MD_BENCH_DIAG_SKIP_SIDE") in ("both", "rpn"):      # diagnosis only: the chain alone (results are NOT a bench value)
-                rpn = None
-                join.record(aux)
-            else:
-              with torch.cuda.stream(aux):     # (measured: started after Proposal or beside the RoIAlign forward instead, the step is 10 / 25 us longer)
+            with torch.cuda.stream(aux):
                 rpn = rp.rpn_targets(inp["gts"], inp["gt_valid"], anchors, avalid)
                 join.record(aux)
-        nh = args.split if timers is None else 1
+        feats_h = inp["feats"]
+        props, pmask = rp.proposal(inp["cls_scores"], inp["bbox_preds"])
         zeroed = None
-
-        def chain(a, b):
-            """Proposal -> RCNN targets -> RoIAlign fwd -> bwd for images [a, b) on the current stream"""
-            sl = lambda xs: [x[a:b] for x in xs]
-            feats_h = sl(inp["feats"])
-            props, pmask = rp.proposal(sl(inp["cls_scores"]), sl(inp["bbox_preds"]))
-            nonlocal zeroed
-            if overlap and nh == 1:
-                # The RoIAlign gradient's zero-fill (731 MB of DRAM writes, ~105 us) has no producer: it runs on its own
-                # (lower-priority) stream and the backward accumulates (MdRoiAlignBwdAcc).  Started here, beside the RCNN
-                # targets and the head of the RoIAlign forward, not at the top of the step: the Proposal kernels share
-                # the SMs badly with a kernel that wants every SM's store bandwidth (measured: 1.008 -> 0.999 ms, and
-                # 0.985 ms with Proposal's own two lanes, which only pay off without the fill beside them; started after
-                # the RCNN targets instead: 0.997 ms).
-                zfork.record(torch.cuda.current_stream())
-                zstream.wait_event(zfork)
-                with torch.cuda.stream(zstream):
-                    zeroed = [torch.empty_like(f) if os.environ.get("MD_BENCH_DIAG_SKIP_SIDE") in ("both", "zero") else torch.zeros_like(f)
-                              for f in inp["feats"]]
-                    zjoin.record(zstream)
-            if nh == 1:
-                mark("proposal")
-                nonlocal_rpn()
-                mark("rpn_assign_sample")
-            rcnn = rp.rcnn_targets(inp["gts"][a:b], inp["gt_labels"][a:b], pmask, props, inp["gt_valid"][a:b])
-            mark("rcnn_assign_sample")
-            rois = rcnn["rois"].reshape(-1, 5)
-            roi_feats = rp.extractor._forward(rois, feats_h)
-            mark("roialign_fwd")
-            n_roi = rois.shape[0] // (b - a)
-            if zeroed is not None:
-                torch.cuda.current_stream().wait_event(zjoin)
-                dfe = rp.extractor._backward_into(rois, inp["dout"][a * n_roi:b * n_roi], zeroed)
-            else:
-                dfe = rp.extractor._backward(rois, inp["dout"][a * n_roi:b * n_roi], [tuple(f.shape) for f in feats_h])
-            mark("roialign_bwd")
-            return dict(props=props, pmask=pmask, rcnn=rcnn, rois=rois, roi_feats=roi_feats, dfeats=dfe, first_image=a)
-
-        rpn_box = [rpn if overlap else None]
-
-        def nonlocal_rpn():
-            if not overlap:
-                rpn_box[0] = rp.rpn_targets(inp["gts"], inp["gt_valid"], anchors, avalid)
-
-        if nh == 1:
-            halves = [chain(0, BATCH)]
+        if overlap:
+            # The RoIAlign gradient's zero-fill (731 MB of DRAM writes, ~105 us) has no producer: it runs on its own
+            # (lower-priority) stream and the backward accumulates (MdRoiAlignBwdAcc).  Started after Proposal: the
+            # Proposal kernels share the SMs badly with a kernel that wants every SM's store bandwidth.
+            zfork.record(torch.cuda.current_stream())
+            zstream.wait_event(zfork)
+            with torch.cuda.stream(zstream):
+                zeroed = [torch.zeros_like(f) for f in inp["feats"]]
+                zjoin.record(zstream)
+        mark("proposal")
+        if not overlap:
+            rpn = rp.rpn_targets(inp["gts"], inp["gt_valid"], anchors, avalid)
+        mark("rpn_assign_sample")
+        rcnn = rp.rcnn_targets(inp["gts"], inp["gt_labels"], pmask, props, inp["gt_valid"])
+        mark("rcnn_assign_sample")
+        rois = rcnn["rois"].reshape(-1, 5)
+        roi_feats = rp.extractor._forward(rois, feats_h)
+        mark("roialign_fwd")
+        if zeroed is not None:
+            torch.cuda.current_stream().wait_event(zjoin)
+            dfe = rp.extractor._backward_into(rois, inp["dout"], zeroed)
         else:
-            # Images are independent: the batch runs as `nh` groups on `nh` streams, so the latency-bound kernels of one
-            # group (cluster top-k, NMS sweep, samplers) fill the SMs the bandwidth-bound RoIAlign of the other leaves idle.
-            cur = torch.cuda.current_stream()
-            gfork.record(cur)
-            halves = []
-            for h in range(nh):
-                a, b = h * BATCH // nh, (h + 1) * BATCH // nh
-                if h == 0:
-                    halves.append(chain(a, b))
-                else:
-                    st = group_streams[h - 1]
-                    st.wait_event(gfork)
-                    with torch.cuda.stream(st):
-                        halves.append(chain(a, b))
-                        group_join[h - 1].record(st)
-            for h in range(1, nh):
-                cur.wait_event(group_join[h - 1])
-            nonlocal_rpn()
+            dfe = rp.extractor._backward(rois, inp["dout"], [tuple(f.shape) for f in feats_h])
+        mark("roialign_bwd")
+        res = dict(props=props, pmask=pmask, rcnn=rcnn, rois=rois, roi_feats=roi_feats, dfeats=dfe)
+        if mask_branch:
+            # Mask R-CNN: the <=128 positive slots of every image -> 14x14 mask RoIAlign (fwd + bwd into the same gradient
+            # tensors) and the 28x28 target crop of the assigned gt's mask
+            prois = rcnn["rois"][:, :128].reshape(-1, 5).contiguous()
+            res["mask_feats"] = mext._forward(prois, feats_h)
+            mark("mask_roialign_fwd")
+            mext._backward_into(prois, inp["dout_mask"], list(dfe))
+            mark("mask_roialign_bwd")
+            res["mask_targets"] = mtarget(inp["gt_masks"], prois, rcnn["pos_gt"].reshape(-1).contiguous())
+            mark("mask_targets")
         if overlap:
             torch.cuda.current_stream().wait_event(join)
-        rpn = rpn_box[0]
-        top100 = halves[0]["props"][:, :100].contiguous() if nh == 1 else torch.cat([h_["props"][:, :100] for h_ in halves])
-        return dict(halves=halves, rpn=rpn, top100=top100)
+        top100 = props[:, :100].contiguous()
+        return dict(halves=[res], rpn=rpn, top100=top100)
 
     with torch.cuda.stream(side):
         dev = pipeline.to_device(host)
@@ -327,12 +582,13 @@ def run_b200(args):
                 stage_ms.setdefault(n1, []).append(e0.elapsed_time(e1))
         stage_ms = {k: float(np.median(v)) for k, v in stage_ms.items()}
 
-        # CUDA graph of the whole step (launch-bound otherwise: 16 kernels + 5 memsets behind 7 ctypes calls)
-        graph = None
+        # CUDA graph of the whole step (launch-bound otherwise: ~25 kernels + memsets behind 7 ctypes calls)
+        graph, launches = None, None
         if not args.no_graph:
-            graph = torch.cuda.CUDAGraph()
+            graph = new_graph()
             with torch.cuda.graph(graph, stream=side):
                 out = step(dev)
+            launches = count_graph_kernels(graph)
             graph.replay()
             side.synchronize()
 
@@ -345,7 +601,7 @@ def run_b200(args):
             if world > 1 and not os.environ.get("MD_BENCH_NO_GATHER"):   # (debug switch: isolates the collective's cost)
                 # the path's only collective: all-gather of the final detections (top-100 proposals / image).  Asynchronous:
                 # the records of step i travel on NCCL's stream while step i+1 computes; at most 2 in flight.
-                pending.append(shard.gather_detections(o["top100"], world * BATCH, async_op=True))
+                pending.append(shard.gather_detections(o["top100"], world * batch, async_op=True))
                 if len(pending) > 2:
                     o["gathered"] = pending.pop(0).result()
             return o
@@ -381,21 +637,40 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1) / K
-        if os.environ.get("MD_BENCH_DIAG_SKIP_SIDE"):
-            print(f"[diag] skipped side work = {os.environ['MD_BENCH_DIAG_SKIP_SIDE']}: {ms:.4f} ms / step", file=sys.stderr, flush=True)
-            os._exit(0)
+
+        # ---- what did we just compute?  every rank, its own inputs, against the CPU oracle -------------------------
+        parity = None
+        if not args.no_parity:
+            import oracle as O
+            cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            bad, fp = parity_check_region(O, out, host, rp, max(1, cores // max(1, world)))
+            if mask_branch and not bad:
+                h = out["halves"][0]
+                prois = h["rcnn"]["rois"][:, :128].reshape(-1, 5).cpu().numpy()
+                pg = h["rcnn"]["pos_gt"].reshape(-1).cpu().numpy()
+                mt = h["mask_targets"].cpu().numpy().astype(np.uint8)
+                mk = host["gt_masks"].numpy()
+                for b in range(min(batch, 2)):
+                    sel = slice(b * 128, (b + 1) * 128)
+                    if not np.array_equal(mt[sel], O.mask_targets(mk[b], prois[sel, 1:], pg[sel], 28, 2)):
+                        bad.append(f"mask_targets[{b}]")
+                mf = O.roialign_fwd([x.numpy()[:1] for x in host["feats"]], synth.STRIDES[:4], prois[:128], P=14, S=2)
+                if not np.allclose(h["mask_feats"][:128].cpu().numpy(), mf, rtol=1e-5, atol=1e-6):
+                    bad.append("mask_feats")
+            parity = {"int_exact": not bad, "fp_max_rel": fp, "mismatched": bad}
 
         # per-stage durations, live with CUDA events on the launching stream (eager, same kernels), K passes
         per = {}
-        for _ in range(K):
+        for _ in range(min(K, 10)):
             tm = []
             step(dev, tm)
             side.synchronize()
             for (n0, ev0), (n1, ev1) in zip(tm[:-1], tm[1:]):
                 per.setdefault(n1, []).append(ev0.elapsed_time(ev1))
         live_ms = {k: float(np.median(v)) for k, v in per.items()}     # median: robust to host-side launch hiccups of the eager pass
+        nms = nms_latency(rp, dev) if rank == 0 else None
 
-        # ---- e2e: every step copies ALL inputs pinned host -> device and reads the step's compact results back.
+        # ---- e2e: every step copies ALL inputs pinned host -> device and reads a token sample of the results back.
         # Two device input sets + a copy stream: the H2D of step i+1 overlaps the kernels of step i (a user
         # feeding the op from host memory would do the same); each set has its own captured graph. ------------
         cs = torch.cuda.Stream()
@@ -439,7 +714,7 @@ def run_b200(args):
             else:
                 o = step(sets[b])
             if world > 1:
-                pending.append(shard.gather_detections(o["top100"], world * BATCH, async_op=True))
+                pending.append(shard.gather_detections(o["top100"], world * batch, async_op=True))
                 if len(pending) > 2:
                     o["gathered"] = pending.pop(0).result()
             res = results_of(o)
@@ -468,11 +743,28 @@ def run_b200(args):
         if rank == 0:
             sampler.join(timeout=2)
 
+    g64 = None
+    if world > 1 and not args.global_batch and not args.no_global64 and not mask_branch:
+        del dev2, graphs, outs
+        torch.cuda.empty_cache()
+        g64 = global64_measure(world, rank, K, W)
+
+    per_rank = [ms]
+    parity_ranks = [parity]
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
-    def leave():
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        per_rank = [float(x[0]) for x in allr]
+        per_rank_e2e = [float(x[1]) for x in allr]
+        ms, e2e_ms = max(per_rank), max(per_rank_e2e)
+        objs = [None] * world
+        dist.all_gather_object(objs, parity)
+        parity_ranks = objs
+    else:
+        per_rank_e2e = [e2e_ms]
+
+    def leave(code=0):
         # N > 1: leave through a barrier and a hard exit.  Tearing the NCCL communicator down while CUDA graphs, pinned
         # buffers and side streams are still alive has been seen to hang a rank after the result was already printed.
         if world > 1:
@@ -481,21 +773,26 @@ def run_b200(args):
             try:
                 dist.barrier()
             finally:
-                os._exit(0)
+                os._exit(code)
+        elif code:
+            sys.exit(code)
 
+    checked = [p for p in parity_ranks if p is not None]
+    parity_ok = all(p["int_exact"] for p in checked)
     if rank != 0:
-        leave()
+        leave(0 if parity_ok else 3)
         return
 
-    value = world * BATCH / (ms * 1e-3)
+    value = world * batch / (ms * 1e-3)
     # ---- rooflines (HBM): algorithmic bytes per launch / live CUDA-event duration of the stage -------------
     peak, peak_src = peaks()
-    rois_np = torch.cat([torch.cat([h_["rois"][:, :1] + h_["first_image"], h_["rois"][:, 1:]], 1) for h_ in out["halves"]]).cpu().numpy()
+    h0 = out["halves"][0]
+    rois_np = h0["rois"].cpu().numpy()
     C, P = 256, 7
     shapes = synth.level_shapes()[:4]
     fp = footprint_bytes(rois_np, shapes, synth.STRIDES[:4], C)
     out_bytes = rois_np.shape[0] * C * P * P * 4
-    dx_bytes = sum(BATCH * C * h * w * 4 for h, w in shapes)
+    dx_bytes = sum(batch * C * h * w * 4 for h, w in shapes)
     n_anchor = sum(3 * h * w for h, w in synth.level_shapes())
     alg = {
         # RoI tensor written + exact union of the bilinear footprints read
@@ -503,9 +800,9 @@ def run_b200(args):
         # dY read + union footprint updated + zero-init of every dX byte
         "roialign_bwd": out_bytes + fp + dx_bytes,
         # scores read + (deltas gathered, boxes written, NMS in/out, proposals out) per image
-        "proposal": BATCH * (n_anchor * 4 + 8819 * (16 + 16 + 8 + 25) + 2000 * 21),
+        "proposal": batch * (n_anchor * 4 + 8819 * (16 + 16 + 8 + 25) + 2000 * 21),
         # anchors + valid read, assigned written and re-read by the samplers
-        "rpn_assign_sample": BATCH * (n_anchor * (16 + 1 + 4 + 4)),
+        "rpn_assign_sample": batch * (n_anchor * (16 + 1 + 4 + 4)),
     }
     rooflines = {k: {"achieved": alg[k] / (live_ms[k] * 1e-3) / 1e9, "frac": alg[k] / (live_ms[k] * 1e-3) / 1e9 / peak,
                      "algorithmic_bytes_per_launch": alg[k], "ms": live_ms[k]} for k in alg}
@@ -520,46 +817,150 @@ def run_b200(args):
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        cpu = cpu_baseline()
+        restore_affinity()                                         # the CPU arm may use every host core again
+        v, cores, busy, sample = cpu_region_throughput(10.0)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "threads_busy": busy, "kind": "port", "sample": sample}
+    nk = launches if launches is not None else (23 + (6 if mask_branch else 0))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "parallelism": f"image-sharded dp{world}",
-                       "l2": "inputs larger than L2 (731 MB of features per step vs 126 MB L2)",
-                       "cuda_graph": graph is not None,
-                       "streams": (f"{args.split} image groups on {args.split} streams; " if args.split > 1 else "") +
-                                  ("rpn target assignment and the RoIAlign-gradient zero-fill on their own streams (backward accumulates: MdRoiAlignBwdAcc)"
-                                   if not args.no_overlap else "rpn targets in line, MdRoiAlignBwd zero-fills in line")},
+            "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(args, world, batch),
+            "run": {"cuda_graph": graph is not None, "same_seed": bool(args.same_seed),
+                    "streams": ("rpn target assignment and the RoIAlign-gradient zero-fill on their own streams (backward accumulates: "
+                                "MdRoiAlignBwdAcc)" if not args.no_overlap else "rpn targets in line, MdRoiAlignBwd zero-fills in line"),
+                    "numa": numa},
+            "per_rank_ms": {"min": min(per_rank), "median": float(np.median(per_rank)), "max": max(per_rank), "all": per_rank},
             "clocks": sampler.summary(),
-            "e2e": {"value": world * BATCH / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms},
-            "gpu_launches": (17 * args.split + 6) * K,   # per image group: proposal 7 (2 lanes x (select, nms mask, nms sweep) + merge) + rcnn targets 6 + RoIAlign fwd 2 + bwd 2; rpn targets 6
+            "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
+                    "h2d_GBps_per_rank": [h2d_bytes / (t * 1e-3) / 1e9 for t in per_rank_e2e],
+                    "readback": "a token sample of the results (sampled ids, targets, RoIs, top-100 proposals, 4 RoI feature maps, "
+                                "8 gradient values per level): the real consumers of roi_feats / dX are on-device heads"},
+            "gpu_launches": nk * K,
+            "gpu_launches_per_step": {"kernels": nk, "source": "kernel nodes of the captured CUDA graph" if launches is not None
+                                      else "counted from the call sequence (the graph's node list is not exposed by this torch)"},
             "nccl_collectives_per_step": 1 if world > 1 else 0,
+            "parity_checked": {"ranks": len(checked), "int_exact": parity_ok,
+                               "fp_max_rel": max([p["fp_max_rel"] for p in checked], default=None),
+                               "mismatched": sorted({m for p in checked for m in p["mismatched"]}),
+                               "what": "last replay of the timed loop vs oracle.region_path_batch on the rank's own inputs: proposals, "
+                                       "masks, assigned gt indices, sampled ids, RoIs, labels, RoI levels bit-exact; RoIAlign fwd rtol 1e-5, "
+                                       "bwd 1e-5 of the gradient scale"},
+            "nms": nms, "global64": g64,
             "roofline": roofline, "stage_ms": stage_ms, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
-    leave()
+    leave(0 if parity_ok else 3)
 
 
-def cpu_baseline():
-    """Oracle port of the whole path timed on this box's host cores on a bounded sample."""
-    import oracle as O
-    from minddet_b200 import pipeline, synth
-    cores = os.cpu_count() or 1
-    nimg = max(1, min(BATCH, cores))
-    inp = pipeline.make_inputs(nimg, seed=0xD37)
-    cfg = region_cfg(O)
-    arrs = ([x.numpy() for x in inp["cls_scores"]], [x.numpy() for x in inp["bbox_preds"]], synth.base_anchor_sets(), synth.STRIDES,
-            [x.numpy() for x in inp["feats"]], inp["gts"].numpy(), inp["gt_labels"].numpy(), inp["gt_valid"].numpy().astype(np.uint8))
-    dout = inp["dout"].numpy()
-    O.region_path_batch(*arrs, cfg, dout=dout, nthreads=cores)          # warm-up (page faults, thread start)
-    reps, t0 = 0, time.perf_counter()
-    while True:
-        O.region_path_batch(*arrs, cfg, dout=dout, nthreads=cores)
-        reps += 1
-        dt = time.perf_counter() - t0
-        if dt >= 10.0 or reps >= 64:
-            break
-    return {"value": reps * nimg / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{reps} passes over {nimg} images of the same workload ({dt:.1f} s), {cores} pthreads (one image per task)"}
+# ------------------------------------------------------------------------------------------------
+def run_yolo(args, world, rank, local, saved_stdout):
+    """--config 5: YOLOv8 640x640, 64 images per GPU: DFL decode (roofline kernel) + class-aware NMS."""
+    import torch
+    import torch.distributed as dist
+    from minddet_b200 import YoloV8PostProcess
+    W, K = max(3, args.warmup), max(1, args.steps)
+    B, nc = (args.global_batch // world) if args.global_batch else 64, 80
+    shapes, strides = [(80, 80), (40, 40), (20, 20)], (8, 16, 32)
+    A = sum(h * w for h, w in shapes)
+    rng = np.random.default_rng(0xD37 + (0 if args.same_seed else rank))
+    hp = rng.normal(0, 1, (2, B, 64 + nc, A)).astype(np.float32)
+    hp[:, :, 64:] -= 5.0
+    host = [torch.from_numpy(hp[i]).pin_memory() for i in range(2)]
+    preds = [h.cuda() for h in host]                                   # 2 x 310 MB, used alternately: inputs > L2
+    op = YoloV8PostProcess(shapes, strides, conf_thr=0.25, nms_pre=2048, max_det=300)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for i in range(W):
+            out = op(preds[i & 1])
+        st.synchronize()
+        if saved_stdout is not None:
+            if world > 1:
+                dist.barrier()
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            out = op(preds[i & 1])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        # the decode kernel alone (roofline)
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for i in range(K):
+            dets = op.decode(preds[i & 1])
+        d1.record()
+        torch.cuda.synchronize()
+        dec_ms = d0.elapsed_time(d1) / K
+        # parity: first 4 images of the last step against the oracle
+        import oracle as O
+        last = (K - 1) & 1
+        res, keep, cnt = [t.cpu().numpy() for t in op(preds[last])]
+        bad = []
+        for b in range(min(B, 4)):
+            dd = O.yolo_decode(hp[last, b], shapes, strides)
+            ro, ri, rc = O.yolo_nms(dd, 0.25, 2048, 0.7, False, 300)
+            if cnt[b] != rc or not np.array_equal(keep[b], ri) or not np.array_equal(res[b], ro):
+                bad.append(b)
+        # e2e: H2D of the prediction tensor + D2H of the detections every step
+        pin_out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in out]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            preds[i & 1].copy_(host[i & 1], non_blocking=True)
+            o = op(preds[i & 1])
+            for d, s_ in zip(pin_out, o):
+                d.copy_(s_, non_blocking=True)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / K
+        sampler.stop_flag = True
+    per_rank = [ms]
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms, dec_ms], device="cuda")
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        per_rank = [float(x[0]) for x in allr]
+        ms, e2e_ms, dec_ms = max(per_rank), max(float(x[1]) for x in allr), max(float(x[2]) for x in allr)
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            os._exit(3 if bad else 0)
+        return
+    peak, peak_src = peaks()
+    alg = B * A * ((64 + nc) * 4 + 24)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        restore_affinity()
+        v, cores, busy, sample = cpu_yolo_throughput(10.0)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "threads_busy": busy, "kind": "port", "sample": sample}
+    h2d = hp[0].nbytes
+    d2h = sum(t.numel() * t.element_size() for t in out)
+    line = {"metric": "YOLOv8 post-process throughput", "value": world * B / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(args, world, B),
+            "per_rank_ms": {"min": min(per_rank), "median": float(np.median(per_rank)), "max": max(per_rank), "all": per_rank},
+            "clocks": sampler.summary(),
+            "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+            "gpu_launches": 6 * K, "gpu_launches_per_step": {"kernels": 6, "source": "decode + (cfg, select, mask, sweep, emit) of the NMS call"},
+            "parity_checked": {"ranks": 1, "int_exact": not bad, "mismatched": bad,
+                               "what": "detections, keep indices and counts of the first 4 images bit-exact vs oracle yolo_decode + yolo_nms"},
+            "roofline": {"kernel": "yolo_decode_kernel", "bound": "hbm", "achieved": alg / (dec_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (dec_ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC["yolo_decode"], "algorithmic_bytes_per_launch": alg,
+                         "kernel_ms": dec_ms, "peak_source": peak_src,
+                         "note": "algorithmic bytes = (64+nc)*4 B read + 24 B written per anchor"},
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        sys.stdout.flush()
+        dist.barrier()
+        os._exit(3 if bad else 0)
+    if bad:
+        sys.exit(3)
 
 
 def main():
@@ -568,11 +969,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
+                    help="BASELINE.json workload: 2 = configs[1] (default), 4 = configs[3] Mask R-CNN, 5 = configs[4] YOLOv8 post-process")
+    ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: this many images over all GPUs (64 = configs[2])")
+    ap.add_argument("--same-seed", action="store_true", help="every rank works on identical images (separates data variance from interference)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--split", type=int, default=1,
-                    help="run the step as this many independent image groups on as many streams (measured: 2 -> no gain, 4 -> 2%%)")
-    ap.add_argument("--no-overlap", action="store_true", help="run the RPN target assignment in line instead of on a second stream")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-global64", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run the RPN target assignment and the zero-fill in line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -28,6 +28,9 @@ class _Cell:
         return self.construct(*a, **k)
 
     def _cfg(self, values, device, dtype=torch.float32):
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         key = (str(device), dtype, tuple(values))
         cache = self.__dict__.setdefault("_cfg_cache", {})
         if key not in cache:
