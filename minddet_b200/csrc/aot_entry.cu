@@ -192,7 +192,7 @@ int MdNms(MD_AOT_ARGS)
     REQ(ld >= 4);
     REQ(numel(ndims[1], shapes[1]) >= MD_NMS_LEN);
     REQ(numel(ndims[2], shapes[2]) == (int64_t)B * K && numel(ndims[3], shapes[3]) == (int64_t)B * K && numel(ndims[4], shapes[4]) == B);
-    if (K > 2048) return MD_ERR_SIZE;
+    if (K > 4096) return MD_ERR_SIZE;                  // sweep capacity: 64 mask words per row
     void *ws = nullptr;
     int rc = get_workspace(stream, md::nms_workspace_bytes(B, K), &ws);
     if (rc) return rc;
@@ -426,7 +426,7 @@ static int bev_nms_impl(int mode, int keep_is_64, MD_AOT_ARGS)
     REQ(ndims[0] == 2 && shapes[0][1] == 7 && numel(ndims[1], shapes[1]) >= 1 && numel(ndims[3], shapes[3]) >= 1);
     const int n = (int)shapes[0][0];
     REQ(numel(ndims[2], shapes[2]) == n);
-    if (n > 2048) return MD_ERR_SIZE;
+    if (n > 4096) return MD_ERR_SIZE;
     void *ws = nullptr;
     int rc = get_workspace(stream, md::bev_nms_workspace_bytes(n), &ws);
     if (rc) return rc;

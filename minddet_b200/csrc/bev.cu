@@ -232,7 +232,7 @@ cudaError_t launch_bev_nms(const float *boxes, int n, const float *thr, int mode
                            int32_t *num_out, cudaStream_t s)
 {
     const int nb = (n + 63) / 64, nbp = (nb + 1) & ~1;
-    if (nb > 32) return cudaErrorInvalidValue;               // sweep capacity: 2048 boxes
+    if (nb > 64) return cudaErrorInvalidValue;               // sweep capacity: 4096 boxes (the reference's older CPU copy: N = 4096)
     unsigned char *p = reinterpret_cast<unsigned char *>(ws);
     unsigned long long *mask = reinterpret_cast<unsigned long long *>(p); p += (size_t)nb * 64 * nbp * 8;
     unsigned long long *init_removed = reinterpret_cast<unsigned long long *>(p); p += (size_t)nbp * 8;

@@ -511,10 +511,15 @@ template <int N> MD_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_gr
 // One __syncthreads per chunk; keep_mask / keep_pos are written by all threads after the walk from kept_all[].
 constexpr int kSweepHelpers = 8;                            // helper warps
 constexpr int kSweepThreads = 32 * (1 + kSweepHelpers);
-constexpr int kSweepMaxNb = 32;    // K <= 2048
-constexpr int kSweepStages = 6;    // a chunk is issued 4 iterations (~1 us) before the resolver needs its diagonal
-constexpr size_t kSweepSmem = (size_t)kSweepStages * 64 * kSweepMaxNb * sizeof(unsigned long long);
+// Two instantiations: <32 words, 6 stages> for K <= 2048 (a chunk is issued 4 iterations, ~1 us, before the resolver needs
+// its diagonal) and <64 words, 4 stages> for K <= 4096 (the ring is bounded by shared memory: 4 x 32 KB).
+constexpr int kSweepMaxNbAny = 64;
+template <int kSweepMaxNb, int kSweepStages> constexpr size_t sweep_smem_bytes()
+{
+    return (size_t)kSweepStages * 64 * kSweepMaxNb * sizeof(unsigned long long);
+}
 
+template <int kSweepMaxNb, int kSweepStages>
 __global__ void __launch_bounds__(kSweepThreads)
 nms_sweep_kernel(const NmsSegs sg, const unsigned long long *__restrict__ mask,
                  const unsigned long long *__restrict__ init_removed /* nullable: (nseg, nbp) boxes dead on entry */,
@@ -597,14 +602,20 @@ nms_sweep_kernel(const NmsSegs sg, const unsigned long long *__restrict__ mask,
         } else {
             issue(c + kSweepStages - 2);
             // rows of chunk c - 1, words c + 1 ..: `kept` is warp-uniform, so a row that was not kept costs one predicate
-            if (c >= 1 && lane > c && lane < nb) {
+            if (c >= 1) {
                 const unsigned long long kept = kept_all[c - 1] >> (hw * kRowsPerWarp);
-                const unsigned long long *col = stage[(c - 1) % kSweepStages] + (hw * kRowsPerWarp) * nbp + lane;
-                unsigned long long acc = 0ull;
 #pragma unroll
-                for (int b = 0; b < kRowsPerWarp; b++)
-                    if ((kept >> b) & 1ull) acc |= col[b * nbp];
-                if (acc) atomicOr(&removed[lane], acc);
+                for (int w0 = 0; w0 < kSweepMaxNb; w0 += 32) {
+                    const int w = w0 + lane;                         // lane j = words j, j + 32
+                    if (w > c && w < nb) {
+                        const unsigned long long *col = stage[(c - 1) % kSweepStages] + (hw * kRowsPerWarp) * nbp + w;
+                        unsigned long long acc = 0ull;
+#pragma unroll
+                        for (int b = 0; b < kRowsPerWarp; b++)
+                            if ((kept >> b) & 1ull) acc |= col[b * nbp];
+                        if (acc) atomicOr(&removed[w], acc);
+                    }
+                }
             }
         }
     }
@@ -612,18 +623,23 @@ nms_sweep_kernel(const NmsSegs sg, const unsigned long long *__restrict__ mask,
     __syncthreads();
     // outputs: kept_before[c] = boxes kept in chunks < c, then every thread writes its boxes
     if (warp == 0) {
-        const int n = lane < nb ? __popcll(kept_all[lane]) : 0;
-        int incl = n;
+        int base = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
+        for (int w0 = 0; w0 < kSweepMaxNb; w0 += 32) {
+            const int n = w0 + lane < nb ? __popcll(kept_all[w0 + lane]) : 0;
+            int incl = n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            kept_before[w0 + lane] = base + incl - n;
+            base += __shfl_sync(0xffffffffu, incl, 31);
         }
-        kept_before[lane] = incl - n;
-        if (lane == 31) kept_before[32] = incl;
+        if (lane == 0) kept_before[kSweepMaxNb] = base;
     }
     __syncthreads();
-    const int nkept = kept_before[32];
+    const int nkept = kept_before[kSweepMaxNb];
     for (int i = tid; i < mask_stride; i += kSweepThreads) {
         bool k = false;
         if (i < K) {
@@ -654,33 +670,42 @@ cudaError_t run_nms(const NmsSegs &sg, int nseg, int Kmax, const float *cfg, uns
 {
     if (nseg == 0) return cudaSuccess;
     const int nb = (Kmax + 63) / 64;
-    if (nb > kSweepMaxNb) return cudaErrorInvalidValue;
+    if (nb > kSweepMaxNbAny) return cudaErrorInvalidValue;
     const int tiles = nb * (nb + 1) / 2;
     if (tiles > 0) {
         const dim3 grid = kMaskGroup == 1 ? dim3(tiles, 1, nseg) : dim3(nb, (nb + kMaskGroup - 1) / kMaskGroup, nseg);
         if (sg.labels) nms_mask_kernel<true><<<grid, 64, 0, s>>>(sg, cfg, mask);
         else nms_mask_kernel<false><<<grid, 64, 0, s>>>(sg, cfg, mask);
     }
-    const size_t sweep_smem = kSweepSmem;
-    {   // the attribute is per DEVICE and the value is a constant: set it on every launch (no process-wide "done" flag)
-        cudaError_t e = cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem);
+    if (nb <= 32) {
+        // the attribute is per DEVICE and the value is a constant: set it on every launch (no process-wide "done" flag)
+        cudaError_t e = cudaFuncSetAttribute(nms_sweep_kernel<32, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes<32, 6>());
         if (e != cudaSuccess) return e;
+        nms_sweep_kernel<32, 6><<<nseg, kSweepThreads, sweep_smem_bytes<32, 6>(), s>>>(sg, mask, nullptr, keep_pos, keep_stride, keep_mask, mask_stride, count);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(nms_sweep_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes<64, 4>());
+        if (e != cudaSuccess) return e;
+        nms_sweep_kernel<64, 4><<<nseg, kSweepThreads, sweep_smem_bytes<64, 4>(), s>>>(sg, mask, nullptr, keep_pos, keep_stride, keep_mask, mask_stride, count);
     }
-    nms_sweep_kernel<<<nseg, kSweepThreads, sweep_smem, s>>>(sg, mask, nullptr, keep_pos, keep_stride, keep_mask, mask_stride, count);
     return cudaGetLastError();
 }
 
-// one segment of n boxes whose bitmask was produced elsewhere (bev.cu)
 cudaError_t launch_nms_sweep_single(const unsigned long long *mask, const unsigned long long *init_removed, int n, int nbp,
                                     int32_t *keep_pos, uint8_t *keep_mask, int32_t *count, cudaStream_t s)
 {
     NmsSegs sg{};
     sg.L = 1; sg.K[0] = n; sg.nbp = nbp; sg.rows_pad = ((n + 63) / 64) * 64;
-    if ((n + 63) / 64 > kSweepMaxNb) return cudaErrorInvalidValue;
-    const size_t sweep_smem = kSweepSmem;
-    cudaError_t e = cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem);
-    if (e != cudaSuccess) return e;
-    nms_sweep_kernel<<<1, kSweepThreads, sweep_smem, s>>>(sg, mask, init_removed, keep_pos, n, keep_mask, n, count);
+    const int nb = (n + 63) / 64;
+    if (nb > kSweepMaxNbAny) return cudaErrorInvalidValue;
+    if (nb <= 32) {
+        cudaError_t e = cudaFuncSetAttribute(nms_sweep_kernel<32, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes<32, 6>());
+        if (e != cudaSuccess) return e;
+        nms_sweep_kernel<32, 6><<<1, kSweepThreads, sweep_smem_bytes<32, 6>(), s>>>(sg, mask, init_removed, keep_pos, n, keep_mask, n, count);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(nms_sweep_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes<64, 4>());
+        if (e != cudaSuccess) return e;
+        nms_sweep_kernel<64, 4><<<1, kSweepThreads, sweep_smem_bytes<64, 4>(), s>>>(sg, mask, init_removed, keep_pos, n, keep_mask, n, count);
+    }
     return cudaGetLastError();
 }
 

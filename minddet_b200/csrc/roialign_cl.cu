@@ -52,7 +52,6 @@ constexpr int kClP = 7;
 constexpr int kClStageFloats = 32 * kClP * kClP;       // 32 channels x 49 outputs
 constexpr int kClStageBytes = kClStageFloats * 4;      // 6272
 
-enum { CL_OK = 0, CL_ZERO = 1, CL_DECLINE = 2 };
 
 // Staged rows are [row][channel][4*NQ floats], unpadded (the TMA box).  Lane c reads channel c with LDS.128; a quarter
 // warp (8 lanes) must hit 8 distinct 16-byte slots of a 128-byte bank row.  With a channel pitch of 32 / 64 bytes lanes
@@ -71,25 +70,32 @@ struct ClMaps { CUtensorMap m[kClLevels * 4 * kClRsel]; };       // [level][nq -
 
 constexpr int kClMaxChunks = 4;             // column chunks of <= 4 quads
 constexpr int kClMaxPieces = 28;            // (chunk, bin range) pieces per (RoI, channel group)
+constexpr int kClMaxOps = 36;               // bulk-tensor row operations per RoI (rows + one per extra piece)
 
 // one bin: compact rows [ja, ja + nr), nr <= 4, and their weights (1/S folded in, both samples summed)
 struct __align__(16) ClBin { int ja, nr, pad0, pad1; float w[4]; };
 // one bilinear output column q of one column chunk: 4 taps = byte offsets into the lane's scratch column + weights
 struct __align__(16) ClTap { int o[4]; float w[4]; };
-// one staged piece: columns [x0, x0 + 4 nqc) of compact rows [jA, jA + rows), producing bins [p0, p1)
-struct __align__(16) ClPiece { int x0, nqc, jA, rows, p0, p1, chunk, first; };
+// one staged piece: columns [x0, x0 + 4 nqc) of compact rows [jA, jA + rows), producing bins [p0, p1);
+// its rows arrive as the bulk-tensor operations op[op0 .. op0 + nop)
+struct __align__(16) ClPiece { int x0, nqc, jA, rows, p0, p1, chunk, ops; };   // ops = op0 | nop << 16
+struct ClOp { short j, lr; };               // rows j .. j + (1 << lr) - 1 of the compact list (consecutive feature rows)
 
+enum { CL_OK = 0, CL_ZERO = 1, CL_DECLINE = 2 };
+
+// Everything the kernels need to know about one RoI, built ONCE by roialign_plan_kernel (one warp per RoI) and then
+// pulled into shared memory by one bulk copy per (RoI, channel chunk) item, one item ahead of its use.
 struct __align__(16) ClItem {
     ClBin bin[8];
     ClTap tap[kClMaxChunks][8];      // Ax, sparse, per column chunk
     ClPiece piece[kClMaxPieces];
+    ClOp op[kClMaxOps];
     int yof[32];                     // feature row of compact row j
-    int xlo[16], xhi[16];            // x samples, columns relative to x_lo
+    int xlo[16], xhi[16];            // x samples, columns relative to x_lo (the backward's dense Ax is built from these)
     float xwl[16], xwh[16];
-    int r, chunk, b, l, x_lo, nq, nrows, npiece, nxc;
-    unsigned runmask;                // bit j: compact row j+1 is the feature row right below compact row j
-    int pad_[2];
+    int status, b, l, x_lo, nq, nrows, npiece, nxc;
 };
+static_assert(sizeof(ClItem) % 16 == 0, "bulk copies move multiples of 16 bytes");
 struct ClBuild { float ew[kClRows][8]; int ja[8], jb[8]; };     // scratch of cl_build_item
 
 MD_DEVINL float4 lds128f(uint32_t a)
@@ -105,10 +111,10 @@ MD_DEVINL void sts128f(uint32_t a, float4 v)
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// ---- per-item geometry (one whole warp): lanes 0..13 own the y samples, lanes 16..29 the x samples ----------------
-template <int P, int SLOTB>
+// ---- per-RoI geometry (one whole warp): lanes 0..13 own the y samples, lanes 16..29 the x samples ------------------
+template <int P>
 MD_DEVINL int cl_build_item(ClItem &it, ClBuild &bs, const RoiFeat &f, int tma_mask, const float *__restrict__ rois5, int r,
-                            int chunk, int lane)
+                            int slot_bytes, int lane)
 {
     constexpr int S = 2, NS = P * S;
     static_assert(NS <= 16, "one half-warp per axis");
@@ -157,6 +163,7 @@ MD_DEVINL int cl_build_item(ClItem &it, ClBuild &bs, const RoiFeat &f, int tma_m
 
     float *ew = &bs.ew[0][0];
     for (int i = lane; i < kClRows * 8; i += 32) ew[i] = 0.0f;
+    it.yof[lane] = 0;
     __syncwarp();
     if (is_y && ok) { it.yof[idx_lo] = lo; it.yof[idx_hi] = hi; }
     if (!is_y) {
@@ -178,13 +185,13 @@ MD_DEVINL int cl_build_item(ClItem &it, ClBuild &bs, const RoiFeat &f, int tma_m
         const int lo0 = __shfl_sync(0xffffffffu, idx_lo, 2 * p), lo1 = __shfl_sync(0xffffffffu, idx_lo, 2 * p + 1);
         const int hi0 = __shfl_sync(0xffffffffu, idx_hi, 2 * p), hi1 = __shfl_sync(0xffffffffu, idx_hi, 2 * p + 1);
         const int tot1 = __shfl_sync(0xffffffffu, tot, 2 * p + 1);
-        if (lane < P) {
-            const int ja = ok0 ? lo0 : (ok1 ? lo1 : tot1), jb = ok1 ? hi1 + 1 : (ok0 ? hi0 + 1 : tot1);
+        if (lane < 8) {
+            const int ja = lane < P ? (ok0 ? lo0 : (ok1 ? lo1 : tot1)) : 0, jb = lane < P ? (ok1 ? hi1 + 1 : (ok0 ? hi0 + 1 : tot1)) : 0;
             bs.ja[lane] = ja; bs.jb[lane] = jb;
             ClBin bn;
             bn.ja = ja; bn.nr = jb - ja; bn.pad0 = bn.pad1 = 0;
 #pragma unroll
-            for (int i = 0; i < 4; i++) bn.w[i] = ja + i < jb ? bs.ew[ja + i][lane] : 0.0f;
+            for (int i = 0; i < 4; i++) bn.w[i] = (lane < P && ja + i < jb) ? bs.ew[ja + i][lane] : 0.0f;
             it.bin[lane] = bn;
         }
     }
@@ -194,9 +201,11 @@ MD_DEVINL int cl_build_item(ClItem &it, ClBuild &bs, const RoiFeat &f, int tma_m
     const unsigned runmask = __ballot_sync(0xffffffffu, lane + 1 < nrows && it.yof[min(lane + 1, 31)] == it.yof[lane] + 1);
     {
         const int ch = lane >> 3, q = lane & 7;
+        ClTap t;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { t.o[i] = 0; t.w[i] = 0.0f; }
         if (ch < nxc && q < P) {
             const int qa = ch * nq / nxc, c0 = 4 * qa, c1 = 4 * ((ch + 1) * nq / nxc);
-            ClTap t;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int sx = q * S + (i >> 1);
@@ -206,14 +215,14 @@ MD_DEVINL int cl_build_item(ClItem &it, ClBuild &bs, const RoiFeat &f, int tma_m
                 t.o[i] = in ? (col - c0) * 128 : 0;
                 t.w[i] = in ? w : 0.0f;
             }
-            it.tap[ch][q] = t;
         }
+        it.tap[ch][q] = t;
     }
-    // pieces: per column chunk, as many whole bins as fit one stage slot (uniform; lane 0 writes)
-    const int maxrows = min(kClRows, SLOTB / cl_row_bytes(nqc_max));
-    int k = 0;
-    for (int ch = 0; ch < nxc; ch++) {
-        const int qa = ch * nq / nxc, nqc = (ch + 1) * nq / nxc - qa;
+    // pieces: as many whole bins as fit one stage slot, the same bin ranges for every column chunk; the rows of a piece
+    // travel as bulk-tensor operations of 8 / 4 / 2 / 1 consecutive feature rows (uniform code; lane 0 writes)
+    const int maxrows = min(kClRows, slot_bytes / cl_row_bytes(nqc_max));
+    int k = 0, nop = 0;
+    {
         int p = 0;
         while (p < P) {
             const int jA = bs.ja[p];
@@ -221,37 +230,69 @@ MD_DEVINL int cl_build_item(ClItem &it, ClBuild &bs, const RoiFeat &f, int tma_m
             const int p0 = p;
             p++;
             while (p < P && bs.jb[p] - jA <= maxrows) { jB = max(jB, bs.jb[p]); p++; }
-            if (lane == 0 && k < kClMaxPieces) {
+            const int op0 = nop;
+            int j = jA;
+            while (j < jB) {
+                const unsigned cont = ~(runmask >> j);              // first zero bit = end of the run that starts at row j
+                const int run = min(cont ? __ffs(cont) : 32, jB - j);
+                const int lr = run >= 8 ? 3 : (run >= 4 ? 2 : (run >= 2 ? 1 : 0));
+                if (lane == 0 && nop < kClMaxOps) { ClOp o; o.j = (short)j; o.lr = (short)lr; it.op[nop] = o; }
+                nop++;
+                j += 1 << lr;
+            }
+            for (int ch = 0; ch < nxc; ch++) {
+                const int kk = ch * 8 + k;                             // provisional slot: compacted below
+                (void)kk;
+            }
+            if (lane == 0 && k < 8) {
                 ClPiece pc;
-                pc.x0 = x_lo + 4 * qa; pc.nqc = nqc; pc.jA = jA; pc.rows = jB - jA; pc.p0 = p0; pc.p1 = p; pc.chunk = ch; pc.first = ch == 0;
-                it.piece[k] = pc;
+                pc.x0 = 0; pc.nqc = 0; pc.jA = jA; pc.rows = jB - jA; pc.p0 = p0; pc.p1 = p; pc.chunk = 0; pc.ops = op0 | ((nop - op0) << 16);
+                it.piece[k] = pc;                                      // chunk 0 first; the other chunks are copies (below)
             }
             k++;
         }
     }
-    if (k > kClMaxPieces) return CL_DECLINE;                          // (wide AND tall: left to the gather kernel)
+    if (k * nxc > kClMaxPieces || nop > kClMaxOps || k > 7) return CL_DECLINE;   // (wide AND tall: left to the gather kernel)
+    __syncwarp();
+    // chunk-major piece list: piece[ch * k + i]
+    for (int idx = lane; idx < k * nxc; idx += 32) {
+        const int ch = idx / k, i = idx - ch * k;
+        ClPiece pc = it.piece[i];
+        const int qa = ch * nq / nxc;
+        pc.x0 = x_lo + 4 * qa; pc.nqc = (ch + 1) * nq / nxc - qa; pc.chunk = ch;
+        __syncwarp(__activemask());
+        it.piece[idx] = pc;
+    }
     if (lane == 0) {
-        it.r = r; it.chunk = chunk; it.b = g.b; it.l = g.l; it.x_lo = x_lo; it.nq = nq; it.nrows = nrows;
-        it.npiece = k; it.nxc = nxc; it.runmask = runmask;
+        it.status = CL_OK; it.b = g.b; it.l = g.l; it.x_lo = x_lo; it.nq = nq; it.nrows = nrows; it.npiece = k * nxc; it.nxc = nxc;
     }
     __syncwarp();
     return CL_OK;
 }
 
-
-// Rows [jA, jA + rows) of a piece as bulk-tensor operations of 8 / 4 / 2 / 1 consecutive feature rows.  fn(j, lr): rows
-// j .. j + (1 << lr) - 1.  Uniform over the warp; the caller elects the issuing lane.
-template <class Fn>
-MD_DEVINL void cl_for_row_ops(unsigned runmask, int jA, int rows, Fn fn)
+// one warp per RoI -> items[r] (global); flags[r] = 1 for the RoIs left to the gather kernels
+constexpr int kPlanWarps = 4;
+template <int P>
+__global__ void __launch_bounds__(32 * kPlanWarps)
+roialign_plan_kernel(const RoiFeat f, const int tma_mask, const float *__restrict__ rois5, const int R, const int slot_bytes,
+                     ClItem *__restrict__ items, int32_t *__restrict__ flag)
 {
-    int j = jA;
-    const int jB = jA + rows;
-    while (j < jB) {
-        const unsigned cont = ~(runmask >> j);                  // first zero bit = end of the run that starts at row j
-        const int run = min(cont ? __ffs(cont) : 32, jB - j);
-        const int lr = run >= 8 ? 3 : (run >= 4 ? 2 : (run >= 2 ? 1 : 0));
-        fn(j, lr);
-        j += 1 << lr;
+    __shared__ ClItem its[kPlanWarps];
+    __shared__ ClBuild bld[kPlanWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kPlanWarps + warp;
+    if (r >= R) return;
+    ClItem &it = its[warp];
+    const int st = cl_build_item<P>(it, bld[warp], f, tma_mask, rois5, r, slot_bytes, lane);
+    if (st != CL_OK && lane == 0) it.status = st;
+    if (lane == 0) flag[r] = st == CL_DECLINE ? 1 : 0;
+    __syncwarp();
+    const uint4 *src = reinterpret_cast<const uint4 *>(&it);
+    uint4 *dst = reinterpret_cast<uint4 *>(items + r);
+    if (st == CL_OK) {
+        for (int i = lane; i < (int)(sizeof(ClItem) / 16); i += 32) dst[i] = src[i];
+    } else if (lane == 0) {
+        items[r].status = st;
     }
 }
 
@@ -268,10 +309,12 @@ MD_DEVINL void cl_lane_offsets(uint32_t (&off)[NQ], uint32_t (&col)[NQ], int lan
     }
 }
 
-// ---- forward piece: bin by bin, straight-line ---------------------------------------------------------------------
-// Bin p needs at most 4 staged rows: A[x] = sum_i w_i row_i[x] (y-step, registers), the lane parks its 4*NQ column sums
+// ---- forward piece: bin by bin, software-pipelined ----------------------------------------------------------------
+// Bin p needs at most 4 staged rows: A[x] = sum_i w_i row_i[x] (y-step, registers); the lane parks its 4*NQ column sums
 // in its private scratch column, and the x-step reads back just the 4 taps of each output q:
 // Out[p][q] (+)= sum_i w_i A[col_i] -> staging tile (stride 49 floats per lane: conflict-free).
+// The shared-memory accesses are volatile asm, so they stay in program order; the loop is arranged so that the row loads
+// of bin p+1 are in flight during the x-step of bin p and every batch of loads is issued before its first use.
 template <int NQ>
 MD_DEVINL void cl_fwd_piece(const ClItem &it, const ClTap (&tp)[kClP], uint32_t slot, uint32_t stg, uint32_t scr, int p0, int p1,
                             int jA, bool first, int lane)
@@ -283,80 +326,108 @@ MD_DEVINL void cl_fwd_piece(const ClItem &it, const ClTap (&tp)[kClP], uint32_t 
     const uint32_t bins = smem_u32(&it.bin[0]);
     const uint32_t so = stg + (uint32_t)lane * (P * P * 4), sl = scr + (uint32_t)lane * 4u;
 #pragma unroll 1
-    for (int p = p0; p < p1; p++) {
-        const uint4 bi = lds128(bins + 32u * p);
-        const float4 bw = lds128f(bins + 32u * p + 16u);
-        const int nr = (int)bi.y;
-        const uint32_t ra = slot + (uint32_t)((int)bi.x - jA) * RB;
-        float A[X];
-        if (nr > 0) {
-            float4 v0[NQ], v1[NQ];
+    for (int p = p0 - 1; p < p1; p++) {
+        const bool nxt = p + 1 < p1;
+        // (a) rows of bin p + 1
+        int nr = 0;
+        float4 bw = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float4 v0[NQ], v1[NQ], v2[NQ], v3[NQ];
+        if (nxt) {
+            const uint4 bi = lds128(bins + 32u * (p + 1));
+            bw = lds128f(bins + 32u * (p + 1) + 16u);
+            nr = (int)bi.y;
+            const uint32_t ra = slot + (uint32_t)((int)bi.x - jA) * RB;
+            if (nr > 0) {
 #pragma unroll
-            for (int k = 0; k < NQ; k++) { v0[k] = lds128f(ra + off[k]); v1[k] = lds128f(ra + (nr > 1 ? RB : 0u) + off[k]); }
+                for (int k = 0; k < NQ; k++) { v0[k] = lds128f(ra + off[k]); v1[k] = lds128f(ra + (nr > 1 ? RB : 0u) + off[k]); }
+            }
+            if (nr > 2) {
 #pragma unroll
-            for (int k = 0; k < NQ; k++) {
-                A[4 * k] = __fmaf_rn(bw.y, v1[k].x, mul(bw.x, v0[k].x)); A[4 * k + 1] = __fmaf_rn(bw.y, v1[k].y, mul(bw.x, v0[k].y));
-                A[4 * k + 2] = __fmaf_rn(bw.y, v1[k].z, mul(bw.x, v0[k].z)); A[4 * k + 3] = __fmaf_rn(bw.y, v1[k].w, mul(bw.x, v0[k].w));
+                for (int k = 0; k < NQ; k++) v2[k] = lds128f(ra + 2u * RB + off[k]);
+            }
+            if (nr > 3) {
+#pragma unroll
+                for (int k = 0; k < NQ; k++) v3[k] = lds128f(ra + 3u * RB + off[k]);
+            }
+        }
+        // (b, c) x-step of bin p from the scratch column parked one iteration ago
+        if (p >= p0) {
+            const uint32_t oa = so + (uint32_t)p * (P * 4);
+            float t[P][4], old[P];
+#pragma unroll
+            for (int q = 0; q < P; q++) {
+                t[q][0] = lds32f(sl + tp[q].o[0]); t[q][1] = lds32f(sl + tp[q].o[1]);
+                t[q][2] = lds32f(sl + tp[q].o[2]); t[q][3] = lds32f(sl + tp[q].o[3]);
+            }
+            if (!first) {
+#pragma unroll
+                for (int q = 0; q < P; q++) old[q] = lds32f(oa + 4 * q);
+            }
+#pragma unroll
+            for (int q = 0; q < P; q++) {
+                float acc = mul(tp[q].w[0], t[q][0]);
+                acc = __fmaf_rn(tp[q].w[1], t[q][1], acc);
+                acc = __fmaf_rn(tp[q].w[2], t[q][2], acc);
+                acc = __fmaf_rn(tp[q].w[3], t[q][3], acc);
+                if (!first) acc = add(acc, old[q]);
+                sts32f(oa + 4 * q, acc);
+            }
+        }
+        // (d, e) y-step of bin p + 1, parked for the next iteration
+        if (nxt) {
+            float A[X];
+            if (nr > 0) {
+#pragma unroll
+                for (int k = 0; k < NQ; k++) {
+                    A[4 * k] = __fmaf_rn(bw.y, v1[k].x, mul(bw.x, v0[k].x)); A[4 * k + 1] = __fmaf_rn(bw.y, v1[k].y, mul(bw.x, v0[k].y));
+                    A[4 * k + 2] = __fmaf_rn(bw.y, v1[k].z, mul(bw.x, v0[k].z)); A[4 * k + 3] = __fmaf_rn(bw.y, v1[k].w, mul(bw.x, v0[k].w));
+                }
+            } else {
+#pragma unroll
+                for (int x = 0; x < X; x++) A[x] = 0.0f;
             }
             if (nr > 2) {
 #pragma unroll
                 for (int k = 0; k < NQ; k++) {
-                    const float4 v = lds128f(ra + 2u * RB + off[k]);
-                    A[4 * k] = __fmaf_rn(bw.z, v.x, A[4 * k]); A[4 * k + 1] = __fmaf_rn(bw.z, v.y, A[4 * k + 1]);
-                    A[4 * k + 2] = __fmaf_rn(bw.z, v.z, A[4 * k + 2]); A[4 * k + 3] = __fmaf_rn(bw.z, v.w, A[4 * k + 3]);
+                    A[4 * k] = __fmaf_rn(bw.z, v2[k].x, A[4 * k]); A[4 * k + 1] = __fmaf_rn(bw.z, v2[k].y, A[4 * k + 1]);
+                    A[4 * k + 2] = __fmaf_rn(bw.z, v2[k].z, A[4 * k + 2]); A[4 * k + 3] = __fmaf_rn(bw.z, v2[k].w, A[4 * k + 3]);
                 }
             }
             if (nr > 3) {
 #pragma unroll
                 for (int k = 0; k < NQ; k++) {
-                    const float4 v = lds128f(ra + 3u * RB + off[k]);
-                    A[4 * k] = __fmaf_rn(bw.w, v.x, A[4 * k]); A[4 * k + 1] = __fmaf_rn(bw.w, v.y, A[4 * k + 1]);
-                    A[4 * k + 2] = __fmaf_rn(bw.w, v.z, A[4 * k + 2]); A[4 * k + 3] = __fmaf_rn(bw.w, v.w, A[4 * k + 3]);
+                    A[4 * k] = __fmaf_rn(bw.w, v3[k].x, A[4 * k]); A[4 * k + 1] = __fmaf_rn(bw.w, v3[k].y, A[4 * k + 1]);
+                    A[4 * k + 2] = __fmaf_rn(bw.w, v3[k].z, A[4 * k + 2]); A[4 * k + 3] = __fmaf_rn(bw.w, v3[k].w, A[4 * k + 3]);
                 }
             }
-        } else {
 #pragma unroll
-            for (int x = 0; x < X; x++) A[x] = 0.0f;
-        }
-#pragma unroll
-        for (int k = 0; k < NQ; k++) {
-            sts32f(sl + col[k], A[4 * k]); sts32f(sl + col[k] + 128u, A[4 * k + 1]);
-            sts32f(sl + col[k] + 256u, A[4 * k + 2]); sts32f(sl + col[k] + 384u, A[4 * k + 3]);
-        }
-        // x-step: every tap load first (the shared-memory accesses are volatile asm and keep their order: interleaving
-        // loads with the stores below would expose one shared-memory round trip per output)
-        const uint32_t oa = so + (uint32_t)p * (P * 4);
-        float t[P][4], old[P];
-#pragma unroll
-        for (int q = 0; q < P; q++) {
-            t[q][0] = lds32f(sl + tp[q].o[0]); t[q][1] = lds32f(sl + tp[q].o[1]);
-            t[q][2] = lds32f(sl + tp[q].o[2]); t[q][3] = lds32f(sl + tp[q].o[3]);
-        }
-        if (!first) {
-#pragma unroll
-            for (int q = 0; q < P; q++) old[q] = lds32f(oa + 4 * q);
-        }
-#pragma unroll
-        for (int q = 0; q < P; q++) {
-            float acc = mul(tp[q].w[0], t[q][0]);
-            acc = __fmaf_rn(tp[q].w[1], t[q][1], acc);
-            acc = __fmaf_rn(tp[q].w[2], t[q][2], acc);
-            acc = __fmaf_rn(tp[q].w[3], t[q][3], acc);
-            if (!first) acc = add(acc, old[q]);
-            sts32f(oa + 4 * q, acc);
+            for (int k = 0; k < NQ; k++) {
+                sts32f(sl + col[k], A[4 * k]); sts32f(sl + col[k] + 128u, A[4 * k + 1]);
+                sts32f(sl + col[k] + 256u, A[4 * k + 2]); sts32f(sl + col[k] + 384u, A[4 * k + 3]);
+            }
         }
     }
 }
 
+// ---- the item stream shared by the forward and the backward kernel ------------------------------------------------
+// A persistent 1-warp CTA takes (RoI, channel chunk) items from a global ticket (the NEXT ticket is requested while the
+// current item is being worked on), pulls each item's table into one of two shared-memory buffers with a bulk copy, and
+// walks three cursors over the same item sequence: l (tables requested) >= p (producer) >= c (consumer), l <= c + 2.
+struct ClStream {
+    int l_seq, p_seq, c_seq;
+    int tick_next;
+    bool exhausted;
+    int tr[2], tc[2];                       // RoI / channel chunk of the items in the two table buffers
+};
+
 constexpr int kClStgBytes = 6400;           // 32 x 49 floats, padded
 constexpr int kClScrBytes = 2048;           // 16 columns x 32 lanes
-constexpr size_t kClSmemBytes = 1024 + (size_t)kClSlots * kClSlotBytes + kClStgBytes + kClScrBytes + 2 * sizeof(ClItem) + sizeof(ClBuild) + 64;
+constexpr size_t kClSmemBytes = 1024 + (size_t)kClSlots * kClSlotBytes + kClStgBytes + kClScrBytes + 2 * sizeof(ClItem) + 64;
 
 template <int P>
 __global__ void __launch_bounds__(32, MD_CL_CTAS)
-roialign_fwd_cl_kernel(const __grid_constant__ ClMaps maps, const RoiFeat f, const int tma_mask,
-                       const float *__restrict__ rois5, const int R, const int seg, const int nchunk,
-                       float *__restrict__ out, int32_t *__restrict__ flag, int *__restrict__ ctr)
+roialign_fwd_cl_kernel(const __grid_constant__ ClMaps maps, const ClItem *__restrict__ items, const int R, const int C,
+                       const int seg, const int nchunk, float *__restrict__ out, int *__restrict__ ctr)
 {
     static_assert(P == kClP, "7x7 only");
     extern __shared__ unsigned char dsm_raw[];
@@ -365,85 +436,110 @@ roialign_fwd_cl_kernel(const __grid_constant__ ClMaps maps, const RoiFeat f, con
     unsigned char *stgp = sp; sp += kClStgBytes;
     unsigned char *scrp = sp; sp += kClScrBytes;
     ClItem *tabs = reinterpret_cast<ClItem *>(sp); sp += 2 * sizeof(ClItem);
-    ClBuild *bld = reinterpret_cast<ClBuild *>(sp); sp += sizeof(ClBuild);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(sp);
+    unsigned long long *tfull = full + kClSlots;
 
     const int lane = threadIdx.x;
-    const int C = f.C, CH = C / nchunk, ngroups = CH / 32;
+    const int CH = C / nchunk, ngroups = CH / 32;
     const int total = R * nchunk;
     if (lane == 0) {
         for (int i = 0; i < kClSlots; i++) mbar_init(&full[i], 1);
+        mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
         fence_barrier_init();
     }
     __syncwarp();
     const uint32_t stg = smem_u32(stgp), scr = smem_u32(scrp);
 
-    // the warp is producer (takes items from the ticket, builds their tables, issues the TMA loads up to kClSlots pieces
-    // ahead) and consumer (one staged piece at a time)
-    int p_seq = 0, c_seq = 0;                 // sequence numbers (of items with work) the producer / consumer are in
-    bool p_have = false, exhausted = false;
+    ClStream st;
+    st.l_seq = st.p_seq = st.c_seq = 0;
+    st.exhausted = false;
+    {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(ctr, 1);
+        st.tick_next = __shfl_sync(0xffffffffu, t, 0);
+    }
+    bool p_ready = false, c_ready = false;    // the table of item p_seq / c_seq has landed and holds work
     int p_g = 0, p_k = 0, c_g = 0, c_k = 0;
     int n_iss = 0, n_con = 0;
     int tap_seq = -1, tap_ch = -1;
     bool store_pending = false;
     ClTap tp[P];
 
-    auto fetch = [&]() {
-        for (;;) {
-            int t = 0;
-            if (lane == 0) t = atomicAdd(ctr, 1);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            if (t >= total) { exhausted = true; p_have = false; return; }
-            const WorkItem wi = work_item(t, R, seg, nchunk);
-            const int st = cl_build_item<P, kClSlotBytes>(tabs[p_seq & 1], *bld, f, tma_mask, rois5, wi.r, wi.chunk, lane);
-            if (wi.chunk == 0 && lane == 0) flag[wi.r] = st == CL_DECLINE ? 1 : 0;
-            if (st == CL_OK) { p_have = true; p_g = p_k = 0; return; }
-            if (st == CL_ZERO) {
-                float *o = out + ((int64_t)wi.r * C + (int64_t)wi.chunk * CH) * (P * P);
-                for (int i = lane; i < CH * P * P; i += 32) o[i] = 0.0f;
-            }
-        }
-    };
-
 #pragma unroll 1
     for (;;) {
+        // ---- request tables: at most two items beyond the consumer's ---------------------------------------------
+        while (!st.exhausted && st.l_seq < st.c_seq + 2) {
+            const int t = st.tick_next;
+            if (t >= total) { st.exhausted = true; break; }
+            int tn = 0;
+            if (lane == 0) tn = atomicAdd(ctr, 1);                   // the NEXT ticket: its latency hides behind this item
+            st.tick_next = __shfl_sync(0xffffffffu, tn, 0);
+            const WorkItem wi = work_item(t, R, seg, nchunk);
+            const int b = st.l_seq & 1;
+            st.tr[b] = wi.r; st.tc[b] = wi.chunk;
+            if (lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&tfull[b], (uint32_t)sizeof(ClItem));
+                bulk_load_1d(&tabs[b], items + wi.r, (uint32_t)sizeof(ClItem), &tfull[b]);
+            }
+            st.l_seq++;
+        }
+        // ---- producer: keep the stage slots full ------------------------------------------------------------------
 #pragma unroll 1
         for (;;) {
-            if (!p_have) {
-                if (exhausted || c_seq < p_seq - 1) break;       // (the consumer still reads the table this item would take)
-                fetch();
-                if (!p_have) break;
+            if (st.p_seq >= st.l_seq) break;
+            const int b = st.p_seq & 1;
+            if (!p_ready) {
+                mbar_wait(&tfull[b], (uint32_t)(st.p_seq >> 1) & 1u);
+                if (tabs[b].status != CL_OK) { st.p_seq++; continue; }   // no pieces (the consumer writes the zeros)
+                p_ready = true; p_g = p_k = 0;
             }
             if (n_iss - n_con >= kClSlots) break;
-            const ClItem &it = tabs[p_seq & 1];
+            const ClItem &it = tabs[b];
             const ClPiece pc = it.piece[p_k];
             const int slot = n_iss % kClSlots;
             const int rb = 512 * pc.nqc;
-            fence_proxy_async();
-            if (lane == 0) mbar_expect_tx(&full[slot], (uint32_t)(pc.rows * rb));
-            __syncwarp();
             if (lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&full[slot], (uint32_t)(pc.rows * rb));
                 const CUtensorMap *mp = &maps.m[(it.l * 4 + pc.nqc - 1) * kClRsel];
-                const int z = it.b * C + it.chunk * CH + 32 * p_g;
+                const int z = it.b * C + st.tc[b] * CH + 32 * p_g;
                 unsigned char *dst = slots + slot * kClSlotBytes - pc.jA * rb;
-                cl_for_row_ops(it.runmask, pc.jA, pc.rows, [&](int j, int lr) {
-                    tma_load_3d(dst + j * rb, mp + lr, pc.x0, z, it.yof[j], &full[slot]);
-                });
+                const int op0 = pc.ops & 0xffff, nop = pc.ops >> 16;
+                for (int o = op0; o < op0 + nop; o++) {
+                    const ClOp op = it.op[o];
+                    tma_load_3d(dst + op.j * rb, mp + op.lr, pc.x0, z, it.yof[op.j], &full[slot]);
+                }
             }
             n_iss++;
             if (++p_k == it.npiece) {
                 p_k = 0;
-                if (++p_g == ngroups) { p_have = false; p_seq++; }
+                if (++p_g == ngroups) { p_ready = false; st.p_seq++; }
             }
         }
-        if (n_con == n_iss) break;
-        // ---- consume one staged piece -----------------------------------------------------------------------------
-        const ClItem &it = tabs[c_seq & 1];
+        // ---- consumer -----------------------------------------------------------------------------------------------
+        if (st.c_seq >= st.l_seq) break;                         // every ticket taken, every item done
+        const int cb = st.c_seq & 1;
+        if (!c_ready) {
+            mbar_wait(&tfull[cb], (uint32_t)(st.c_seq >> 1) & 1u);
+            const int status = tabs[cb].status;
+            if (status != CL_OK) {
+                if (status == CL_ZERO) {
+                    float *o = out + ((int64_t)st.tr[cb] * C + (int64_t)st.tc[cb] * CH) * (P * P);
+                    for (int i = lane; i < CH * P * P; i += 32) o[i] = 0.0f;
+                }
+                __syncwarp();
+                st.c_seq++;
+                continue;
+            }
+            c_ready = true; c_g = c_k = 0;
+        }
+        const ClItem &it = tabs[cb];
         const ClPiece pc = it.piece[c_k];
-        if (tap_seq != c_seq || tap_ch != pc.chunk) {
+        if (tap_seq != st.c_seq || tap_ch != pc.chunk) {
 #pragma unroll
             for (int q = 0; q < P; q++) tp[q] = it.tap[pc.chunk][q];
-            tap_seq = c_seq; tap_ch = pc.chunk;
+            tap_seq = st.c_seq; tap_ch = pc.chunk;
         }
         if (store_pending && c_k == 0) {                         // the staging tile is about to be overwritten
             if (lane == 0) bulk_wait_read<0>();
@@ -454,10 +550,10 @@ roialign_fwd_cl_kernel(const __grid_constant__ ClMaps maps, const RoiFeat f, con
         mbar_wait(&full[slot], (uint32_t)(n_con / kClSlots) & 1u);
         const uint32_t sa = smem_u32(slots + slot * kClSlotBytes);
         switch (pc.nqc) {
-            case 1: cl_fwd_piece<1>(it, tp, sa, stg, scr, pc.p0, pc.p1, pc.jA, pc.first != 0, lane); break;
-            case 2: cl_fwd_piece<2>(it, tp, sa, stg, scr, pc.p0, pc.p1, pc.jA, pc.first != 0, lane); break;
-            case 3: cl_fwd_piece<3>(it, tp, sa, stg, scr, pc.p0, pc.p1, pc.jA, pc.first != 0, lane); break;
-            default: cl_fwd_piece<4>(it, tp, sa, stg, scr, pc.p0, pc.p1, pc.jA, pc.first != 0, lane); break;
+            case 1: cl_fwd_piece<1>(it, tp, sa, stg, scr, pc.p0, pc.p1, pc.jA, pc.chunk == 0, lane); break;
+            case 2: cl_fwd_piece<2>(it, tp, sa, stg, scr, pc.p0, pc.p1, pc.jA, pc.chunk == 0, lane); break;
+            case 3: cl_fwd_piece<3>(it, tp, sa, stg, scr, pc.p0, pc.p1, pc.jA, pc.chunk == 0, lane); break;
+            default: cl_fwd_piece<4>(it, tp, sa, stg, scr, pc.p0, pc.p1, pc.jA, pc.chunk == 0, lane); break;
         }
         __syncwarp();
         n_con++;
@@ -466,14 +562,14 @@ roialign_fwd_cl_kernel(const __grid_constant__ ClMaps maps, const RoiFeat f, con
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                bulk_store_1d(out + ((int64_t)it.r * C + it.chunk * CH + 32 * c_g) * (P * P), stgp, kClStageBytes);
+                bulk_store_1d(out + ((int64_t)st.tr[cb] * C + st.tc[cb] * CH + 32 * c_g) * (P * P), stgp, kClStageBytes);
                 bulk_commit();
             }
             store_pending = true;
         }
         if (++c_k == npiece) {
             c_k = 0;
-            if (++c_g == ngroups) { c_g = 0; c_seq++; }
+            if (++c_g == ngroups) { c_ready = false; st.c_seq++; }
         }
     }
     if (lane == 0) {
@@ -484,25 +580,34 @@ roialign_fwd_cl_kernel(const __grid_constant__ ClMaps maps, const RoiFeat f, con
     }
 }
 
-// dense Ax[q][16] of one column chunk (columns [4*qa, 4*qa + 4*nqc) of the footprint) -- the backward's x operator
-MD_DEVINL void cl_build_ax(float *axw, const ClItem &it, int qa, int nqc, int lane)
+// dense Ax of one column chunk in the lane's (rotated) quad order, in registers: ax[q][4k + i] = Ax[q][4 quad(k) + i]
+template <int NQ>
+MD_DEVINL void cl_load_ax(float (&ax)[kClP][4 * NQ], const ClItem &it, int chunk, int lane)
 {
     constexpr int P = kClP, S = 2;
+    const int nq = it.nq, nxc = it.nxc;
+    const int c0 = 4 * (chunk * nq / nxc);
+    const int rot = cl_rot(NQ, lane);
 #pragma unroll
-    for (int i = 0; i < 4; i++) axw[lane + 32 * i] = 0.0f;          // 7 x 16 = 112 floats (128 reserved)
-    __syncwarp();
-    const int c0 = 4 * qa, c1 = c0 + 4 * nqc;
+    for (int q = 0; q < P; q++) {
 #pragma unroll
-    for (int ph = 0; ph < S; ph++) {
-        if (lane < P) {
-            const int s = lane * S + ph;
-            const int lo = it.xlo[s], hi = it.xhi[s];
+        for (int x = 0; x < 4 * NQ; x++) ax[q][x] = 0.0f;
+#pragma unroll
+        for (int ph = 0; ph < S; ph++) {
+            const int s = q * S + ph;
+            const int lo = it.xlo[s] - c0, hi = it.xhi[s] - c0;
             const float wl = it.xwl[s], wh = it.xwh[s];
-            if (lo >= c0 && lo < c1) axw[lane * 16 + lo - c0] += wl;
-            if (hi >= c0 && hi < c1) axw[lane * 16 + hi - c0] += wh;
+#pragma unroll
+            for (int k = 0; k < NQ; k++) {
+                const int base = 4 * ((k + rot) % NQ);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (lo == base + i) ax[q][4 * k + i] = add(ax[q][4 * k + i], wl);
+                    if (hi == base + i) ax[q][4 * k + i] = add(ax[q][4 * k + i], wh);
+                }
+            }
         }
     }
-    __syncwarp();
 }
 
 // =====================================================================================================
@@ -516,20 +621,20 @@ MD_DEVINL void cl_build_ax(float *axw, const ClItem &it, int qa, int nqc, int la
 #endif
 constexpr int kClbSlotBytes = MD_CLB_SLOT_KB * 1024;
 constexpr int kClbGBufBytes = 6400;
-constexpr size_t kClbSmemBytes = 1024 + (size_t)kClSlots * kClbSlotBytes + 2 * kClbGBufBytes + 512 + 2 * sizeof(ClItem) + sizeof(ClBuild) + 64;
+constexpr size_t kClbSmemBytes = 1024 + (size_t)kClSlots * kClbSlotBytes + 2 * kClbGBufBytes + 2 * sizeof(ClItem) + 64;
 
-// one piece, bin by bin: T[x] = sum_q dY[p][q] Ax[q][x] (registers), then the bin's <= 4 rows of the slot += w_i T
-// (the rows of a piece are zeroed first; the lane owns its channel's bytes of every row, so plain read-modify-write)
+// one piece, bin by bin: T[x] = sum_q dY[p][q] Ax[q][x] (registers, Ax register-resident), then the bin's <= 4 rows of
+// the slot += w_i T (the rows of a piece are zeroed first; the lane owns its channel's bytes of every row, so plain
+// read-modify-write; loads of row i+1 are issued before the stores of row i)
 template <int NQ>
-MD_DEVINL void cl_bwd_piece(const ClItem &it, uint32_t slot, uint32_t gbuf, uint32_t axw, int p0, int p1, int jA, int rows, int lane)
+MD_DEVINL void cl_bwd_piece(const ClItem &it, const float (&ax)[kClP][4 * NQ], uint32_t slot, uint32_t gbuf, int p0, int p1,
+                            int jA, int rows, int lane)
 {
     constexpr int P = kClP, X = 4 * NQ;
     constexpr uint32_t RB = (uint32_t)cl_row_bytes(NQ);
     uint32_t off[NQ];
 #pragma unroll
     for (int k = 0; k < NQ; k++) off[k] = (uint32_t)(lane * cl_pitch(NQ) + 16 * ((k + cl_rot(NQ, lane)) % NQ));
-    // Ax in the lane's (rotated) quad order: ax[q][4k + i] = Ax[q][4 * quad(k) + i]
-    const int rot = cl_rot(NQ, lane);
 #pragma unroll 1
     for (int j = 0; j < rows; j++)
 #pragma unroll
@@ -542,154 +647,198 @@ MD_DEVINL void cl_bwd_piece(const ClItem &it, uint32_t slot, uint32_t gbuf, uint
         const float4 bw = lds128f(bins + 32u * p + 16u);
         const int nr = (int)bi.y;
         if (nr <= 0) continue;
+        const uint32_t ga = go + (uint32_t)p * (P * 4);
+        float g[P];
+#pragma unroll
+        for (int q = 0; q < P; q++) g[q] = lds32f(ga + 4 * q);
+        const uint32_t ra = slot + (uint32_t)((int)bi.x - jA) * RB;
+        float4 d0[NQ], d1[NQ];
+#pragma unroll
+        for (int k = 0; k < NQ; k++) { d0[k] = lds128f(ra + off[k]); d1[k] = lds128f(ra + (nr > 1 ? RB : 0u) + off[k]); }
         float T[X];
 #pragma unroll
-        for (int x = 0; x < X; x++) T[x] = 0.0f;
-        const uint32_t ga = go + (uint32_t)p * (P * 4);
+        for (int x = 0; x < X; x++) {
+            float acc = mul(g[0], ax[0][x]);
 #pragma unroll
-        for (int q = 0; q < P; q++) {
-            const float g = lds32f(ga + 4 * q);
+            for (int q = 1; q < P; q++) acc = __fmaf_rn(g[q], ax[q][x], acc);
+            T[x] = acc;
+        }
+        float4 d2[NQ], d3[NQ];
+        if (nr > 2) {
+#pragma unroll
+            for (int k = 0; k < NQ; k++) d2[k] = lds128f(ra + 2u * RB + off[k]);
+        }
+        if (nr > 3) {
+#pragma unroll
+            for (int k = 0; k < NQ; k++) d3[k] = lds128f(ra + 3u * RB + off[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < NQ; k++) {
+            d0[k].x = __fmaf_rn(bw.x, T[4 * k], d0[k].x); d0[k].y = __fmaf_rn(bw.x, T[4 * k + 1], d0[k].y);
+            d0[k].z = __fmaf_rn(bw.x, T[4 * k + 2], d0[k].z); d0[k].w = __fmaf_rn(bw.x, T[4 * k + 3], d0[k].w);
+            sts128f(ra + off[k], d0[k]);
+        }
+        if (nr > 1) {
 #pragma unroll
             for (int k = 0; k < NQ; k++) {
-                const float4 a = lds128f(axw + (uint32_t)(q * 16 + 4 * ((k + rot) % NQ)) * 4u);
-                T[4 * k] = __fmaf_rn(g, a.x, T[4 * k]); T[4 * k + 1] = __fmaf_rn(g, a.y, T[4 * k + 1]);
-                T[4 * k + 2] = __fmaf_rn(g, a.z, T[4 * k + 2]); T[4 * k + 3] = __fmaf_rn(g, a.w, T[4 * k + 3]);
+                d1[k].x = __fmaf_rn(bw.y, T[4 * k], d1[k].x); d1[k].y = __fmaf_rn(bw.y, T[4 * k + 1], d1[k].y);
+                d1[k].z = __fmaf_rn(bw.y, T[4 * k + 2], d1[k].z); d1[k].w = __fmaf_rn(bw.y, T[4 * k + 3], d1[k].w);
+                sts128f(ra + RB + off[k], d1[k]);
             }
         }
-        const uint32_t ra = slot + (uint32_t)((int)bi.x - jA) * RB;
-        const float w[4] = { bw.x, bw.y, bw.z, bw.w };
-        // all loads, then all FMAs, then all stores (volatile shared-memory accesses keep their order)
-        float4 d[4][NQ];
+        if (nr > 2) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (i < nr) {
-#pragma unroll
-                for (int k = 0; k < NQ; k++) d[i][k] = lds128f(ra + (uint32_t)i * RB + off[k]);
+            for (int k = 0; k < NQ; k++) {
+                d2[k].x = __fmaf_rn(bw.z, T[4 * k], d2[k].x); d2[k].y = __fmaf_rn(bw.z, T[4 * k + 1], d2[k].y);
+                d2[k].z = __fmaf_rn(bw.z, T[4 * k + 2], d2[k].z); d2[k].w = __fmaf_rn(bw.z, T[4 * k + 3], d2[k].w);
+                sts128f(ra + 2u * RB + off[k], d2[k]);
             }
         }
+        if (nr > 3) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (i < nr) {
-#pragma unroll
-                for (int k = 0; k < NQ; k++) {
-                    d[i][k].x = __fmaf_rn(w[i], T[4 * k], d[i][k].x); d[i][k].y = __fmaf_rn(w[i], T[4 * k + 1], d[i][k].y);
-                    d[i][k].z = __fmaf_rn(w[i], T[4 * k + 2], d[i][k].z); d[i][k].w = __fmaf_rn(w[i], T[4 * k + 3], d[i][k].w);
-                    sts128f(ra + (uint32_t)i * RB + off[k], d[i][k]);
-                }
+            for (int k = 0; k < NQ; k++) {
+                d3[k].x = __fmaf_rn(bw.w, T[4 * k], d3[k].x); d3[k].y = __fmaf_rn(bw.w, T[4 * k + 1], d3[k].y);
+                d3[k].z = __fmaf_rn(bw.w, T[4 * k + 2], d3[k].z); d3[k].w = __fmaf_rn(bw.w, T[4 * k + 3], d3[k].w);
+                sts128f(ra + 3u * RB + off[k], d3[k]);
             }
         }
     }
 }
 
+template <int NQ>
+MD_DEVINL void cl_bwd_chunk(const ClItem &it, int chunk, int k0, int k1, uint32_t gbuf, unsigned char *slots, int &n_piece,
+                            const CUtensorMap *maps_l, int z, int lane)
+{
+    float ax[kClP][4 * NQ];
+    cl_load_ax<NQ>(ax, it, chunk, lane);
+#pragma unroll 1
+    for (int k = k0; k < k1; k++) {
+        const ClPiece pc = it.piece[k];
+        if (pc.rows <= 0) continue;
+        const int rb = 512 * NQ;
+        const int slot = n_piece % kClSlots;
+        bulk_wait_read<kClSlots - 1>();          // this lane's reduce that last read the slot has finished reading
+        __syncwarp();
+        cl_bwd_piece<NQ>(it, ax, smem_u32(slots + slot * kClbSlotBytes), gbuf, pc.p0, pc.p1, pc.jA, pc.rows, lane);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            const CUtensorMap *mp = maps_l + (NQ - 1) * kClRsel;
+            const unsigned char *src = slots + slot * kClbSlotBytes - pc.jA * rb;
+            const int op0 = pc.ops & 0xffff, nop = pc.ops >> 16;
+            for (int o = op0; o < op0 + nop; o++) {
+                const ClOp op = it.op[o];
+                tma_reduce_add_3d(mp + op.lr, pc.x0, z, it.yof[op.j], src + op.j * rb);
+            }
+        }
+        bulk_commit();
+        n_piece++;
+    }
+}
+
 template <int P>
 __global__ void __launch_bounds__(32, MD_CLB_CTAS)
-roialign_bwd_cl_kernel(const __grid_constant__ ClMaps maps, const RoiFeat f, const int tma_mask,
-                       const float *__restrict__ rois5, const int R, const int seg, const int nchunk,
-                       const float *__restrict__ dout, int32_t *__restrict__ flag, int *__restrict__ ctr)
+roialign_bwd_cl_kernel(const __grid_constant__ ClMaps maps, const ClItem *__restrict__ items, const int R, const int C,
+                       const int seg, const int nchunk, const float *__restrict__ dout, int *__restrict__ ctr)
 {
     static_assert(P == kClP, "7x7 only");
     extern __shared__ unsigned char dsm_raw[];
     unsigned char *sp = dsm_raw + ((1024u - (smem_u32(dsm_raw) & 1023u)) & 1023u);
     unsigned char *slots = sp; sp += kClSlots * kClbSlotBytes;
     unsigned char *gbufs = sp; sp += 2 * kClbGBufBytes;
-    float *axw_p = reinterpret_cast<float *>(sp); sp += 512;
     ClItem *tabs = reinterpret_cast<ClItem *>(sp); sp += 2 * sizeof(ClItem);
-    ClBuild *bld = reinterpret_cast<ClBuild *>(sp); sp += sizeof(ClBuild);
     unsigned long long *gfull = reinterpret_cast<unsigned long long *>(sp);
+    unsigned long long *tfull = gfull + 2;
 
     const int lane = threadIdx.x;
-    const int C = f.C, CH = C / nchunk, ngroups = CH / 32;
+    const int CH = C / nchunk, ngroups = CH / 32;
     const int total = R * nchunk;
     if (lane == 0) {
         mbar_init(&gfull[0], 1); mbar_init(&gfull[1], 1);
+        mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
         fence_barrier_init();
     }
     __syncwarp();
-    const uint32_t axw = smem_u32(axw_p);
 
-    // producer = the dY loads, one (item, channel group) ahead of the consumer; consumer = everything else
-    int p_seq = 0, c_seq = 0;
-    bool p_have = false, exhausted = false;
+    ClStream st;
+    st.l_seq = st.p_seq = st.c_seq = 0;
+    st.exhausted = false;
+    {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(ctr, 1);
+        st.tick_next = __shfl_sync(0xffffffffu, t, 0);
+    }
+    bool p_ready = false, c_ready = false;
     int p_g = 0, c_g = 0;
     int g_iss = 0, g_con = 0;             // dY buffers issued / released
     int n_piece = 0;                      // pieces written so far (slot ring position)
-    int ax_seq = -1, ax_xc = -1;
-
-    auto fetch = [&]() {
-        for (;;) {
-            int t = 0;
-            if (lane == 0) t = atomicAdd(ctr, 1);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            if (t >= total) { exhausted = true; p_have = false; return; }
-            const WorkItem wi = work_item(t, R, seg, nchunk);
-            const int st = cl_build_item<P, kClbSlotBytes>(tabs[p_seq & 1], *bld, f, tma_mask, rois5, wi.r, wi.chunk, lane);
-            if (wi.chunk == 0 && lane == 0) flag[wi.r] = st == CL_DECLINE ? 1 : 0;
-            if (st == CL_OK) { p_have = true; p_g = 0; return; }      // CL_ZERO: no sample in range -> no gradient
-        }
-    };
 
 #pragma unroll 1
     for (;;) {
-#pragma unroll 1
-        for (;;) {
-            if (!p_have) {
-                if (exhausted || c_seq < p_seq - 1) break;
-                fetch();
-                if (!p_have) break;
-            }
-            if (g_iss - g_con >= 2) break;
-            const ClItem &it = tabs[p_seq & 1];
-            const int b = g_iss & 1;
+        while (!st.exhausted && st.l_seq < st.c_seq + 2) {
+            const int t = st.tick_next;
+            if (t >= total) { st.exhausted = true; break; }
+            int tn = 0;
+            if (lane == 0) tn = atomicAdd(ctr, 1);
+            st.tick_next = __shfl_sync(0xffffffffu, tn, 0);
+            const WorkItem wi = work_item(t, R, seg, nchunk);
+            const int b = st.l_seq & 1;
+            st.tr[b] = wi.r; st.tc[b] = wi.chunk;
             if (lane == 0) {
                 fence_proxy_async();
-                mbar_expect_tx(&gfull[b], kClStageBytes);
-                bulk_load_1d(gbufs + b * kClbGBufBytes, dout + ((int64_t)it.r * C + it.chunk * CH + 32 * p_g) * (P * P), kClStageBytes, &gfull[b]);
+                mbar_expect_tx(&tfull[b], (uint32_t)sizeof(ClItem));
+                bulk_load_1d(&tabs[b], items + wi.r, (uint32_t)sizeof(ClItem), &tfull[b]);
+            }
+            st.l_seq++;
+        }
+        // producer = the dY loads, at most one (item, channel group) ahead of the consumer
+#pragma unroll 1
+        for (;;) {
+            if (st.p_seq >= st.l_seq) break;
+            const int b = st.p_seq & 1;
+            if (!p_ready) {
+                mbar_wait(&tfull[b], (uint32_t)(st.p_seq >> 1) & 1u);
+                if (tabs[b].status != CL_OK) { st.p_seq++; continue; }
+                p_ready = true; p_g = 0;
+            }
+            if (g_iss - g_con >= 2) break;
+            const int gb = g_iss & 1;
+            if (lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&gfull[gb], kClStageBytes);
+                bulk_load_1d(gbufs + gb * kClbGBufBytes, dout + ((int64_t)st.tr[b] * C + st.tc[b] * CH + 32 * p_g) * (P * P), kClStageBytes, &gfull[gb]);
             }
             g_iss++;
-            if (++p_g == ngroups) { p_have = false; p_seq++; }
+            if (++p_g == ngroups) { p_ready = false; st.p_seq++; }
         }
-        if (g_con == g_iss) break;
-        // ---- one (item, channel group): all its pieces ----------------------------------------------------------
-        const ClItem &it = tabs[c_seq & 1];
+        if (st.c_seq >= st.l_seq) break;
+        const int cb = st.c_seq & 1;
+        if (!c_ready) {
+            mbar_wait(&tfull[cb], (uint32_t)(st.c_seq >> 1) & 1u);
+            if (tabs[cb].status != CL_OK) { __syncwarp(); st.c_seq++; continue; }      // no sample in range / declined: no gradient here
+            c_ready = true; c_g = 0;
+        }
+        // ---- one (item, channel group): all its pieces, chunk by chunk ----------------------------------------------
+        const ClItem &it = tabs[cb];
         const int gb = g_con & 1;
         mbar_wait(&gfull[gb], (uint32_t)(g_con >> 1) & 1u);
         const uint32_t gbuf = smem_u32(gbufs + gb * kClbGBufBytes);
-        const int nq = it.nq, nxc = it.nxc, npiece = it.npiece;
-        const int z = it.b * C + it.chunk * CH + 32 * c_g;
+        const int nxc = it.nxc, per = it.npiece / nxc;
+        const int z = it.b * C + st.tc[cb] * CH + 32 * c_g;
+        const CUtensorMap *maps_l = &maps.m[it.l * 4 * kClRsel];
 #pragma unroll 1
-        for (int k = 0; k < npiece; k++) {
-            const ClPiece pc = it.piece[k];
-            if (pc.rows <= 0) continue;
-            if (ax_seq != c_seq || ax_xc != pc.chunk) {
-                cl_build_ax(axw_p, it, pc.chunk * nq / nxc, pc.nqc, lane);
-                ax_seq = c_seq; ax_xc = pc.chunk;
+        for (int ch = 0; ch < nxc; ch++) {
+            const int nqc = it.piece[ch * per].nqc;
+            switch (nqc) {
+                case 1: cl_bwd_chunk<1>(it, ch, ch * per, (ch + 1) * per, gbuf, slots, n_piece, maps_l, z, lane); break;
+                case 2: cl_bwd_chunk<2>(it, ch, ch * per, (ch + 1) * per, gbuf, slots, n_piece, maps_l, z, lane); break;
+                case 3: cl_bwd_chunk<3>(it, ch, ch * per, (ch + 1) * per, gbuf, slots, n_piece, maps_l, z, lane); break;
+                default: cl_bwd_chunk<4>(it, ch, ch * per, (ch + 1) * per, gbuf, slots, n_piece, maps_l, z, lane); break;
             }
-            const int rb = 512 * pc.nqc;
-            const int slot = n_piece % kClSlots;
-            bulk_wait_read<kClSlots - 1>();          // this lane's reduce that last read the slot has finished reading
-            __syncwarp();
-            const uint32_t sa = smem_u32(slots + slot * kClbSlotBytes);
-            switch (pc.nqc) {
-                case 1: cl_bwd_piece<1>(it, sa, gbuf, axw, pc.p0, pc.p1, pc.jA, pc.rows, lane); break;
-                case 2: cl_bwd_piece<2>(it, sa, gbuf, axw, pc.p0, pc.p1, pc.jA, pc.rows, lane); break;
-                case 3: cl_bwd_piece<3>(it, sa, gbuf, axw, pc.p0, pc.p1, pc.jA, pc.rows, lane); break;
-                default: cl_bwd_piece<4>(it, sa, gbuf, axw, pc.p0, pc.p1, pc.jA, pc.rows, lane); break;
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                const CUtensorMap *mp = &maps.m[(it.l * 4 + pc.nqc - 1) * kClRsel];
-                const unsigned char *src = slots + slot * kClbSlotBytes - pc.jA * rb;
-                cl_for_row_ops(it.runmask, pc.jA, pc.rows, [&](int j, int lr) {
-                    tma_reduce_add_3d(mp + lr, pc.x0, z, it.yof[j], src + j * rb);
-                });
-            }
-            bulk_commit();
-            n_piece++;
         }
         __syncwarp();                                    // every lane is done with this dY buffer
         g_con++;
-        if (++c_g == ngroups) { c_g = 0; c_seq++; }
+        if (++c_g == ngroups) { c_ready = false; st.c_seq++; }
     }
     bulk_wait_all<0>();
     __syncwarp();
@@ -776,45 +925,56 @@ static int cl_grid(int ctas_per_sm)
 }
 
 // ctr: two ints, zero before the first launch (the kernel re-arms them)
-cudaError_t launch_roialign_fwd_cl(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, float *out,
-                                   int32_t *fallback_flag, int *ctr, cudaStream_t s, bool *launched)
+size_t roialign_cl_workspace_bytes(int R) { return (size_t)(R > 0 ? R : 0) * sizeof(ClItem) + 256; }
+
+// plan (one warp per RoI) -> items; then the persistent kernel.  ctr: two ints, zero before the first launch (the kernel
+// re-arms them); items: roialign_cl_workspace_bytes(R) bytes of scratch
+template <bool FWD>
+static cudaError_t cl_launch(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, float *out, const float *dout,
+                             int32_t *fallback_flag, void *items_ws, int *ctr, cudaStream_t s, bool *launched)
 {
     *launched = false;
-    if ((fs.C & 31) || P != kClP || R <= 0) return cudaSuccess;
+    if ((fs.C & 31) || P != kClP || R <= 0 || !items_ws) return cudaSuccess;
     if (!cl_enabled()) return cudaSuccess;
     ClMaps maps;
     const int mask = cl_build_maps(fs, &maps);
     if (!mask) return cudaSuccess;
-    auto kern = roialign_fwd_cl_kernel<kClP>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClSmemBytes);   // per device: set every time
+    ClItem *items = reinterpret_cast<ClItem *>((reinterpret_cast<uintptr_t>(items_ws) + 255) & ~(uintptr_t)255);
+    roialign_plan_kernel<kClP><<<(R + kPlanWarps - 1) / kPlanWarps, 32 * kPlanWarps, 0, s>>>(
+        f, mask, rois5, R, FWD ? kClSlotBytes : kClbSlotBytes, items, fallback_flag);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     const int nchunk = cl_chunks_for(fs.C);
-    const int total = R * nchunk, grid = cl_grid(MD_CL_CTAS);
-    kern<<<total < grid ? total : grid, 32, kClSmemBytes, s>>>(maps, f, mask, rois5, R, 512, nchunk, out, fallback_flag, ctr);
+    const int total = R * nchunk;
+    if (FWD) {
+        auto kern = roialign_fwd_cl_kernel<kClP>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClSmemBytes);   // per device: set every time
+        if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        const int grid = cl_grid(MD_CL_CTAS);
+        kern<<<total < grid ? total : grid, 32, kClSmemBytes, s>>>(maps, items, R, fs.C, 512, nchunk, out, ctr);
+    } else {
+        auto kern = roialign_bwd_cl_kernel<kClP>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClbSmemBytes);
+        if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        const int grid = cl_grid(MD_CLB_CTAS);
+        kern<<<total < grid ? total : grid, 32, kClbSmemBytes, s>>>(maps, items, R, fs.C, 512, nchunk, dout, ctr);
+    }
     *launched = true;
     return cudaGetLastError();
 }
 
+cudaError_t launch_roialign_fwd_cl(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, float *out,
+                                   int32_t *fallback_flag, void *items_ws, int *ctr, cudaStream_t s, bool *launched)
+{
+    return cl_launch<true>(fs, f, rois5, R, P, out, nullptr, fallback_flag, items_ws, ctr, s, launched);
+}
 
 cudaError_t launch_roialign_bwd_cl(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, const float *dout,
-                                   int32_t *fallback_flag, int *ctr, cudaStream_t s, bool *launched)
+                                   int32_t *fallback_flag, void *items_ws, int *ctr, cudaStream_t s, bool *launched)
 {
-    *launched = false;
-    if ((fs.C & 31) || P != kClP || R <= 0) return cudaSuccess;
-    if (!cl_enabled()) return cudaSuccess;
-    ClMaps maps;
-    const int mask = cl_build_maps(fs, &maps);
-    if (!mask) return cudaSuccess;
-    auto kern = roialign_bwd_cl_kernel<kClP>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClbSmemBytes);
-    if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    const int nchunk = cl_chunks_for(fs.C);
-    const int total = R * nchunk, grid = cl_grid(MD_CLB_CTAS);
-    kern<<<total < grid ? total : grid, 32, kClbSmemBytes, s>>>(maps, f, mask, rois5, R, 512, nchunk, dout, fallback_flag, ctr);
-    *launched = true;
-    return cudaGetLastError();
+    return cl_launch<false>(fs, f, rois5, R, P, nullptr, dout, fallback_flag, items_ws, ctr, s, launched);
 }
 
 }  // namespace md

@@ -51,8 +51,8 @@ def test_bad_dtype_or_shape_returns_2_without_touching_cuda():
     sh[0][1] = 3   # fewer than 4 coordinates
     assert lib.MdNms(n, params, ndims, shapes, (ctypes.c_char_p * n)(*good), None, None) == 2
     sh[0][1] = 5
-    sh[0][0] = 4096   # K > 2048 is refused, not silently truncated
-    sh[2][0] = sh[3][0] = 4096
+    sh[0][0] = 4097   # K > 4096 (64 mask words per row) is refused, not silently truncated
+    sh[2][0] = sh[3][0] = 4097
     assert lib.MdNms(n, params, ndims, shapes, (ctypes.c_char_p * n)(*good), None, None) == 4
 
 

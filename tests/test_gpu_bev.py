@@ -63,7 +63,7 @@ def test_rotated_nms_live_against_compiled_reference():
         assert int(cnt) == cnt_ref and np.array_equal(keep.cpu().numpy(), keep_ref)
 
 
-@pytest.mark.parametrize("n", [1, 63, 64, 65, 1000, 2048])
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 1000, 2048, 2100, 4096])
 def test_normal_nms_vs_numpy_restatement(n):
     rng = np.random.default_rng(100 + n)
     from tests.golden.make_bev_golden import make_boxes
@@ -78,8 +78,8 @@ def test_normal_nms_vs_numpy_restatement(n):
 
 def test_bev_nms_error_codes_and_sizes():
     from minddet_b200 import AotError
-    boxes = torch.zeros(2049, 7, device="cuda")
+    boxes = torch.zeros(4097, 7, device="cuda")
     with pytest.raises(AotError):
-        NumGpu()(boxes, torch.tensor([0.2], device="cuda"))          # > 2048 boxes: unsupported size (rc 4)
+        NumGpu()(boxes, torch.tensor([0.2], device="cuda"))          # > 4096 boxes: unsupported size (rc 4)
     with pytest.raises(AotError):
         BoxesIouBevGpu()(torch.zeros(4, 6, device="cuda"), torch.zeros(4, 7, device="cuda"))   # bad shape (rc 2)

@@ -107,7 +107,7 @@ def _sorted_dets(rng, n, cluster, sigma=12.0):
     return np.concatenate([b, s[:, None]], 1).astype(np.float32)
 
 
-@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 819, 2000, 2048])
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 819, 2000, 2048, 2049, 3000, 4096])      # > 2048: the 64-word sweep
 def test_nms_default_mode_bit_exact(n):
     rng = np.random.default_rng(100 + n)
     dets = np.stack([_sorted_dets(rng, n, cluster=max(1, n // 25)) for _ in range(3)])

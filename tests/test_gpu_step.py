@@ -191,6 +191,7 @@ def test_first_call_inside_a_capture_is_refused_not_corrupted():
     st = torch.cuda.Stream()                           # fresh stream -> fresh (device, stream) workspace
     boxes = dev(np.concatenate([synth.rand_boxes(np.random.default_rng(1), 64), np.linspace(1, 0, 64, dtype=np.float32)[:, None]], 1))
     nms = NMSWithMask(0.5)
+    nms._cfg(nms.cfg_values, boxes.device)             # the cfg tensor itself is an H2D copy: not capturable either
     with torch.cuda.stream(st):
         g = torch.cuda.CUDAGraph()
         with pytest.raises(AotError, match="5"):
