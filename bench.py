@@ -386,16 +386,22 @@ def nms_latency(rp, dev, iters=20):
     allb = torch.stack(rows, 1).contiguous()            # (B, 5, 2000, 5)
     nms = NMSWithMask(0.7)
     res = {}
+    cur = torch.cuda.current_stream()
     for name, t in (("b8", allb.reshape(-1, 2000, 5)), ("b1", allb[:1].reshape(-1, 2000, 5).contiguous())):
         for _ in range(3):
             nms(t)
-        torch.cuda.synchronize()
+        cur.synchronize()
+        g = torch.cuda.CUDAGraph()                     # mask + sweep as the graph executor launches them (no ctypes gap)
+        with torch.cuda.graph(g, stream=cur):
+            nms(t)
+        g.replay()
+        cur.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(iters):
-            nms(t)
+            g.replay()
         e1.record()
-        torch.cuda.synchronize()
+        cur.synchronize()
         res[name] = e0.elapsed_time(e1) / iters * 1e3
     nimg = allb.shape[0]
     return {"nms_us_per_image": res["b8"] / nimg, "nms_us_b1_latency": res["b1"], "boxes_per_level": 2000, "levels": 5,
