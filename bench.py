@@ -315,6 +315,8 @@ def count_graph_kernels(graph):
 
 def new_graph():
     import torch
+    if os.environ.get("MD_BENCH_KEEP_GRAPH", "1") == "0":
+        return torch.cuda.CUDAGraph()
     try:
         return torch.cuda.CUDAGraph(keep_graph=True)             # keeps the cudaGraph_t so that its nodes can be counted
     except TypeError:
@@ -490,7 +492,7 @@ def run_b200(args):
         batch = args.global_batch // world
     mask_branch = args.config == 4
 
-    rp = pipeline.RegionPath(seed=0)
+    rp = pipeline.RegionPath(seed=int(os.environ.get("MD_BENCH_SAMPLER_SEED", "0")), advance=os.environ.get("MD_BENCH_FREEZE_SAMPLES") != "1")   # (diagnosis switches)
     seed = 0xD37 if args.same_seed else 0xD37 + rank
     host = pipeline.make_inputs(batch, seed=seed, pin=True)
     if mask_branch:
