@@ -176,16 +176,16 @@ cudaError_t launch_roialign_fwd_tma(const FeatSet &fs, const RoiFeat &f, const f
                                     float *out, int32_t *fallback_flag, cudaStream_t s, bool *launched);
 cudaError_t launch_roialign_bwd_tma(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P,
                                     const float *dout, int32_t *fallback_flag, cudaStream_t s, bool *launched);
-// roialign_cl.cu: channel-per-lane kernels (7x7, C % 32 == 0); RoIs they decline are flagged for the gather kernels
-cudaError_t launch_roialign_fwd_cl(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, float *out,
-                                   int32_t *fallback_flag, void *items_ws, int *ctr, cudaStream_t s, bool *launched);
-cudaError_t launch_roialign_bwd_cl(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, const float *dout,
-                                   int32_t *fallback_flag, void *items_ws, int *ctr, cudaStream_t s, bool *launched);
-size_t roialign_cl_workspace_bytes(int R);
+// roialign_ch.cu: channel-per-lane kernels (7x7, S = 2, C % 32 == 0); RoIs they decline are flagged for the gather kernels
+cudaError_t launch_roialign_fwd_ch(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, float *out,
+                                   int32_t *fallback_flag, void *plan_ws, cudaStream_t s, bool *launched);
+cudaError_t launch_roialign_bwd_ch(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, const float *dout,
+                                   int32_t *fallback_flag, void *plan_ws, cudaStream_t s, bool *launched);
+size_t roialign_ch_workspace_bytes(int R);
 
-// flags (R ints, padded) + the channel-lane kernels' per-RoI tables
+// flags (R ints, padded) + the channel-lane kernels' per-RoI plans
 static size_t roi_flag_bytes(int R) { return ((size_t)(R > 0 ? R : 0) * sizeof(int32_t) + 255) & ~(size_t)255; }
-size_t roialign_workspace_bytes(int R) { return roi_flag_bytes(R) + roialign_cl_workspace_bytes(R) + 256; }
+size_t roialign_workspace_bytes(int R) { return roi_flag_bytes(R) + roialign_ch_workspace_bytes(R) + 256; }
 
 // mode: 0 = TMA separable kernel + gather for the RoIs it declines (default); 1 = gather only (bit-exact fwd)
 cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
@@ -198,12 +198,12 @@ cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, in
     bool tma = false;
     if (mode == 0 && flags) {
         cudaError_t e = cudaSuccess;
-        if (ctl) e = launch_roialign_fwd_cl(fs, f, rois5, R, P, out, flags, reinterpret_cast<unsigned char *>(ws) + roi_flag_bytes(R), ctl + MD_CTL_ROI_FWD, s, &tma);
+        e = launch_roialign_fwd_ch(fs, f, rois5, R, P, out, flags, reinterpret_cast<unsigned char *>(ws) + roi_flag_bytes(R), s, &tma);
         if (e != cudaSuccess) return e;
         if (!tma) e = launch_roialign_fwd_tma(fs, f, rois5, R, P, out, flags, s, &tma);
         if (e != cudaSuccess) return e;
     }
-    const int csplit = (fs.C >= 64 && !tma) ? 4 : 1;
+    const int csplit = fs.C >= 64 ? 4 : 1;
     roialign_fwd_gather_kernel<<<dim3(tma ? (R < 592 ? R : 592) : R, csplit), kRoiThreads, 0, s>>>(f, rois5, R, P, csplit, out, tma ? flags : nullptr);
     return cudaGetLastError();
 }
@@ -222,12 +222,12 @@ cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, in
     bool tma = false;
     if (mode == 0 && flags) {
         cudaError_t e = cudaSuccess;
-        if (ctl) e = launch_roialign_bwd_cl(fs, f, rois5, R, P, dout, flags, reinterpret_cast<unsigned char *>(ws) + roi_flag_bytes(R), ctl + MD_CTL_ROI_BWD, s, &tma);
+        e = launch_roialign_bwd_ch(fs, f, rois5, R, P, dout, flags, reinterpret_cast<unsigned char *>(ws) + roi_flag_bytes(R), s, &tma);
         if (e != cudaSuccess) return e;
         if (!tma) e = launch_roialign_bwd_tma(fs, f, rois5, R, P, dout, flags, s, &tma);
         if (e != cudaSuccess) return e;
     }
-    const int csplit = (fs.C >= 64 && !tma) ? 4 : 1;
+    const int csplit = fs.C >= 64 ? 4 : 1;
     roialign_bwd_gather_kernel<<<dim3(tma ? (R < 592 ? R : 592) : R, csplit), kRoiThreads, 0, s>>>(f, rois5, R, P, csplit, dout, tma ? flags : nullptr);
     return cudaGetLastError();
 }

@@ -13,7 +13,7 @@ sed -i "$expr" $tmp/*.cu $tmp/*.cuh
 sed -i 's|"../../include/md_region_aot.h"|"../../../include/md_region_aot.h"|' $tmp/*.cu $tmp/*.h $tmp/*.cuh
 FL="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC,-fvisibility=hidden -cudart static"
 objs=""
-for f in proposal assign roialign roialign_tma roialign_cl bev yolo rcnn_post aot_entry; do
+for f in proposal assign roialign roialign_tma roialign_ch bev yolo rcnn_post aot_entry; do
   if [[ " $srcs " == *" $f "* ]]; then /usr/local/cuda/bin/nvcc $FL -c $tmp/$f.cu -o $tmp/$f.o; objs="$objs $tmp/$f.o"; else objs="$objs minddet_b200/lib/$f.o"; fi
 done
 /usr/local/cuda/bin/nvcc -shared -cudart static -gencode arch=compute_100a,code=sm_100a -o minddet_b200/lib/variant_$name.so $objs

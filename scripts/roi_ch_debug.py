@@ -1,5 +1,5 @@
 """Debug harness for the channel-lane RoIAlign kernels: small controlled cases against the oracle, with error structure
-printed (per RoI, per channel, per bin).  python scripts/roi_cl_debug.py [C]"""
+printed (per RoI, per channel, per bin).  python scripts/roi_ch_debug.py [C]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

@@ -372,6 +372,43 @@ def test_roialign_full_size_vs_oracle():
         np.testing.assert_allclose(host(ft[l].grad), dref[l], rtol=1e-5, atol=1e-5 * max(1.0, np.abs(dref[l]).max()))
 
 
+@pytest.mark.parametrize("C", [32, 256])
+def test_roialign_channel_lane_kernels_vs_oracle(C, monkeypatch):
+    """The opt-in channel-per-lane kernels (roialign_ch.cu, MD_ROI_CH=1; the launcher reads the switch on every call):
+    compact, tall, wide (in-kernel gather), edge-clamped, outside and bad-batch RoIs on all four levels, several
+    (RoI, channel group) items per persistent warp."""
+    monkeypatch.setenv("MD_ROI_CH", "1")
+    rng = np.random.default_rng(46)
+    B = 2
+    shapes = synth.level_shapes()[:4]
+    strides = synth.STRIDES[:4]
+    feats = [rng.uniform(-1, 1, (B, C, h, w)).astype(np.float32) for h, w in shapes]
+    n = 3000 if C == 32 else 700              # > 4 items per warp of the persistent grid
+    rois = _rois(rng, n, B)
+    rois[0, 1:] = [-30, -30, 40, 50]
+    rois[1, 1:] = [1300, 760, 1343, 799]
+    rois[2, 1:] = [20, 20, 20.4, 20.2]
+    rois[3, 1:] = [0, 0, 1343, 799]
+    rois[4, 1:] = [100, 5, 130, 790]
+    rois[5, 1:] = [5, 100, 1300, 130]
+    rois[6, 1:] = [-500, -500, -300, -300]
+    rois[7, 1:] = [300, 300, 301, 301]
+    rois[8, 1:] = [10, 10, 450, 120]
+    rois[9, 1:] = [200, 100, 255, 160]
+    rois[10, 0] = -1
+    rois[11, 0] = B
+    ext = SingleRoIExtractor()
+    ft = [dev(f).requires_grad_(True) for f in feats]
+    out = ext(dev(rois), *ft)
+    ref = O.roialign_fwd(feats, strides, rois)
+    np.testing.assert_allclose(host(out), ref, rtol=1e-5, atol=1e-6)
+    dout = rng.uniform(-1, 1, ref.shape).astype(np.float32)
+    out.backward(dev(dout))
+    dref = O.roialign_bwd([f.shape for f in feats], strides, rois, dout)
+    for l in range(4):
+        np.testing.assert_allclose(host(ft[l].grad), dref[l], rtol=1e-5, atol=1e-5 * max(1.0, np.abs(dref[l]).max()))
+
+
 def test_roialign_bwd_accumulates_into_caller_tensors():
     """MdRoiAlignBwdAcc: acc_l += ROIAlignGrad(dout).  Starting from zeros it is the plain bprop (oracle), starting
     from an existing gradient it adds to it; the self-contained MdRoiAlignBwd stays the zero-filling form."""
