@@ -204,7 +204,7 @@ cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, in
         if (e != cudaSuccess) return e;
     }
     const int csplit = fs.C >= 64 ? 4 : 1;
-    roialign_fwd_gather_kernel<<<dim3(tma ? (R < 592 ? R : 592) : R, csplit), kRoiThreads, 0, s>>>(f, rois5, R, P, csplit, out, tma ? flags : nullptr);
+    roialign_fwd_gather_kernel<<<dim3(tma ? (R < 148 ? R : 148) : R, csplit), kRoiThreads, 0, s>>>(f, rois5, R, P, csplit, out, tma ? flags : nullptr);
     return cudaGetLastError();
 }
 
@@ -228,7 +228,7 @@ cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, in
         if (e != cudaSuccess) return e;
     }
     const int csplit = fs.C >= 64 ? 4 : 1;
-    roialign_bwd_gather_kernel<<<dim3(tma ? (R < 592 ? R : 592) : R, csplit), kRoiThreads, 0, s>>>(f, rois5, R, P, csplit, dout, tma ? flags : nullptr);
+    roialign_bwd_gather_kernel<<<dim3(tma ? (R < 148 ? R : 148) : R, csplit), kRoiThreads, 0, s>>>(f, rois5, R, P, csplit, dout, tma ? flags : nullptr);
     return cudaGetLastError();
 }
 
