@@ -84,7 +84,10 @@ cudaError_t launch_decode_rows(const float *anchors, const float *deltas, int64_
 constexpr int kDecThreads = 128;
 constexpr int kDecCells = kDecThreads * 4;
 
-template <bool VEC>
+// AU > 0: the anchor count is a compile-time constant and ALL 4*AU delta planes of a thread's four cells are requested
+// before the first box is decoded (AU*64 bytes in flight per thread instead of 64: the kernel is a pure stream, and with
+// one anchor at a time its loads queued behind its own exps).  AU == 0: any A, one anchor at a time.
+template <bool VEC, int AU>
 __global__ void __launch_bounds__(kDecThreads)
 decode_level_kernel(const float *__restrict__ deltas, const float *__restrict__ base, int A, int H, int W,
                     const float *__restrict__ cfg, float4 *__restrict__ out)
@@ -95,31 +98,41 @@ decode_level_kernel(const float *__restrict__ deltas, const float *__restrict__ 
     const int HW = H * W;
     const int b = blockIdx.y;
     const int tiles = (HW + kDecCells - 1) / kDecCells;
+    constexpr int AB = AU > 0 ? AU : 1;      // anchors per batch of loads
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int p0 = tile * kDecCells + threadIdx.x * 4;
-        for (int a = 0; a < A; a++) {
-            float d[4][4];   // [coord][cell]
+        float sx[4], sy[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float *plane = deltas + ((int64_t)b * 4 * A + a * 4 + k) * HW;
-                if (VEC) {
-                    float4 v = make_float4(0, 0, 0, 0);
-                    if (p0 < HW) v = ldg_stream(reinterpret_cast<const float4 *>(plane + p0));
-                    d[k][0] = v.x; d[k][1] = v.y; d[k][2] = v.z; d[k][3] = v.w;
-                } else {
+        for (int j = 0; j < 4; j++) {
+            const int p = p0 + j;
+            const int w = p % W, h = p / W;
+            sx[j] = mul((float)w, stride); sy[j] = mul((float)h, stride);
+        }
+        for (int a0 = 0; a0 < A; a0 += AB) {
+            float d[AB][4][4];   // [anchor][coord][cell]
 #pragma unroll
-                    for (int j = 0; j < 4; j++) d[k][j] = (p0 + j < HW) ? __ldg(plane + p0 + j) : 0.0f;
+            for (int i = 0; i < AB; i++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float *plane = deltas + ((int64_t)b * 4 * A + (a0 + i) * 4 + k) * HW;
+                    if (VEC) {
+                        float4 v = make_float4(0, 0, 0, 0);
+                        if (p0 < HW) v = ldg_stream(reinterpret_cast<const float4 *>(plane + p0));
+                        d[i][k][0] = v.x; d[i][k][1] = v.y; d[i][k][2] = v.z; d[i][k][3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) d[i][k][j] = (p0 + j < HW) ? __ldg(plane + p0 + j) : 0.0f;
+                    }
                 }
-            }
-            const float4 bs = __ldg(reinterpret_cast<const float4 *>(base) + a);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int p = p0 + j;
-                const int w = p % W, h = p / W;
-                const float sx = mul((float)w, stride), sy = mul((float)h, stride);
-                const float4 anc = make_float4(add(bs.x, sx), add(bs.y, sy), add(bs.z, sx), add(bs.w, sy));
-                stage[(threadIdx.x * 4 + j) * A + a] =
-                    decode_box(anc, make_float4(d[0][j], d[1][j], d[2][j], d[3][j]), c);
+            for (int i = 0; i < AB; i++) {
+                const float4 bs = __ldg(reinterpret_cast<const float4 *>(base) + a0 + i);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float4 anc = make_float4(add(bs.x, sx[j]), add(bs.y, sy[j]), add(bs.z, sx[j]), add(bs.w, sy[j]));
+                    stage[(threadIdx.x * 4 + j) * A + a0 + i] =
+                        decode_box(anc, make_float4(d[i][0][j], d[i][1][j], d[i][2][j], d[i][3][j]), c);
+                }
             }
         }
         __syncthreads();
@@ -140,7 +153,7 @@ cudaError_t launch_decode_level(const float *deltas, const float *base, int B, i
     const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(deltas) & 15) == 0);
     const int tiles = (HW + kDecCells - 1) / kDecCells;
     const int gx = tiles;                                  // one tile per CTA: several waves hide the load -> sync -> store phases
-    auto kern = vec ? decode_level_kernel<true> : decode_level_kernel<false>;
+    auto kern = vec ? (A == 3 ? decode_level_kernel<true, 3> : decode_level_kernel<true, 0>) : decode_level_kernel<false, 0>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
