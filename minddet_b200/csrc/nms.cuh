@@ -16,6 +16,10 @@ struct NmsSegs {                 // segment s -> boxes + K
     int l0, nl;                  // optional level subset: launch index z serves segment (z / nl) * L + l0 + z % nl (nl == 0: z)
     const float *scores;         // optional (nseg, seg_stride) with kept_keys: the sweep also writes the monotone keys of
     uint32_t *kept_keys;         // the kept boxes' scores, in kept order, (nseg, keep_stride) -- the cross-level merge's input
+    int labels_sorted;           // the rows of a segment are grouped by label (run_nms's label-major permutation): a tile whose row and
+                                 // column label ranges do not meet is all zeros and is not evaluated
+    const int32_t *dyn_k;        // optional (nseg): rows really present in a segment (device side); rows beyond it are padding and
+                                 // neither the mask tiles nor the sweep touch them (a post-process with few candidates pays for those only)
 };
 
 // cfg: MD_CFG_NMS (thr, offset, inclusive, union_eps) on the device; keep_pos/keep_mask strides in elements

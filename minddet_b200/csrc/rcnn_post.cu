@@ -154,6 +154,7 @@ cudaError_t launch_rcnn_post(const float *rois, int roi_ld, const uint8_t *roi_v
     const int nb = (nms_pre + 63) / 64;
     sg.nbp = (nb + 1) & ~1; sg.rows_pad = nb * 64;
     sg.labels = w.labels; sg.agnostic = nullptr;
+    sg.dyn_k = w.selected;                      // candidates really selected per image: the padding rows cost nothing
     e = run_nms(sg, B, nms_pre, w.nms_cfg, w.mask, w.keep_pos, nms_pre, w.keep_mask, nms_pre, w.count, s);
     if (e != cudaSuccess) return e;
     rcnn_gather_kernel<<<B, 128, 0, s>>>(nms_pre, max_det, w.boxes, w.scores, w.labels, cand_idx, w.selected, w.keep_pos, w.count,

@@ -279,6 +279,7 @@ cudaError_t launch_yolo_nms(const float *dets, int B, int A, const float *cfg, v
     const int nb = (nms_pre + 63) / 64;
     sg.nbp = (nb + 1) & ~1; sg.rows_pad = nb * 64;
     sg.labels = w.labels; sg.agnostic = cfg + 2;
+    sg.dyn_k = w.selected;                      // candidates really selected per image: the padding rows cost nothing
     e = run_nms(sg, B, nms_pre, w.nms_cfg, w.mask, w.keep_pos, nms_pre, w.keep_mask, nms_pre, w.count, s);
     if (e != cudaSuccess) return e;
     yolo_gather_kernel<<<B, 128, 0, s>>>(dets, A, nms_pre, max_det, cand_idx, w.selected, w.keep_pos, w.count, out, keep_idx, num_out);
