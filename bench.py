@@ -18,6 +18,7 @@ After the timed region every rank compares what it just computed with the CPU or
 (`parity_checked`); a mismatch is a non-zero exit.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -466,7 +467,20 @@ def global64_measure(world, rank, K, W):
 
 
 # ------------------------------------------------------------------------------------------------
+ZERO_BY_MEMSET = os.environ.get("MD_BENCH_ZERO", "memset") == "memset"
+ZERO_AT = os.environ.get("MD_BENCH_ZERO_AT", "proposal")
+CUDART = None
+
+
 def run_b200(args):
+    global CUDART
+    if ZERO_BY_MEMSET:
+        import ctypes as _ct
+        import glob as _glob
+        import torch as _torch
+        cands = _glob.glob(os.path.join(os.path.dirname(_torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*"))
+        CUDART = _ct.CDLL(cands[0] if cands else "libcudart.so")
+        CUDART.cudaMemsetAsync.restype = _ct.c_int
     import torch
     import torch.distributed as dist
 
@@ -544,17 +558,33 @@ def run_b200(args):
                 rpn = rp.rpn_targets(inp["gts"], inp["gt_valid"], anchors, avalid)
                 join.record(aux)
         feats_h = inp["feats"]
-        props, pmask = rp.proposal(inp["cls_scores"], inp["bbox_preds"])
-        zeroed = None
-        if overlap:
+
+        def start_zero_fill():
             # The RoIAlign gradient's zero-fill (731 MB of DRAM writes, ~105 us) has no producer: it runs on its own
-            # (lower-priority) stream and the backward accumulates (MdRoiAlignBwdAcc).  Started after Proposal: the
-            # Proposal kernels share the SMs badly with a kernel that wants every SM's store bandwidth.
+            # (lower-priority) stream and the backward accumulates (MdRoiAlignBwdAcc).  cudaMemsetAsync nodes rather than
+            # fill kernels: measured 0.985 vs 1.012 ms per step (MD_BENCH_ZERO=fill goes back to torch.zeros_like).
             zfork.record(torch.cuda.current_stream())
             zstream.wait_event(zfork)
             with torch.cuda.stream(zstream):
-                zeroed = [torch.zeros_like(f) for f in inp["feats"]]
+                if ZERO_BY_MEMSET:
+                    z_ = [torch.empty_like(f) for f in inp["feats"]]
+                    for z in z_:
+                        rc = CUDART.cudaMemsetAsync(ctypes.c_void_p(z.data_ptr()), 0, ctypes.c_size_t(z.numel() * 4),
+                                                    ctypes.c_void_p(zstream.cuda_stream))
+                        if rc != 0:
+                            raise RuntimeError(f"cudaMemsetAsync returned {rc}")
+                else:
+                    z_ = [torch.zeros_like(f) for f in inp["feats"]]
                 zjoin.record(zstream)
+            return z_
+
+        zeroed = None
+        if overlap and ZERO_AT == "top":
+            zeroed = start_zero_fill()
+        props, pmask = rp.proposal(inp["cls_scores"], inp["bbox_preds"])
+        if overlap and ZERO_AT != "top":
+            # started after Proposal: the Proposal kernels share the SMs badly with work that wants every SM's store bandwidth
+            zeroed = start_zero_fill()
         mark("proposal")
         if not overlap:
             rpn = rp.rpn_targets(inp["gts"], inp["gt_valid"], anchors, avalid)
@@ -688,6 +718,26 @@ def run_b200(args):
             for (n0, ev0), (n1, ev1) in zip(tm[:-1], tm[1:]):
                 per.setdefault(n1, []).append(ev0.elapsed_time(ev1))
         live_ms = {k: float(np.median(v)) for k, v in per.items()}     # median: robust to host-side launch hiccups of the eager pass
+        # The two RoIAlign stages feed `roofline`: in the eager pass above a stage also contains the host's launch gap
+        # (ctypes call, tensor-map lookup) before its first kernel, 60-90 us on a 0.3 ms stage.  Timed again as six calls
+        # back to back on the step's own RoIs, so that the stream never runs dry: kernel time only (+ the in-line dX
+        # memsets for the backward).  Inputs (731 MB of features / gradients per call) exceed L2.
+        def back_to_back(fn, n=6):
+            for _ in range(2):
+                fn()
+            side.synchronize()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for _ in range(n):
+                fn()
+            b1.record()
+            side.synchronize()
+            return b0.elapsed_time(b1) / n
+        rois_t = out["halves"][0]["rois"]
+        fshapes = [tuple(f.shape) for f in dev["feats"][:4]]
+        eager_ms = {k: live_ms[k] for k in ("roialign_fwd", "roialign_bwd") if k in live_ms}
+        live_ms["roialign_fwd"] = back_to_back(lambda: rp.extractor._forward(rois_t, dev["feats"][:4]))
+        live_ms["roialign_bwd"] = back_to_back(lambda: rp.extractor._backward(rois_t, dev["dout"], fshapes))
         nms = nms_latency(rp, dev) if rank == 0 else None
 
         # ---- e2e: every step copies ALL inputs pinned host -> device and reads a token sample of the results back.
@@ -830,7 +880,9 @@ def run_b200(args):
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": rooflines[dominant]["achieved"], "peak": peak, "unit": "GB/s",
                 "frac": rooflines[dominant]["frac"], "traffic": NCU_TRAFFIC.get(dominant),
                 "algorithmic_bytes_per_launch": alg[dominant], "kernel_ms": live_ms[dominant], "peak_source": peak_src,
-                "note": "stage = the stream kernel + gather kernel for declined RoIs (+ the 4 dX memsets for bwd); "
+                "note": "stage = the stream kernel + gather kernel for declined RoIs (+ the 4 dX memsets for bwd), timed as six "
+                        "calls back to back with CUDA events on the launching stream (kernel time; the eager per-stage pass "
+                        "of stage_ms also holds the host's launch gaps); "
                         "algorithmic bytes = RoI tensor (R*C*49*4) + exact union of bilinear footprints of this step's RoIs "
                         "(+ zero-init of dX for bwd); traffic = dram read+write of the stream kernel from profiles/ (ncu --set full)",
                 "all": rooflines}
