@@ -469,6 +469,9 @@ def global64_measure(world, rank, K, W):
 # ------------------------------------------------------------------------------------------------
 ZERO_BY_MEMSET = os.environ.get("MD_BENCH_ZERO", "memset") == "memset"
 ZERO_AT = os.environ.get("MD_BENCH_ZERO_AT", "proposal")
+# diagnosis only (the line carries "diag_skip"): leave the RPN targets and / or the zero-fill out of the step to see what they cost
+DIAG_SKIP = set(x for x in os.environ.get("MD_BENCH_SKIP", "").split(",") if x)
+RPN_AT = os.environ.get("MD_BENCH_RPN_AT", "top")          # top | fwd | bwd: where the RPN-target branch forks off the chain
 CUDART = None
 
 
@@ -548,21 +551,34 @@ def run_b200(args):
         anchors, avalid = rp.anchors()
         overlap = timers is None and not args.no_overlap
         rpn = None
-        if overlap:
+
+        def fork_rpn_targets():
             # RPN target assignment depends only on anchors + gts, not on the proposals: it runs on a second stream
-            # beside the (latency-bound) Proposal chain, as any graph executor is free to do; joined below
-            cur = torch.cuda.current_stream()
-            fork.record(cur)
+            # beside the chain (fork / join through events: legal under graph capture)
+            if "rpn" in DIAG_SKIP and step.cached_rpn is not None:
+                return step.cached_rpn
+            fork.record(torch.cuda.current_stream())
             aux.wait_event(fork)
             with torch.cuda.stream(aux):
-                rpn = rp.rpn_targets(inp["gts"], inp["gt_valid"], anchors, avalid)
+                r = rp.rpn_targets(inp["gts"], inp["gt_valid"], anchors, avalid)
                 join.record(aux)
+            step.cached_rpn = r
+            step.rpn_forked = True
+            return r
+
+        step.rpn_forked = False
+        if overlap and RPN_AT == "top":
+            rpn = fork_rpn_targets()
         feats_h = inp["feats"]
 
         def start_zero_fill():
             # The RoIAlign gradient's zero-fill (731 MB of DRAM writes, ~105 us) has no producer: it runs on its own
             # (lower-priority) stream and the backward accumulates (MdRoiAlignBwdAcc).  cudaMemsetAsync nodes rather than
             # fill kernels: measured 0.985 vs 1.012 ms per step (MD_BENCH_ZERO=fill goes back to torch.zeros_like).
+            if "zero" in DIAG_SKIP and step.cached_zero is not None:
+                step.zero_forked = False
+                return step.cached_zero
+            step.zero_forked = True
             zfork.record(torch.cuda.current_stream())
             zstream.wait_event(zfork)
             with torch.cuda.stream(zstream):
@@ -576,6 +592,7 @@ def run_b200(args):
                 else:
                     z_ = [torch.zeros_like(f) for f in inp["feats"]]
                 zjoin.record(zstream)
+            step.cached_zero = z_
             return z_
 
         zeroed = None
@@ -592,10 +609,15 @@ def run_b200(args):
         rcnn = rp.rcnn_targets(inp["gts"], inp["gt_labels"], pmask, props, inp["gt_valid"])
         mark("rcnn_assign_sample")
         rois = rcnn["rois"].reshape(-1, 5)
+        if overlap and RPN_AT == "fwd":
+            rpn = fork_rpn_targets()
         roi_feats = rp.extractor._forward(rois, feats_h)
         mark("roialign_fwd")
+        if overlap and RPN_AT == "bwd":
+            rpn = fork_rpn_targets()
         if zeroed is not None:
-            torch.cuda.current_stream().wait_event(zjoin)
+            if step.zero_forked:
+                torch.cuda.current_stream().wait_event(zjoin)
             dfe = rp.extractor._backward_into(rois, inp["dout"], zeroed)
         else:
             dfe = rp.extractor._backward(rois, inp["dout"], [tuple(f.shape) for f in feats_h])
@@ -611,10 +633,12 @@ def run_b200(args):
             mark("mask_roialign_bwd")
             res["mask_targets"] = mtarget(inp["gt_masks"], prois, rcnn["pos_gt"].reshape(-1).contiguous())
             mark("mask_targets")
-        if overlap:
+        if overlap and step.rpn_forked:
             torch.cuda.current_stream().wait_event(join)
         top100 = props[:, :100].contiguous()
         return dict(halves=[res], rpn=rpn, top100=top100)
+
+    step.cached_rpn, step.cached_zero, step.rpn_forked, step.zero_forked = None, None, False, True
 
     with torch.cuda.stream(side):
         dev = pipeline.to_device(host)
@@ -896,7 +920,7 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config_dict(args, world, batch),
-            "run": {"cuda_graph": graph is not None, "same_seed": bool(args.same_seed),
+            "run": {"cuda_graph": graph is not None, "same_seed": bool(args.same_seed), "diag_skip": sorted(DIAG_SKIP), "rpn_at": RPN_AT,
                     "streams": ("rpn target assignment and the RoIAlign-gradient zero-fill on their own streams (backward accumulates: "
                                 "MdRoiAlignBwdAcc)" if not args.no_overlap else "rpn targets in line, MdRoiAlignBwd zero-fills in line"),
                     "numa": numa},

@@ -90,6 +90,26 @@ def test_postprocess_dense_crowd_bit_exact(conf, agnostic, nms_pre, max_det):
         assert kept_total > 50            # the stress set really exercises suppression chains
 
 
+@pytest.mark.parametrize("nc,conf", [(1, 0.25), (3, 0.05), (80, 1.5)])
+def test_postprocess_label_grouping_edges(nc, conf):
+    """The label-major NMS path at its edges: one class only (a single diagonal block), three classes (long runs that
+    cross many 64-row tiles), and a threshold nothing passes (zero candidates: dynamic row count 0)."""
+    rng = np.random.default_rng(78 + nc)
+    B = 3
+    pred = crowd_pred(rng, B, nc=nc)
+    op = YoloV8PostProcess(SHAPES, STRIDES, conf_thr=conf, iou_thr=0.7, nms_pre=2048, max_det=300)
+    out, keep_idx, count = op(dev(pred))
+    out, keep_idx, count = out.cpu().numpy(), keep_idx.cpu().numpy(), count.cpu().numpy()
+    for b in range(B):
+        dets = O.yolo_decode(pred[b], SHAPES, STRIDES)
+        ro, ri, rc = O.yolo_nms(dets, conf, 2048, 0.7, False, 300)
+        assert count[b] == rc, (b, count[b], rc)
+        assert np.array_equal(keep_idx[b], ri), b
+        assert np.array_equal(out[b], ro), b
+    if conf > 1.0:
+        assert count.sum() == 0
+
+
 def test_full_batch_properties():
     """config 5 size (B=64): idempotence -- running NMS on its own survivors keeps every one of them."""
     rng = np.random.default_rng(5)
