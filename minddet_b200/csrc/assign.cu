@@ -11,6 +11,7 @@
 // the cluster radix-select of select.cuh.
 #include "kernels.h"
 #include "select.cuh"
+#include "launch.cuh"
 
 namespace md {
 
@@ -103,6 +104,7 @@ assign_gtmax_kernel(const AsIn in, uint32_t *__restrict__ gmax /* (B,G) float bi
                     int32_t *__restrict__ head_assigned /* nullable: RCNN flavour, the gts-as-proposals head of `assigned` */,
                     int64_t head_stride, int32_t *__restrict__ head_cand)
 {
+    pdl_entry();
     extern __shared__ unsigned char smem_raw[];
     GtS *sg = reinterpret_cast<GtS *>(smem_raw);
     uint32_t *smax = reinterpret_cast<uint32_t *>(sg + in.G);
@@ -157,6 +159,7 @@ assign_label_kernel(const AsIn in, const uint32_t *__restrict__ gmax, const floa
                     int32_t *__restrict__ assigned, int64_t assigned_stride, int assigned_offset,
                     int32_t *__restrict__ cand_count /* (B,2) pos|neg */)
 {
+    pdl_entry();
     extern __shared__ unsigned char smem_raw[];
     GtS *sg = reinterpret_cast<GtS *>(smem_raw);
     float *smax = reinterpret_cast<float *>(sg + in.G);
@@ -255,6 +258,7 @@ __global__ void __launch_bounds__(256)
 sample_prefilter_kernel(const int32_t *__restrict__ assigned, int N, int Sp, int Sn, uint32_t stream_base,
                         const int32_t *__restrict__ seed, int has_step, const float *__restrict__ cfg, const SampleLists L)
 {
+    pdl_entry();
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     if (__ldg(cfg + 14) != 0.0f) {                       // MD_AS_FORCE_FULL: mark both lists overflowed -> full-scan select
         if (blockIdx.x == 0 && threadIdx.x < 2) L.count[b * 2 + threadIdx.x] = kListCap + 1;
@@ -356,6 +360,7 @@ __global__ void rpn_finalize_kernel(const AsIn in, int Sp, int Sn, const int32_t
                                     uint8_t *__restrict__ neg_valid, int32_t *__restrict__ pos_gt,
                                     float4 *__restrict__ pos_target, int32_t *__restrict__ num_pos_out, int32_t *step)
 {
+    pdl_entry();
     const int b = blockIdx.x;
     if (step && b == 0 && threadIdx.x == 0) *step += 1;          // the samplers of this call are done: next call, next draw
     const int P = cand_count[b * 2], Q = cand_count[b * 2 + 1];
@@ -400,6 +405,7 @@ __global__ void rcnn_finalize_kernel(const float *__restrict__ props5, int P_, c
                                      int32_t *__restrict__ labels, uint8_t *__restrict__ mask,
                                      int32_t *__restrict__ pos_gt, int32_t *__restrict__ num_pos_out, int32_t *step)
 {
+    pdl_entry();
     if (step && blockIdx.x == 0 && threadIdx.x == 0) *step += 1;   // the samplers of this call are done: next call, next draw
     const int b = blockIdx.x;
     const int S = Sp + Sn, N = G + P_;
@@ -467,9 +473,9 @@ static cudaError_t run_assign(const AsIn &in, int B, const AssignWs &w, int32_t 
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     const size_t smem = (size_t)in.G * (sizeof(GtS) + 4) + 16;
-    assign_gtmax_kernel<<<dim3(gx, B), kAsThreads, smem, s>>>(in, w.gmax, w.best, gt_head ? assigned : nullptr, assigned_stride, w.cand);
-    assign_label_kernel<<<dim3(gx, B), kAsThreads, smem, s>>>(in, w.gmax, w.best, assigned, assigned_stride, assigned_offset, w.cand);
-    return cudaGetLastError();
+    e = launch_pdl(assign_gtmax_kernel, dim3(gx, B), dim3(kAsThreads), smem, s, in, w.gmax, w.best, gt_head ? assigned : (int32_t *)nullptr, assigned_stride, w.cand);
+    if (e != cudaSuccess) return e;
+    return launch_pdl(assign_label_kernel, dim3(gx, B), dim3(kAsThreads), smem, s, in, (const uint32_t *)w.gmax, (const float2 *)w.best, assigned, assigned_stride, assigned_offset, w.cand);
 }
 
 // list fast path, then the full-scan select for the segments it declined (normally none: both kernels of the
@@ -481,8 +487,9 @@ static cudaError_t run_samplers(const int32_t *assigned, int B, int N, int Sp, i
     int gx = (N + 255) / 256;
     const int cap = (148 * 8 + B - 1) / B;
     if (gx > cap) gx = cap;
-    sample_prefilter_kernel<<<dim3(gx, B), 256, 0, s>>>(assigned, N, Sp, Sn, stream_base, seed, has_step, cfg, L);
-    cudaError_t e = launch_select_sorted(ListSrc{ L, Sp, Sn, B }, sink, 2 * B, kListCap, s);
+    cudaError_t e = launch_pdl(sample_prefilter_kernel, dim3(gx, B), dim3(256), 0, s, assigned, N, Sp, Sn, stream_base, seed, has_step, cfg, L);
+    if (e != cudaSuccess) return e;
+    e = launch_select_sorted(ListSrc{ L, Sp, Sn, B }, sink, 2 * B, kListCap, s);
     if (e != cudaSuccess) return e;
     return launch_select_sorted(SampleSrc{ assigned, N, Sp, Sn, stream_base, seed, has_step, B, L }, sink, 2 * B, N, s);
 }
@@ -503,10 +510,9 @@ cudaError_t launch_assign_sample_rpn(const float *boxes, int boxes_per_image, co
     SampleSink sink{ pos_idx, neg_idx, Sp, Sn, Sp, Sn, w.cand };
     e = run_samplers(assigned, B, N, Sp, Sn, 0u, seed, seed_len >= 3, cfg, w, sink, s);
     if (e != cudaSuccess) return e;
-    rpn_finalize_kernel<<<B, 256, 0, s>>>(in, Sp, Sn, w.cand, assigned, pos_idx, pos_valid, neg_idx, neg_valid,
-                                          pos_gt, reinterpret_cast<float4 *>(pos_target), num_pos,
-                                          seed_len >= 3 ? const_cast<int32_t *>(seed) + 2 : nullptr);
-    return cudaGetLastError();
+    return launch_pdl(rpn_finalize_kernel, dim3(B), dim3(256), 0, s, in, Sp, Sn, w.cand, assigned, pos_idx, pos_valid, neg_idx, neg_valid,
+                      pos_gt, reinterpret_cast<float4 *>(pos_target), num_pos,
+                      seed_len >= 3 ? const_cast<int32_t *>(seed) + 2 : (int32_t *)nullptr);
 }
 
 cudaError_t launch_assign_sample_rcnn(const float *props5, const uint8_t *prop_mask, int B, int P,
@@ -528,10 +534,9 @@ cudaError_t launch_assign_sample_rcnn(const float *props5, const uint8_t *prop_m
     SampleSink sink{ sel_idx, sel_idx + Sp, Sp, Sn, S, S, w.cand };
     e = run_samplers(assigned, B, N, Sp, Sn, 2u, seed, seed_len >= 3, cfg, w, sink, s);
     if (e != cudaSuccess) return e;
-    rcnn_finalize_kernel<<<B, 256, 0, s>>>(props5, P, gts, gt_labels, G, cfg, Sp, Sn, w.cand, assigned, sel_idx,
-                                           rois5, reinterpret_cast<float4 *>(deltas), labels, mask, pos_gt, num_pos,
-                                           seed_len >= 3 ? const_cast<int32_t *>(seed) + 2 : nullptr);
-    return cudaGetLastError();
+    return launch_pdl(rcnn_finalize_kernel, dim3(B), dim3(256), 0, s, props5, P, gts, gt_labels, G, cfg, Sp, Sn, w.cand, assigned, sel_idx,
+                      rois5, reinterpret_cast<float4 *>(deltas), labels, mask, pos_gt, num_pos,
+                      seed_len >= 3 ? const_cast<int32_t *>(seed) + 2 : (int32_t *)nullptr);
 }
 
 }  // namespace md

@@ -355,6 +355,7 @@ template <bool LABELS>
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(const NmsSegs sg, const float *__restrict__ cfg, unsigned long long *__restrict__ mask)
 {
+    pdl_entry();
     const int seg = nms_segment(sg, blockIdx.z);
     const int K = sg.dyn_k ? min(sg.K[seg % sg.L], max(__ldg(sg.dyn_k + seg), 0)) : sg.K[seg % sg.L];
     const int nb = (K + 63) >> 6;
@@ -561,8 +562,9 @@ nms_sweep_kernel(const NmsSegs sg, const unsigned long long *__restrict__ mask,
                  const unsigned long long *__restrict__ init_removed /* nullable: (nseg, nbp) boxes dead on entry */,
                  int32_t *__restrict__ keep_pos, int keep_stride, uint8_t *__restrict__ keep_mask,
                  int mask_stride, int32_t *__restrict__ count,
-                 unsigned long long *__restrict__ kept_bits = nullptr /* non-null: only the kept bitmask (nseg, nbp) is written */)
+                 unsigned long long *__restrict__ kept_bits /* non-null: only the kept bitmask (nseg, nbp) is written */)
 {
+    pdl_entry();
     extern __shared__ __align__(16) unsigned long long stage_raw[];
     unsigned long long (*stage)[64 * kSweepMaxNb] = reinterpret_cast<unsigned long long (*)[64 * kSweepMaxNb]>(stage_raw);
     __shared__ unsigned long long diag[kSweepStages][64];    // word c     of the rows of chunk c (the 64 x 64 diagonal block)
@@ -825,7 +827,7 @@ cudaError_t run_nms(const NmsSegs &sg, int nseg, int Kmax, const float *cfg, uns
         NmsSegs sp = sg;
         sp.boxes = reinterpret_cast<const float *>(boxes_p); sp.ld = 4; sp.seg_stride = Kp;
         sp.labels = labels_p; sp.agnostic = nullptr; sp.labels_sorted = 1;
-        nms_mask_kernel<true><<<dim3(tiles, 1, nseg), 64, 0, s>>>(sp, cfg, mask);
+        nms_mask_kernel<true><<<dim3(tiles, 1, nseg), 64, 0, s>>>(sp, cfg, mask);     // behind the permutation kernel: plain launch
         if (nb <= 32) {
             cudaError_t e = cudaFuncSetAttribute(nms_sweep_kernel<32, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes<32, 6>());
             if (e != cudaSuccess) return e;
@@ -840,18 +842,21 @@ cudaError_t run_nms(const NmsSegs &sg, int nseg, int Kmax, const float *cfg, uns
     }
     if (tiles > 0) {
         const dim3 grid = kMaskGroup == 1 ? dim3(tiles, 1, nseg) : dim3(nb, (nb + kMaskGroup - 1) / kMaskGroup, nseg);
-        if (sg.labels) nms_mask_kernel<true><<<grid, 64, 0, s>>>(sg, cfg, mask);
-        else nms_mask_kernel<false><<<grid, 64, 0, s>>>(sg, cfg, mask);
+        cudaError_t e = sg.labels ? launch_pdl(nms_mask_kernel<true>, grid, dim3(64), 0, s, sg, cfg, mask)
+                                  : launch_pdl(nms_mask_kernel<false>, grid, dim3(64), 0, s, sg, cfg, mask);
+        if (e != cudaSuccess) return e;
     }
     if (nb <= 32) {
         // the attribute is per DEVICE and the value is a constant: set it on every launch (no process-wide "done" flag)
         cudaError_t e = cudaFuncSetAttribute(nms_sweep_kernel<32, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes<32, 6>());
         if (e != cudaSuccess) return e;
-        nms_sweep_kernel<32, 6><<<nseg, kSweepThreads, sweep_smem_bytes<32, 6>(), s>>>(sg, mask, nullptr, keep_pos, keep_stride, keep_mask, mask_stride, count);
+        return launch_pdl(nms_sweep_kernel<32, 6>, dim3(nseg), dim3(kSweepThreads), sweep_smem_bytes<32, 6>(), s, sg, mask, (const unsigned long long *)nullptr,
+                          keep_pos, keep_stride, keep_mask, mask_stride, count, (unsigned long long *)nullptr);
     } else {
         cudaError_t e = cudaFuncSetAttribute(nms_sweep_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes<64, 4>());
         if (e != cudaSuccess) return e;
-        nms_sweep_kernel<64, 4><<<nseg, kSweepThreads, sweep_smem_bytes<64, 4>(), s>>>(sg, mask, nullptr, keep_pos, keep_stride, keep_mask, mask_stride, count);
+        return launch_pdl(nms_sweep_kernel<64, 4>, dim3(nseg), dim3(kSweepThreads), sweep_smem_bytes<64, 4>(), s, sg, mask, (const unsigned long long *)nullptr,
+                          keep_pos, keep_stride, keep_mask, mask_stride, count, (unsigned long long *)nullptr);
     }
     return cudaGetLastError();
 }
@@ -866,11 +871,11 @@ cudaError_t launch_nms_sweep_single(const unsigned long long *mask, const unsign
     if (nb <= 32) {
         cudaError_t e = cudaFuncSetAttribute(nms_sweep_kernel<32, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes<32, 6>());
         if (e != cudaSuccess) return e;
-        nms_sweep_kernel<32, 6><<<1, kSweepThreads, sweep_smem_bytes<32, 6>(), s>>>(sg, mask, init_removed, keep_pos, n, keep_mask, n, count);
+        nms_sweep_kernel<32, 6><<<1, kSweepThreads, sweep_smem_bytes<32, 6>(), s>>>(sg, mask, init_removed, keep_pos, n, keep_mask, n, count, nullptr);
     } else {
         cudaError_t e = cudaFuncSetAttribute(nms_sweep_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes<64, 4>());
         if (e != cudaSuccess) return e;
-        nms_sweep_kernel<64, 4><<<1, kSweepThreads, sweep_smem_bytes<64, 4>(), s>>>(sg, mask, init_removed, keep_pos, n, keep_mask, n, count);
+        nms_sweep_kernel<64, 4><<<1, kSweepThreads, sweep_smem_bytes<64, 4>(), s>>>(sg, mask, init_removed, keep_pos, n, keep_mask, n, count, nullptr);
     }
     return cudaGetLastError();
 }

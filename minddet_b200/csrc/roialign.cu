@@ -12,6 +12,7 @@
 
 #include "kernels.h"
 #include "roialign_common.cuh"
+#include "launch.cuh"
 
 namespace md {
 
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(kRoiThreads)
 roialign_fwd_gather_kernel(const RoiFeat f, const float *__restrict__ rois5, int R, int P, int csplit,
                            float *__restrict__ out, const int32_t *__restrict__ only_flagged)
 {
+    pdl_entry();
     __shared__ Tap taps[kRoiMaxTaps];
     // grid.x <= R: a block walks RoIs blockIdx.x, blockIdx.x + gridDim.x, ... (as the fallback behind the TMA kernel the
     // grid is a few blocks per SM and nearly every RoI is skipped after one flag load)
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(kRoiThreads)
 roialign_bwd_gather_kernel(const RoiFeat f, const float *__restrict__ rois5, int R, int P, int csplit,
                            const float *__restrict__ dout, const int32_t *__restrict__ only_flagged)
 {
+    pdl_entry();
     __shared__ Tap taps[kRoiMaxTaps];
     for (int r = blockIdx.x; r < R; r += gridDim.x) {      // see roialign_fwd_gather_kernel
         if (only_flagged && !only_flagged[r]) continue;
@@ -204,8 +207,8 @@ cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, in
         if (e != cudaSuccess) return e;
     }
     const int csplit = fs.C >= 64 ? 4 : 1;
-    roialign_fwd_gather_kernel<<<dim3(tma ? (R < 148 ? R : 148) : R, csplit), kRoiThreads, 0, s>>>(f, rois5, R, P, csplit, out, tma ? flags : nullptr);
-    return cudaGetLastError();
+    return launch_pdl(roialign_fwd_gather_kernel, dim3(tma ? (R < 148 ? R : 148) : R, csplit), dim3(kRoiThreads), 0, s, f, rois5, R, P, csplit, out,
+                      tma ? (const int32_t *)flags : (const int32_t *)nullptr);
 }
 
 cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
@@ -228,8 +231,8 @@ cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, in
         if (e != cudaSuccess) return e;
     }
     const int csplit = fs.C >= 64 ? 4 : 1;
-    roialign_bwd_gather_kernel<<<dim3(tma ? (R < 148 ? R : 148) : R, csplit), kRoiThreads, 0, s>>>(f, rois5, R, P, csplit, dout, tma ? flags : nullptr);
-    return cudaGetLastError();
+    return launch_pdl(roialign_bwd_gather_kernel, dim3(tma ? (R < 148 ? R : 148) : R, csplit), dim3(kRoiThreads), 0, s, f, rois5, R, P, csplit, dout,
+                      tma ? (const int32_t *)flags : (const int32_t *)nullptr);
 }
 
 }  // namespace md

@@ -36,6 +36,7 @@
 #include "roialign_common.cuh"
 #include "tma_host.h"
 #include "tma_ptx.cuh"
+#include "launch.cuh"
 
 namespace md {
 
@@ -149,6 +150,7 @@ roialign_fwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
                            const float *__restrict__ rois5, const int R, const int seg, const int nchunk,
                            float *__restrict__ out, int32_t *__restrict__ fallback_flag)
 {
+    pdl_entry();
     constexpr int S = 2, NS = P * S, PP = P * P;
     constexpr int kUFloats = P * 160;                     // max over LPC of CPW * P * (4*LPC + 4)
     extern __shared__ __align__(128) unsigned char dsm[];
@@ -413,6 +415,7 @@ roialign_bwd_stream_kernel(const __grid_constant__ TmaMaps maps, const RoiFeat f
                            const float *__restrict__ rois5, const int R, const int seg, const int nchunk,
                            const float *__restrict__ dout, int32_t *__restrict__ fallback_flag)
 {
+    pdl_entry();
     static_assert(P == 7 || P == 14, "backward stream kernel: 7x7 (box head) and 14x14 (mask head)");
     constexpr int S = 2, NS = P * S, PP = P * P;
     constexpr int QP = P <= 8 ? 8 : 16;                   // dY rows padded to a multiple of 4 floats
@@ -737,8 +740,7 @@ static cudaError_t launch_fwd(const TmaMaps &maps, const RoiFeat &f, int mask, c
         if (e != cudaSuccess) return e;
     }
     const int nchunk = chunks_for(f.C);
-    kern<<<R * nchunk, kStThreads, fwd_smem<P>(), s>>>(maps, f, mask, rois5, R, kSegRois, nchunk, out, flag);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3(R * nchunk), dim3(kStThreads), fwd_smem<P>(), s, maps, f, mask, rois5, R, kSegRois, nchunk, out, flag);
 }
 
 cudaError_t launch_roialign_fwd_tma(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P,
@@ -764,8 +766,7 @@ static cudaError_t launch_bwd(const TmaMaps &maps, const RoiFeat &f, int mask, c
         if (e != cudaSuccess) return e;
     }
     const int nchunk = chunks_for(f.C);
-    kern<<<R * nchunk, kStThreads, bwd_smem<P>(), s>>>(maps, f, mask, rois5, R, kSegRois, nchunk, dout, flag);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3(R * nchunk), dim3(kStThreads), bwd_smem<P>(), s, maps, f, mask, rois5, R, kSegRois, nchunk, dout, flag);
 }
 
 cudaError_t launch_roialign_bwd_tma(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P,

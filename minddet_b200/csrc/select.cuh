@@ -30,6 +30,7 @@
 #endif
 
 #include "common.cuh"
+#include "launch.cuh"
 
 namespace md {
 namespace cg = cooperative_groups;
@@ -591,6 +592,7 @@ template <class Src, class Sink>
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSelThreads)
 select_sorted_kernel(const Src src, const Sink sink, const int cache_elems)
 {
+    pdl_entry();
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     SelShared &sh = *reinterpret_cast<SelShared *>(dyn_smem);
     uint32_t *keys = reinterpret_cast<uint32_t *>(dyn_smem + sizeof(SelShared));
@@ -635,8 +637,7 @@ cudaError_t launch_select_sorted(const Src &src, const Sink &sink, int nclusters
             if (e != cudaSuccess) return e;
         }
     }
-    kern<<<dim3(nseg * kClusterSize), dim3(kSelThreads), dyn, stream>>>(src, sink, cache);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3(nseg * kClusterSize), dim3(kSelThreads), dyn, stream, src, sink, cache);
 }
 
 }  // namespace md
