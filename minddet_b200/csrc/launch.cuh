@@ -9,7 +9,8 @@
 // programmatic dependency.  MD_PDL=0 switches the attribute off.
 // Measured (config 2): MdProposal alone 148.6 -> 141.6 us, the step 0.986 -> 0.981 ms.  An EARLY trigger
 // (`griddepcontrol.launch_dependents` at the top of every kernel) was worse, 175.7 us / 1.05 ms: the waiting CTAs of the
-// successors take the shared memory and thread slots the other Proposal lane's 8-CTA clusters need.
+// successors take the shared memory and thread slots the other Proposal lane's 8-CTA clusters need; early triggers in the
+// target-assignment kernels alone: 0.990 vs 0.984 ms.
 #pragma once
 #include <cuda_runtime.h>
 
