@@ -843,9 +843,36 @@ def run_b200(args):
         torch.cuda.empty_cache()
         g64 = global64_measure(world, rank, K, W)
 
+    # The platform's host->device ceiling with every rank copying at once and nothing else running: the same pinned feature
+    # buffers, copies only (no kernels).  e2e is PCIe / host-memory bound, so this is what its scaling can reach at best.
+    copy_gbps = None
+    try:
+        src_t = max(host["feats"], key=lambda x: x.numel())
+        dst_t = torch.empty_like(src_t, device="cuda")
+        cs = torch.cuda.Stream()
+        if world > 1:
+            dist.barrier()
+        with torch.cuda.stream(cs):
+            dst_t.copy_(src_t, non_blocking=True)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(4):
+                dst_t.copy_(src_t, non_blocking=True)
+            c1.record()
+        cs.synchronize()
+        copy_gbps = 4 * src_t.numel() * src_t.element_size() / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del dst_t
+    except Exception:
+        copy_gbps = None
+
     per_rank = [ms]
     parity_ranks = [parity]
+    per_rank_copy = [copy_gbps]
     if world > 1:
+        tc = torch.tensor([copy_gbps or 0.0], device="cuda")
+        allc = [torch.zeros_like(tc) for _ in range(world)]
+        dist.all_gather(allc, tc)
+        per_rank_copy = [float(x[0]) for x in allc]
         t = torch.tensor([ms, e2e_ms], device="cuda")
         allr = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allr, t)
@@ -929,6 +956,9 @@ def run_b200(args):
             "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
                     "h2d_GBps_per_rank": [h2d_bytes / (t * 1e-3) / 1e9 for t in per_rank_e2e],
+                    "h2d_copy_only_GBps_per_rank": per_rank_copy,
+                    "h2d_copy_only_note": "all ranks copying the 550 MB pinned level-0 feature tensor at once, nothing else running: "
+                                          "the platform's host-to-device ceiling for this many GPUs",
                     "readback": "a token sample of the results (sampled ids, targets, RoIs, top-100 proposals, 4 RoI feature maps, "
                                 "8 gradient values per level): the real consumers of roi_feats / dX are on-device heads"},
             "gpu_launches": nk * K,
