@@ -7,8 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmdregion.so")
-SOURCES = ["proposal.cu", "assign.cu", "roialign.cu", "roialign_tma.cu", "roialign_ch.cu", "bev.cu", "yolo.cu", "rcnn_post.cu", "aot_entry.cu"]
-HEADERS = ["common.cuh", "select.cuh", "nms.cuh", "kernels.h", "roialign_common.cuh", "tma_ptx.cuh", "tma_host.h", "launch.cuh", os.path.join("..", "..", "include", "md_region_aot.h")]
+SOURCES = ["proposal.cu", "assign.cu", "roialign.cu", "roialign_tma.cu", "roialign_ch.cu", "roialign_tile.cu", "bev.cu", "yolo.cu", "rcnn_post.cu", "aot_entry.cu"]
+HEADERS = ["common.cuh", "select.cuh", "nms.cuh", "kernels.h", "roialign_common.cuh", "tma_ptx.cuh", "tma_host.h", "roialign_tile_plan.h", "launch.cuh", os.path.join("..", "..", "include", "md_region_aot.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "-cudart", "static", "-Xptxas", "-v"]

@@ -9,6 +9,8 @@
 //   * scratch comes from a per-(device,stream) grow-only workspace that is never freed or moved while the library is
 //     loaded (safe under CUDA-graph replay), not cudaMalloc/cudaFree per call (:510-517);
 //   * errors are returned, never exit()ed (:32-40).
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -111,7 +113,11 @@ int64_t numel(int nd, const int64_t *sh)
     for (int i = 0; i < nd; i++) n *= sh[i];
     return n;
 }
-int cuda_rc(cudaError_t e) { return e == cudaSuccess ? MD_OK : (e == cudaErrorInvalidValue ? MD_ERR_SIZE : MD_ERR_CUDA); }
+int cuda_rc(cudaError_t e)
+{
+    if (e != cudaSuccess && getenv("MD_VERBOSE")) fprintf(stderr, "[mdregion] CUDA error %d: %s\n", (int)e, cudaGetErrorString(e));
+    return e == cudaSuccess ? MD_OK : (e == cudaErrorInvalidValue ? MD_ERR_SIZE : MD_ERR_CUDA);
+}
 
 #define REQ(cond) do { if (!(cond)) return MD_ERR_ARG; } while (0)
 #define NEED_ARGS() do { if (!params || !ndims || !shapes || !dtypes) return MD_ERR_ARG; } while (0)
@@ -373,7 +379,7 @@ static int roialign_bwd_impl(int mode, MD_AOT_ARGS)
     const int P = (int)shapes[1][2];
     void *ws = nullptr;
     int *ctl = nullptr;
-    rc = get_workspace(stream, md::roialign_workspace_bytes(R), &ws, &ctl);
+    rc = get_workspace(stream, md::roialign_bwd_workspace_bytes(fs, R), &ws, &ctl);
     if (rc) return rc;
     return cuda_rc(md::launch_roialign_bwd(fs, (const float *)params[0], R, P, (const float *)params[2],
                                            (const float *)params[1], ws, ctl, mode, (cudaStream_t)stream));
@@ -395,7 +401,7 @@ static int roialign_bwd_acc_impl(MD_AOT_ARGS)
     const int P = (int)shapes[1][2];
     void *ws = nullptr;
     int *ctl = nullptr;
-    rc = get_workspace(stream, md::roialign_workspace_bytes(R), &ws, &ctl);
+    rc = get_workspace(stream, md::roialign_bwd_workspace_bytes(fs, R), &ws, &ctl);
     if (rc) return rc;
     rc = cuda_rc(cudaMemsetAsync(params[nparam - 1], 0, sizeof(int32_t), (cudaStream_t)stream));
     if (rc) return rc;

@@ -86,6 +86,7 @@ cudaError_t launch_mask_targets(const uint8_t *masks, int B, int G, int H, int W
                                 int R, int M, const float *cfg, uint8_t *out, cudaStream_t s);
 cudaError_t launch_roi_levels(const float *rois5, int R, const float *cfg, int32_t *out, cudaStream_t s);
 size_t roialign_workspace_bytes(int R);
+size_t roialign_bwd_workspace_bytes(const FeatSet &fs, int R);   // + the tile-stationary backward's plans and lists
 // mode (cfg slot MD_ROI_MODE): 0 = TMA separable kernels (+ gather for RoIs they decline), 1 = gather only
 // ctl: the (device, stream) control block (zero-initialised ints that persist between calls; the channel-lane kernels keep
 // their work tickets in ctl[MD_CTL_ROI_FWD ..] / ctl[MD_CTL_ROI_BWD ..] and re-arm them before they exit)

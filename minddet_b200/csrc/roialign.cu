@@ -185,10 +185,15 @@ cudaError_t launch_roialign_fwd_ch(const FeatSet &fs, const RoiFeat &f, const fl
 cudaError_t launch_roialign_bwd_ch(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, const float *dout,
                                    int32_t *fallback_flag, void *plan_ws, cudaStream_t s, bool *launched);
 size_t roialign_ch_workspace_bytes(int R);
+// roialign_tile.cu: tile-stationary backward (7x7, S = 2, C % 32 == 0): every dX byte written once, no zero-fill
+cudaError_t launch_roialign_bwd_tile(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, const float *dout,
+                                     int32_t *flags, void *tile_ws, bool accumulate, cudaStream_t s, bool *launched);
+size_t roialign_tile_workspace_bytes(const FeatSet &fs, int R);
 
 // flags (R ints, padded) + the channel-lane kernels' per-RoI plans
 static size_t roi_flag_bytes(int R) { return ((size_t)(R > 0 ? R : 0) * sizeof(int32_t) + 255) & ~(size_t)255; }
 size_t roialign_workspace_bytes(int R) { return roi_flag_bytes(R) + roialign_ch_workspace_bytes(R) + 256; }
+size_t roialign_bwd_workspace_bytes(const FeatSet &fs, int R) { return roialign_workspace_bytes(R) + roialign_tile_workspace_bytes(fs, R); }
 
 // mode: 0 = TMA separable kernel + gather for the RoIs it declines (default); 1 = gather only (bit-exact fwd)
 cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
@@ -215,6 +220,22 @@ cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, in
                                 const float *dout, void *ws, int *ctl, int mode, cudaStream_t s, bool accumulate)
 {
     if (P * P * 4 > kRoiMaxTaps || fs.L > kMaxLv) return cudaErrorInvalidValue;
+    const int csplit = fs.C >= 64 ? 4 : 1;
+    // the tile-stationary kernel writes every dX byte once: no zero-fill, no reduce-adds.  MdRoiAlignBwdAcc (accumulate into the
+    // caller's tensors) keeps the scatter-add kernels unless MD_ROI_TILE_ACC=1: adding means reading all of dX back.
+    const char *tile_acc_env = getenv("MD_ROI_TILE_ACC");
+    const bool tile_acc = tile_acc_env && atoi(tile_acc_env) != 0;
+    if (R > 0 && mode == 0 && ws && (!accumulate || tile_acc)) {
+        const RoiFeat f = to_roifeat(fs, cfg);
+        int32_t *flags = reinterpret_cast<int32_t *>(ws);
+        bool tile = false;
+        cudaError_t e = launch_roialign_bwd_tile(fs, f, rois5, R, P, dout, flags, reinterpret_cast<unsigned char *>(ws) + roialign_workspace_bytes(R),
+                                                 accumulate, s, &tile);
+        if (e != cudaSuccess) return e;
+        if (tile)
+            return launch_pdl(roialign_bwd_gather_kernel, dim3(R < 148 ? R : 148, csplit), dim3(kRoiThreads), 0, s, f, rois5, R, P, csplit, dout,
+                              (const int32_t *)flags);
+    }
     for (int l = 0; l < fs.L && !accumulate; l++) {
         cudaError_t e = cudaMemsetAsync(fs.feat[l], 0, (size_t)fs.B * fs.C * fs.H[l] * fs.W[l] * sizeof(float), s);
         if (e != cudaSuccess) return e;
@@ -230,7 +251,6 @@ cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, in
         if (!tma) e = launch_roialign_bwd_tma(fs, f, rois5, R, P, dout, flags, s, &tma);
         if (e != cudaSuccess) return e;
     }
-    const int csplit = fs.C >= 64 ? 4 : 1;
     return launch_pdl(roialign_bwd_gather_kernel, dim3(tma ? (R < 148 ? R : 148) : R, csplit), dim3(kRoiThreads), 0, s, f, rois5, R, P, csplit, dout,
                       tma ? (const int32_t *)flags : (const int32_t *)nullptr);
 }

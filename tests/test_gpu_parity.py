@@ -408,6 +408,64 @@ def test_roialign_channel_lane_kernels_vs_oracle(C, monkeypatch):
     for l in range(4):
         np.testing.assert_allclose(host(ft[l].grad), dref[l], rtol=1e-5, atol=1e-5 * max(1.0, np.abs(dref[l]).max()))
 
+@pytest.mark.parametrize("C,S,acc", [(32, 2, False), (256, 2, False), (64, 2, True), (32, 1, False)])
+def test_roialign_tile_backward_vs_oracle(C, S, acc, monkeypatch):
+    """The tile-stationary backward (roialign_tile.cu: every dX byte written once, no zero-fill): compact, tall, wide, edge-clamped,
+    outside and bad-batch RoIs on all four levels, many RoIs per tile; the output tensors start as garbage (nothing may rely on
+    a zero-fill).  acc: the accumulating form (MD_ROI_TILE_ACC=1) through MdRoiAlignBwdAcc.  S = 1: the plan declines every
+    RoI, so the tile kernel writes zeros and the gather kernel adds everything."""
+    monkeypatch.setenv("MD_ROI_TILE", "1")
+    if acc:
+        monkeypatch.setenv("MD_ROI_TILE_ACC", "1")
+    rng = np.random.default_rng(47)
+    B = 2
+    shapes = synth.level_shapes()[:4]
+    strides = synth.STRIDES[:4]
+    n = 3000 if C <= 64 else 600
+    rois = _rois(rng, n, B)
+    rois[0, 1:] = [-30, -30, 40, 50]
+    rois[1, 1:] = [1300, 760, 1343, 799]
+    rois[2, 1:] = [20, 20, 20.4, 20.2]
+    rois[3, 1:] = [0, 0, 1343, 799]
+    rois[4, 1:] = [100, 5, 130, 790]
+    rois[5, 1:] = [5, 100, 1300, 130]
+    rois[6, 1:] = [-500, -500, -300, -300]
+    rois[7, 1:] = [300, 300, 301, 301]
+    rois[8, 1:] = [10, 10, 450, 120]
+    rois[9, 1:] = [40, 40, 67, 67]
+    rois[10, 0] = -1
+    rois[11, 0] = B
+    rois[12, 1:] = [1342, 798, 1400, 900]
+    rois[13:40, 1:] = rois[13:40, 1:] * 0.05 + np.array([600, 400, 600, 400], np.float32)   # a crowd on a few tiles
+    ext = SingleRoIExtractor(7, S, strides, 56)
+    dout = rng.uniform(-1, 1, (n, C, 7, 7)).astype(np.float32)
+    dref = O.roialign_bwd([(B, C, h, w) for h, w in shapes], strides, rois, dout, S=S)
+    if acc:
+        base = [rng.uniform(-1, 1, (B, C, h, w)).astype(np.float32) for h, w in shapes]
+        got = ext._backward_into(dev(rois), dev(dout), [dev(b) for b in base])
+    else:
+        base = [np.zeros((B, C, h, w), np.float32) for h, w in shapes]
+        junk = [torch.full((B, C, h, w), float("nan"), device="cuda") for h, w in shapes]   # recycled by the caching allocator
+        del junk
+        got = ext._backward(dev(rois), dev(dout), [(B, C, h, w) for h, w in shapes])
+    for l in range(4):
+        tol = 1e-5 * max(1.0, np.abs(dref[l]).max())
+        np.testing.assert_allclose(host(got[l]), base[l] + dref[l], rtol=1e-5, atol=2 * tol if acc else tol)
+
+
+def test_roialign_tile_backward_is_deterministic():
+    """Lists are built in RoI order, so two runs give bit-identical gradients (the scatter-add kernels do not)."""
+    rng = np.random.default_rng(48)
+    B, C = 2, 64
+    shapes = synth.level_shapes()[:4]
+    rois = dev(_rois(rng, 2000, B))
+    dout = torch.rand(2000, C, 7, 7, device="cuda") * 2 - 1
+    ext = SingleRoIExtractor()
+    a = ext._backward(rois, dout, [(B, C, h, w) for h, w in shapes])
+    b = ext._backward(rois, dout, [(B, C, h, w) for h, w in shapes])
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
 
 def test_roialign_bwd_accumulates_into_caller_tensors():
     """MdRoiAlignBwdAcc: acc_l += ROIAlignGrad(dout).  Starting from zeros it is the plain bprop (oracle), starting
