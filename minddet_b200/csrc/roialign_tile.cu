@@ -6,8 +6,9 @@
 //   plan   tile_plan_kernel, one thread per RoI: the separable operators of the RoI (roialign_tile_plan.h: <= 28 touched
 //          feature rows x 7 bin weights; columns dense for footprints <= 16 wide, per bin otherwise), a 16-byte header, and
 //          one count per 8 x 32-pixel dX tile the footprint overlaps.
-//   fill   tile_fill_kernel, one warp per non-empty tile: the RoIs overlapping the tile, in RoI order (ballot + prefix over the
-//          headers, so the order -- and with it the floating-point sum -- is deterministic run to run).
+//   lists  tile_offsets_kernel (one thread per tile: its slice of the list buffer) + tile_scatter_kernel (one thread per RoI
+//          drops its index into every tile it overlaps, in any order); the main kernel visits a tile's RoIs in increasing
+//          index order (warp-wide "smallest entry above the previous one"), so the floating-point sum is deterministic.
 //   main   tile_bwd_kernel, persistent single-warp CTAs, work item = (tile, 32 channels), LANE = CHANNEL: the 8 x 32 x 32-channel
 //          accumulator tile lives in shared memory as [row][channel][33] (odd pitch: conflict-free for lane = channel and for the
 //          lane = column read-out; slot 32 of every row is a dump slot for columns outside the tile).  Per RoI of the tile's list
@@ -46,25 +47,38 @@ constexpr int kStageBytes = kDyBytes + kPlanBytes;
 constexpr int kWytBytes = kTH * 8 * 4;                           // 256
 constexpr int kCotBytes = 32 * 4;
 constexpr int kTileSmem = kTileBytes + kStageBytes + kWytBytes + kCotBytes + 16;
+constexpr int kTileCtasPerSm = (227 * 1024) / (kTileSmem + 1024) < 16 ? (227 * 1024) / (kTileSmem + 1024) : 16;   // 1 KB per CTA is reserved by the system
 static_assert(kTileBytes % 16 == 0 && kDyBytes % 16 == 0 && kPlanBytes % 16 == 0, "bulk copies are 16-byte granular");
+
+// a work item of the main kernel: kChunk (default) consecutive visits of one tile's sorted list, for every channel group
+struct __align__(16) Item {
+    int t, chunk, nchunk, nv;          // tile, chunk index, chunks of the tile, visits in this chunk (0: nobody touches the tile)
+    int first, list, lb, tyx;          // first RoI of the chunk, offset of its list slice, level | image << 8, tile row | column << 16
+};
+static_assert(sizeof(Item) == 32, "item layout");
 
 struct TileArgs {
     Grid g;
-    int C, R, ncg, nitems;
+    int C, R, ncg, chunk, item_cap;
     float *feat[kMaxLv];
     const float *dout;
     const Plan *plans;
-    const int2 *tiles;          // per tile: {offset into lists, count}
-    const int *lists;
+    const int4 *tiles;          // per tile: {offset into lists, count, first item, items}
+    const int *lists;           // per tile: RoI indices, ascending
+    const Item *items;          // crowded tiles (more than one chunk) from the front, the others from the back: the long items
+                                // get the early tickets
+    const int *counters;        // [0] list cursor, [1] ticket, [2] items at the front, [3] items at the back
     int *ticket;
-    long long feat_elems[kMaxLv], lists_cap;
-    int dbg;     // MD_TILE_CHECK builds: extents for the device-side range checks
 };
+constexpr int kChunk = 16;      // default visits per work item: bounds the longest item (a crowd puts > 100 RoIs on one tile)
 
 // ---- plan + count ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-tile_plan_kernel(const __grid_constant__ RoiFeat f, const __grid_constant__ Grid g, const float *__restrict__ rois5, const int R, Plan *__restrict__ plans,
-                 Hdr *__restrict__ hdr, int *__restrict__ cnt, int32_t *__restrict__ flag)
+// One thread per RoI.  The plan is assembled in LOCAL memory (L1-resident: 32-thread blocks keep it at 52 KB per SM) and
+// copied out once; building it in place cost ~200 dependent global read-modify-writes per thread (50 us for 4096 RoIs).
+constexpr int kPlanThreads = 32;
+__global__ void __launch_bounds__(kPlanThreads)
+tile_plan_kernel(const __grid_constant__ RoiFeat f, const __grid_constant__ Grid g, const float *__restrict__ rois5, const int R,
+                 Plan *__restrict__ plans, Hdr *__restrict__ hdr, int *__restrict__ cnt, int32_t *__restrict__ flag)
 {
     pdl_entry();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,11 +87,22 @@ tile_plan_kernel(const __grid_constant__ RoiFeat f, const __grid_constant__ Grid
 #pragma unroll
     for (int k = 0; k < 5; k++) roi[k] = __ldg(rois5 + (int64_t)r * 5 + k);
     int b, l;
-    Plan &pl = plans[r];
+    Plan pl;
     plan_roi(roi, f.B, f.L, f.H, f.W, f.cfg, pl, b, l);
     hdr[r] = make_hdr(pl, b, l);
     flag[r] = pl.status == ST_DECLINE;
     if (pl.status != ST_OK) return;
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(&pl);
+        int4 *dst = reinterpret_cast<int4 *>(plans + r);
+        constexpr int kHead = (int)((sizeof(Plan) - sizeof(pl.xw) - sizeof(pl.bin)) / 16);
+        const int nhead = 2 + 2 * pl.nrows;                                  // header + the rows in use
+        for (int i = 0; i < nhead; i++) dst[i] = src[i];
+        if (pl.wide)
+            for (int i = kHead + (int)sizeof(pl.xw) / 16; i < (int)sizeof(Plan) / 16; i++) dst[i] = src[i];
+        else
+            for (int i = kHead; i < kHead + 2 * pl.ncols; i++) dst[i] = src[i];
+    }
     for (int ty = pl.y0 / kTH; ty <= pl.y1 / kTH; ty++)
         for (int tx = pl.x0 / kTW; tx <= pl.x1 / kTW; tx++) atomicAdd(cnt + tile_id(g, l, b, ty, tx), 1);
 }
@@ -92,78 +117,210 @@ MD_DEVINL void decode_tile(const Grid &g, int t, int &l, int &b, int &ty, int &t
     ty = rem / g.ntx[l]; tx = rem - ty * g.ntx[l];
 }
 
-// ---- lists ----------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-tile_fill_kernel(const __grid_constant__ Grid g, const Hdr *__restrict__ hdr, const int R, const int *__restrict__ cnt, int2 *__restrict__ tiles,
-                 int *__restrict__ cursor, int *__restrict__ lists)
+// ---- lists: offsets (one thread per tile), then one thread per RoI drops its index into every tile it overlaps -------
+__global__ void __launch_bounds__(256)
+tile_offsets_kernel(const __grid_constant__ TileArgs a, int *__restrict__ cnt, int4 *__restrict__ tiles, int *__restrict__ counters,
+                    Item *__restrict__ items)
 {
     pdl_entry();
-    const int lane = threadIdx.x & 31;
-    const int T = g.base[g.L];
-    for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < T; t += gridDim.x * (blockDim.x >> 5)) {
-        const int c = cnt[t];
-        int off = 0;
-        if (lane == 0 && c) off = atomicAdd(cursor, c);
-        off = __shfl_sync(0xffffffffu, off, 0);
-        if (lane == 0) tiles[t] = make_int2(off, c);
-        if (!c) continue;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.g.base[a.g.L]) return;
+    const int c = cnt[t];
+    cnt[t] = 0;                                                              // re-used as the tile's fill cursor
+    const int off = c ? atomicAdd(counters + 0, c) : 0;
+    const int nch = c ? (c + a.chunk - 1) / a.chunk : 1;
+    // items of a crowded tile go to the front of the array (early tickets), everything else fills it from the back
+    const int it = nch > 1 ? atomicAdd(counters + 2, nch) : a.item_cap - 1 - atomicAdd(counters + 3, 1);
+    tiles[t] = make_int4(off, c, it, nch);
+    int l, b, ty, tx;
+    decode_tile(a.g, t, l, b, ty, tx);
+    for (int k = 0; k < nch; k++) {
+        Item im;
+        im.t = t; im.chunk = k; im.nchunk = nch;
+        im.nv = min(a.chunk, c - k * a.chunk);
+        im.first = 0;                                                        // filled by tile_sort_kernel
+        im.list = off + k * a.chunk;
+        im.lb = l | (b << 8);
+        im.tyx = ty | (tx << 16);
+        items[it + k] = im;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+tile_scatter_kernel(const __grid_constant__ Grid g, const Hdr *__restrict__ hdr, const int R, int *__restrict__ cnt,
+                    const int4 *__restrict__ tiles, int *__restrict__ lists)
+{
+    pdl_entry();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int4 h = __ldg(reinterpret_cast<const int4 *>(hdr) + r);
+    if ((h.x & 0xff) != ST_OK) return;
+    const int l = (h.x >> 8) & 0xff, b = h.x >> 16;
+    for (int ty = (h.z & 0xffff) / kTH; ty <= (h.z >> 16) / kTH; ty++)
+        for (int tx = (h.y & 0xffff) / kTW; tx <= (h.y >> 16) / kTW; tx++) {
+            const int t = tile_id(g, l, b, ty, tx);
+            lists[tiles[t].x + atomicAdd(cnt + t, 1)] = r;                   // any order: the main kernel visits in RoI order
+        }
+}
+
+// one block per tile: its list into ascending RoI order (rank = number of smaller entries; entries are distinct)
+constexpr int kSortThreads = 256, kSortSmem = 2048;
+__global__ void __launch_bounds__(kSortThreads)
+tile_sort_kernel(const __grid_constant__ TileArgs a, int *__restrict__ lists, Item *__restrict__ items, const int zero_chunked)
+{
+    pdl_entry();
+    __shared__ int sh[kSortSmem];
+    const int4 rec = a.tiles[blockIdx.x];
+    if (rec.y == 1 && threadIdx.x == 0) items[rec.z].first = lists[rec.x];
+    if (zero_chunked && rec.y > a.chunk) {                                   // several items will add into this tile: zeros first
         int l, b, ty, tx;
-        decode_tile(g, t, l, b, ty, tx);
-        const int key = ST_OK | (l << 8) | (b << 16);
-        int pos = off;
-        for (int base = 0; base < R; base += 32) {
-            const int r = base + lane;
-            bool hit = false;
-            if (r < R) {
-                const int4 h = __ldg(reinterpret_cast<const int4 *>(hdr) + r);
-                hit = h.x == key && (h.y & 0xffff) / kTW <= tx && (h.y >> 16) / kTW >= tx && (h.z & 0xffff) / kTH <= ty &&
-                      (h.z >> 16) / kTH >= ty;
+        decode_tile(a.g, blockIdx.x, l, b, ty, tx);
+        const int H = a.g.H[l], W = a.g.W[l], ty0 = ty * kTH, tx0 = tx * kTW;
+        const int nrow = min(kTH, H - ty0), ncol = min(kTW, W - tx0);
+        float *const base = a.feat[l] + ((int64_t)b * a.C * H + ty0) * W + tx0;
+        const int lane = threadIdx.x & 31;
+        for (int c = threadIdx.x >> 5; c < a.C; c += kSortThreads / 32)                  // one 128-byte row per warp and step
+            for (int row = 0; row < nrow; row++)
+                if (lane < ncol) base[((int64_t)c * H + row) * W + lane] = 0.0f;
+    }
+    if (rec.y < 2) return;
+    int *list = lists + rec.x;
+    if (rec.y <= kSortSmem) {
+        for (int i = threadIdx.x; i < rec.y; i += kSortThreads) sh[i] = list[i];
+        __syncthreads();
+        for (int i = threadIdx.x; i < rec.y; i += kSortThreads) {
+            const int e = sh[i];
+            int rank = 0;
+            for (int j = 0; j < rec.y; j++) rank += sh[j] < e;
+            list[rank] = e;
+        }
+    } else {                                                                 // a list too long for shared memory: selection in place
+        for (int i = 0; i < rec.y; i++) {                                    // (slow; only a degenerate input gets here)
+            __syncthreads();
+            int best = 0x7fffffff, bj = -1;
+            for (int j = i + threadIdx.x; j < rec.y; j += kSortThreads)
+                if (list[j] < best) { best = list[j]; bj = j; }
+            __shared__ int sb[kSortThreads], sj[kSortThreads];
+            sb[threadIdx.x] = best; sj[threadIdx.x] = bj;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int k = 1; k < kSortThreads; k++)
+                    if (sb[k] < best) { best = sb[k]; bj = sj[k]; }
+                const int tmp = list[i]; list[i] = best; list[bj] = tmp;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (hit) lists[pos + __popc(m & ((1u << lane) - 1))] = r;
-            pos += __popc(m);
         }
     }
+    __syncthreads();
+    for (int k = threadIdx.x; k < rec.w; k += kSortThreads) items[rec.z + k].first = list[k * a.chunk];
 }
 
 // ---- main -----------------------------------------------------------------------------------------------------------
 MD_DEVINL float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 
-
-// Dense plans: the touched rows of one visit.  G = ceil(n / 4) column groups; the tile loads of a row are issued before its
-// 49-FMA y-step (which hides their latency), the x-step is G x 4 independent 7-FMA chains, stores are predicated on k < n.
+// Dense plans: one visit.  G = ceil(n / 4) column groups.  The constructor pulls the column weights of the 4 G in-tile columns
+// into registers (after it the stage can be refilled); rows() walks the touched rows: the tile loads of a row are issued
+// before its 49-FMA y-step (which hides their latency), the x-step is 4 G independent 7-FMA chains, loads / stores of the
+// last group are predicated on k < n.
 template <int G>
-MD_DEVINL void dense_rows(unsigned m, const int n, const float *__restrict__ wyt, float *__restrict__ tp0, const float (&d)[kP * kP],
-                          const float (&wk)[kDenseCols][kP])
-{
-    while (m) {
-        const int i = __ffs(m) - 1;
-        m &= m - 1;
-        float *const tp = tp0 + i * kTileRowFloats;
-        float acc[4 * G];
+struct DenseVisit {
+    float wk[4 * G][kP];
+    MD_DEVINL DenseVisit(const Plan *__restrict__ spl, const int ja)
+    {
 #pragma unroll
-        for (int k = 0; k < 4 * G; k++) acc[k] = (k < 4 * (G - 1) || k < n) ? tp[k] : 0.0f;
-        const float4 wa = *reinterpret_cast<const float4 *>(wyt + i * 8), wb = *reinterpret_cast<const float4 *>(wyt + i * 8 + 4);
-        const float wy[kP] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
-        float V[kP];
-#pragma unroll
-        for (int q = 0; q < kP; q++) {
-            V[q] = wy[0] * d[q];
-#pragma unroll
-            for (int p = 1; p < kP; p++) V[q] = fma_(wy[p], d[p * kP + q], V[q]);
+        for (int k = 0; k < 4 * G; k++) {
+            const float4 *src = reinterpret_cast<const float4 *>(spl->xw[min(ja + k, kDenseCols - 1)]);
+            const float4 w0 = src[0], w1 = src[1];
+            wk[k][0] = w0.x; wk[k][1] = w0.y; wk[k][2] = w0.z; wk[k][3] = w0.w;
+            wk[k][4] = w1.x; wk[k][5] = w1.y; wk[k][6] = w1.z;
         }
+    }
+    MD_DEVINL void rows(unsigned m, const int n, const float *__restrict__ wyt, float *__restrict__ tp0, const float (&d)[kP * kP]) const
+    {
+        while (m) {
+            const int i = __ffs(m) - 1;
+            m &= m - 1;
+            float *const tp = tp0 + i * kTileRowFloats;
+            float acc[4 * G];
 #pragma unroll
-        for (int q = 0; q < kP; q++)
+            for (int k = 0; k < 4 * G; k++) acc[k] = (k < 4 * (G - 1) || k < n) ? tp[k] : 0.0f;
+            const float4 wa = *reinterpret_cast<const float4 *>(wyt + i * 8), wb = *reinterpret_cast<const float4 *>(wyt + i * 8 + 4);
+            const float wy[kP] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
+            float V[kP];
 #pragma unroll
-            for (int k = 0; k < 4 * G; k++) acc[k] = fma_(wk[k][q], V[q], acc[k]);
+            for (int q = 0; q < kP; q++) {
+                V[q] = wy[0] * d[q];
 #pragma unroll
-        for (int k = 0; k < 4 * G; k++)
-            if (k < 4 * (G - 1) || k < n) tp[k] = acc[k];
+                for (int p = 1; p < kP; p++) V[q] = fma_(wy[p], d[p * kP + q], V[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < kP; q++)
+#pragma unroll
+                for (int k = 0; k < 4 * G; k++) acc[k] = fma_(wk[k][q], V[q], acc[k]);
+#pragma unroll
+            for (int k = 0; k < 4 * G; k++)
+                if (k < 4 * (G - 1) || k < n) tp[k] = acc[k];
+        }
+    }
+};
+
+MD_DEVINL void red_add_v4(float4 *p, const float4 v)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// 128-byte rows out of the tile.  MODE 0: streaming stores; 1: dX += tile (this warp owns the pixels); 2: reductions at L2
+// (several items share the pixels)
+template <int MODE>
+MD_DEVINL void tile_readout(const float *__restrict__ tile_s, float *__restrict__ gbase, const int H, const int W, const int nrow, const int ncol,
+                            const bool vec, const int lane)
+{
+    if (vec) {
+        // lane = (channel of 4, 16-byte piece): four pitch-33 loads (conflict-free: banks c + 4 piece + j) -> one 16-byte access
+        const int cq = lane >> 3, piece = lane & 7;
+        const float *src = tile_s + cq * kTilePitch + piece * 4;
+        float *dst = gbase + (int64_t)cq * H * W + piece * 4;
+        const int64_t cstep = (int64_t)4 * H * W;
+        for (int cb = 0; cb < kTC / 4; cb++, src += 4 * kTilePitch, dst += cstep) {
+#pragma unroll
+            for (int i = 0; i < kTH; i++) {
+                if (i < nrow) {
+                    const float *sp = src + i * kTileRowFloats;
+                    float4 val = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                    float4 *gp = reinterpret_cast<float4 *>(dst + (int64_t)i * W);
+                    if (MODE == 2) {
+                        red_add_v4(gp, val);
+                    } else {
+                        if (MODE == 1) {
+                            const float4 old = __ldcs(gp);
+                            val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+                        }
+                        __stcs(gp, val);
+                    }
+                }
+            }
+        }
+    } else {
+        for (int c = 0; c < kTC; c++) {
+            const float *src = tile_s + c * kTilePitch + lane;
+            float *dst = gbase + (int64_t)c * H * W + lane;
+#pragma unroll
+            for (int i = 0; i < kTH; i++) {
+                if (i < nrow && lane < ncol) {
+                    float val = src[i * kTileRowFloats];
+                    if (MODE == 2) {
+                        atomicAdd(dst + i * W, val);
+                    } else {
+                        if (MODE == 1) val += __ldcs(dst + i * W);
+                        __stcs(dst + i * W, val);
+                    }
+                }
+            }
+        }
     }
 }
 
 template <bool ACC>
-__global__ void __launch_bounds__(32, 5)
+__global__ void __launch_bounds__(32, kTileCtasPerSm)
 tile_bwd_kernel(const __grid_constant__ TileArgs a)
 {
     pdl_entry();
@@ -180,42 +337,57 @@ tile_bwd_kernel(const __grid_constant__ TileArgs a)
     __syncwarp();
     uint32_t parity = 0;
     float *const tlane = tile_s + lane * kTilePitch;
+    const int nfront = __ldg(a.counters + 2), nback = __ldg(a.counters + 3);
+    const int ntickets = (nfront + nback) * a.ncg;
 
-    for (;;) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(a.ticket, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= a.nitems) break;
-        const int t = item / a.ncg, c0 = (item - t * a.ncg) * kTC;
-        int l, b, ty, tx;
-        decode_tile(a.g, t, l, b, ty, tx);
+    // Software pipeline over work items: the ticket of item i + 2 is requested and the record of item i + 1 is loaded while
+    // item i is being worked on, and the first copies of item i + 1 start as soon as the last visit of item i has left the
+    // stage -- the chain ticket -> record -> copies (three dependent round trips to L2) is off the critical path.
+    auto take = [&]() {
+        int tk = 0;
+        if (lane == 0) tk = atomicAdd(a.ticket, 1);
+        return __shfl_sync(0xffffffffu, tk, 0);
+    };
+    auto record = [&](int tk, Item &im, int &c0) {
+        const int di = tk / a.ncg;
+        c0 = (tk - di * a.ncg) * kTC;
+        const int idx = di < nfront ? di : a.item_cap - 1 - (di - nfront);
+        const int4 *p = reinterpret_cast<const int4 *>(a.items + idx);
+        const int4 u = __ldg(p), w = __ldg(p + 1);
+        im.t = u.x; im.chunk = u.y; im.nchunk = u.z; im.nv = u.w;
+        im.first = w.x; im.list = w.y; im.lb = w.z; im.tyx = w.w;
+    };
+    auto issue = [&](int r, int c0) {
+        if (lane == 0) {
+            mbar_expect_tx(bar, kStageBytes);
+            bulk_load_1d(stage, a.dout + ((int64_t)r * a.C + c0) * (kP * kP), kDyBytes, bar);
+            bulk_load_1d(stage + kDyBytes, a.plans + r, kPlanBytes, bar);
+        }
+    };
+
+    int tk_cur = take(), tk_n1 = take();
+    Item cur{}, nxt{};
+    int c0 = 0, c0n = 0;
+    if (tk_cur < ntickets) {
+        record(tk_cur, cur, c0);
+        if (cur.nv > 0) issue(cur.first, c0);
+    }
+    while (tk_cur < ntickets) {
+        const int tk_n2 = take();
+        const bool have_next = tk_n1 < ntickets;
+        if (have_next) record(tk_n1, nxt, c0n);
+        const int l = cur.lb & 0xff, b = cur.lb >> 8, ty = cur.tyx & 0xffff, tx = cur.tyx >> 16;
         const int H = a.g.H[l], W = a.g.W[l];
         const int ty0 = ty * kTH, tx0 = tx * kTW;
-        int2 rec = __ldg(a.tiles + t);
-        if (a.dbg == 11) rec.y = 0;
-#ifdef MD_TILE_CHECK
-        if (l < 0 || l >= a.g.L || b < 0 || b >= a.g.B || ty < 0 || ty >= a.g.nty[l] || tx < 0 || tx >= a.g.ntx[l] || rec.y < 0 || rec.x < 0 ||
-            rec.y > a.R || c0 + kTC > a.C) {
-            if (lane == 0) printf("tile check: item %d t %d l %d b %d ty %d tx %d rec %d %d c0 %d\n", item, t, l, b, ty, tx, rec.x, rec.y, c0);
-            continue;
-        }
-#endif
         float *const gbase = a.feat[l] + (((int64_t)b * a.C + c0) * H + ty0) * W + tx0;
         const int nrow = min(kTH, H - ty0), ncol = min(kTW, W - tx0);
+        const bool vec = ncol == kTW && (W & 3) == 0;       // 128-byte rows, 16-byte aligned
+        const int nv = cur.nv;
 
-#ifdef MD_TILE_CHECK
-        {
-            const long long first = (((long long)b * a.C + c0) * H + ty0) * W + tx0;
-            const long long last = first + ((long long)(kTC - 1) * H + (nrow - 1)) * W + (ncol - 1);
-            if (first < 0 || last >= a.feat_elems[l] || nrow < 1 || ncol < 1 || (rec.y > 0 && rec.x + (long long)rec.y > a.lists_cap)) {
-                if (lane == 0) printf("tile check: extent t %d l %d b %d ty %d tx %d first %lld last %lld of %lld nrow %d ncol %d rec %d %d\n", t, l, b, ty, tx, first, last, a.feat_elems[l], nrow, ncol, rec.x, rec.y);
-                continue;
-            }
-        }
-#endif
-        if (rec.y == 0) {                                   // no RoI touches this tile: zeros (or nothing, when accumulating)
+        if (nv == 0) {                                      // no RoI touches this tile: zeros (or nothing, when accumulating)
+            if (have_next && nxt.nv > 0) issue(nxt.first, c0n);
             if (!ACC) {
-                if (ncol == kTW && (W & 3) == 0) {          // 128-byte rows, 16-byte aligned: lane = (row of 4, 16-byte piece)
+                if (vec) {                                  // lane = (row of 4, 16-byte piece)
                     float4 *p = reinterpret_cast<float4 *>(gbase + (int64_t)(lane >> 3) * W) + (lane & 7);
                     const bool lo = (lane >> 3) < nrow, hi = (lane >> 3) + 4 < nrow;
                     for (int c = 0; c < kTC; c++, p += (int64_t)H * W / 4) {
@@ -228,175 +400,125 @@ tile_bwd_kernel(const __grid_constant__ TileArgs a)
                             if (lane < ncol) __stcs(gbase + ((int64_t)c * H + row) * W + lane, 0.0f);
                 }
             }
-            continue;
-        }
-
-        if (a.dbg == 12) rec.y = 0;
-        const int *const list = a.lists + rec.x;
-        auto issue = [&](int r) {
-#ifdef MD_TILE_CHECK
-            if (r < 0 || r >= a.R) { if (lane == 0) printf("tile check: list entry %d (t %d rec %d %d)\n", r, t, rec.x, rec.y); r = 0; }
-#endif
-            if (lane == 0) {
-                mbar_expect_tx(bar, kStageBytes);
-                bulk_load_1d(stage, a.dout + ((int64_t)r * a.C + c0) * (kP * kP), kDyBytes, bar);
-                bulk_load_1d(stage + kDyBytes, a.plans + r, kPlanBytes, bar);
-            }
-        };
-        if (rec.y) issue(__ldg(list));
-        {
-            float4 *z = reinterpret_cast<float4 *>(tile_s);
-#pragma unroll 6
-            for (int i = lane; i < kTileBytes / 16; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncwarp();
-
-        for (int v = 0; v < rec.y; v++) {
-            mbar_wait(bar, parity);
-            parity ^= 1;
-            // ---- everything the visit needs leaves the stage now, so the next visit's copies can start
-            float d[kP * kP];
-#pragma unroll
-            for (int k = 0; k < kP * kP; k++) d[k] = sdy[lane * (kP * kP) + k];
-            const int wide = spl->wide, nrows = spl->nrows, ncols = spl->ncols, x0 = spl->x0;
-            if (a.dbg == 13) {
-                __syncwarp();
-                if (v + 1 < rec.y) issue(__ldg(list + v + 1));
-                continue;
-            }
-#ifdef MD_TILE_CHECK
-            if (nrows < 0 || nrows > kMaxRows || ncols < 1 || x0 < 0 || x0 >= W || (!wide && ncols > kDenseCols) || spl->status != ST_OK ||
-                x0 >= tx0 + kTW || x0 + ncols <= tx0) {
-                if (lane == 0) printf("tile check: plan t %d v %d r %d wide %d nrows %d ncols %d x0 %d status %d tx0 %d\n", t, v, list[v], wide, nrows, ncols, x0, spl->status, tx0);
-                __syncwarp();
-                if (v + 1 < rec.y) issue(__ldg(list + v + 1));
-                continue;
-            }
-#endif
-            unsigned rowmask;
+        } else {
+            const int *const list = a.lists + cur.list;
             {
-                unsigned bit = 0;
-                if (lane < nrows) {
-                    const int yy = spl->row[lane].y - ty0;
-                    if (yy >= 0 && yy < kTH) {
-                        bit = 1u << yy;
-                        const float4 *src = reinterpret_cast<const float4 *>(&spl->row[lane]);
-                        float4 w0 = src[0], w1 = src[1];
-                        float4 *dst = reinterpret_cast<float4 *>(wyt + yy * 8);
-                        dst[0] = make_float4(w0.y, w0.z, w0.w, w1.x);          // w[0..3]  (src[0].x is the row index)
-                        dst[1] = make_float4(w1.y, w1.z, w1.w, 0.0f);          // w[4..6]
-                    }
-                }
-                rowmask = __reduce_or_sync(0xffffffffu, bit);        // bit = tile row
+                float4 *z = reinterpret_cast<float4 *>(tile_s);
+#pragma unroll 6
+                for (int i = lane; i < kTileBytes / 16; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (!wide) {
-                const int ja = max(0, tx0 - x0), n = min(ncols, tx0 + kTW - x0) - ja;
-                float wk[kDenseCols][kP];
+            __syncwarp();
+
+            for (int v = 0; v < nv; v++) {
+                const bool last = v + 1 == nv;
+                const int rnext = last ? 0 : __ldg(list + v + 1);
+                // once the visit has read everything it needs from the stage: the next visit's copies, or the next item's first
+                auto refill = [&]() {
+                    if (!last) issue(rnext, c0);
+                    else if (have_next && nxt.nv > 0) issue(nxt.first, c0n);
+                };
+                mbar_wait(bar, parity);
+                parity ^= 1;
+                float d[kP * kP];
 #pragma unroll
-                for (int k = 0; k < kDenseCols; k++) {
-                    if (k < n) {
-                        const float4 *src = reinterpret_cast<const float4 *>(spl->xw[ja + k]);
-                        const float4 w0 = src[0], w1 = src[1];
-                        wk[k][0] = w0.x; wk[k][1] = w0.y; wk[k][2] = w0.z; wk[k][3] = w0.w;
-                        wk[k][4] = w1.x; wk[k][5] = w1.y; wk[k][6] = w1.z;
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < kP; q++) wk[k][q] = 0.0f;
+                for (int k = 0; k < kP * kP; k++) d[k] = sdy[lane * (kP * kP) + k];
+                const int wide = spl->wide, nrows = spl->nrows, ncols = spl->ncols, x0 = spl->x0;
+                unsigned rowmask;
+                {
+                    unsigned bit = 0;
+                    if (lane < nrows) {
+                        const int yy = spl->row[lane].y - ty0;
+                        if (yy >= 0 && yy < kTH) {
+                            bit = 1u << yy;
+                            const float4 *src = reinterpret_cast<const float4 *>(&spl->row[lane]);
+                            float4 w0 = src[0], w1 = src[1];
+                            float4 *dst = reinterpret_cast<float4 *>(wyt + yy * 8);
+                            dst[0] = make_float4(w0.y, w0.z, w0.w, w1.x);          // w[0..3]  (src[0].x is the row index)
+                            dst[1] = make_float4(w1.y, w1.z, w1.w, 0.0f);          // w[4..6]
+                        }
                     }
+                    rowmask = __reduce_or_sync(0xffffffffu, bit);                  // bit = tile row
                 }
-                __syncwarp();
-                if (v + 1 < rec.y) issue(__ldg(list + v + 1));
-                float *const tp0 = tlane + (x0 + ja - tx0);
-                switch ((n + 3) >> 2) {                       // row loop specialised on the number of 4-column groups
-                case 1: dense_rows<1>(rowmask, n, wyt, tp0, d, wk); break;
-                case 2: dense_rows<2>(rowmask, n, wyt, tp0, d, wk); break;
-                case 3: dense_rows<3>(rowmask, n, wyt, tp0, d, wk); break;
-                default: dense_rows<4>(rowmask, n, wyt, tp0, d, wk); break;
-                }
-            } else {
-                if (lane < 4 * kP) {
-                    const int col = spl->bin[lane >> 2].col[lane & 3];
-                    cot[lane] = (col >= tx0 && col < tx0 + kTW) ? col - tx0 : kTW;
-                }
-                float cw[4 * kP];
-#pragma unroll
-                for (int q = 0; q < kP; q++) {
-                    const float4 w = *reinterpret_cast<const float4 *>(spl->bin[q].w);
-                    cw[q * 4 + 0] = w.x; cw[q * 4 + 1] = w.y; cw[q * 4 + 2] = w.z; cw[q * 4 + 3] = w.w;
-                }
-                __syncwarp();
-                int co[4 * kP];
-#pragma unroll
-                for (int q = 0; q < kP; q++) {
-                    const int4 o = *reinterpret_cast<const int4 *>(cot + q * 4);
-                    co[q * 4 + 0] = o.x; co[q * 4 + 1] = o.y; co[q * 4 + 2] = o.z; co[q * 4 + 3] = o.w;
-                }
-                __syncwarp();
-#ifdef MD_TILE_CHECK
-                if (a.dbg == 21 && lane == 0 && c0 == 0) {
-                    printf("wide visit t %d r %d rowmask %x tx0 %d ty0 %d\n", t, list[v], rowmask, tx0, ty0);
-                    for (int q = 0; q < kP; q++)
-                        printf("  q %d co %d %d %d %d cw %.3f %.3f %.3f %.3f plan col %d %d %d %d\n", q, co[q * 4], co[q * 4 + 1], co[q * 4 + 2], co[q * 4 + 3],
-                               cw[q * 4], cw[q * 4 + 1], cw[q * 4 + 2], cw[q * 4 + 3], spl->bin[q].col[0], spl->bin[q].col[1], spl->bin[q].col[2], spl->bin[q].col[3]);
-                }
-                __syncwarp();
-#endif
-                if (v + 1 < rec.y) issue(__ldg(list + v + 1));
-#pragma unroll
-                for (int i = 0; i < kTH; i++) {
-                    if (!((rowmask >> i) & 1u)) continue;
-                    const float4 wa = *reinterpret_cast<const float4 *>(wyt + i * 8), wb = *reinterpret_cast<const float4 *>(wyt + i * 8 + 4);
-                    const float wy[kP] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
-                    float V[kP];
+                if (!wide) {
+                    const int ja = max(0, tx0 - x0), n = min(ncols, tx0 + kTW - x0) - ja;
+                    float *const tp0 = tlane + (x0 + ja - tx0);
+                    switch ((n + 3) >> 2) {                       // specialised on the number of 4-column groups
+                    case 1: { DenseVisit<1> dv(spl, ja); __syncwarp(); refill(); dv.rows(rowmask, n, wyt, tp0, d); } break;
+                    case 2: { DenseVisit<2> dv(spl, ja); __syncwarp(); refill(); dv.rows(rowmask, n, wyt, tp0, d); } break;
+                    case 3: { DenseVisit<3> dv(spl, ja); __syncwarp(); refill(); dv.rows(rowmask, n, wyt, tp0, d); } break;
+                    default: { DenseVisit<4> dv(spl, ja); __syncwarp(); refill(); dv.rows(rowmask, n, wyt, tp0, d); } break;
+                    }
+                } else {
+                    if (lane < 4 * kP) {
+                        const int col = spl->bin[lane >> 2].col[lane & 3];
+                        cot[lane] = (col >= tx0 && col < tx0 + kTW) ? col - tx0 : kTW;
+                    }
+                    float cw[4 * kP];
 #pragma unroll
                     for (int q = 0; q < kP; q++) {
-                        V[q] = wy[0] * d[q];
-#pragma unroll
-                        for (int p = 1; p < kP; p++) V[q] = fma_(wy[p], d[p * kP + q], V[q]);
+                        const float4 w = *reinterpret_cast<const float4 *>(spl->bin[q].w);
+                        cw[q * 4 + 0] = w.x; cw[q * 4 + 1] = w.y; cw[q * 4 + 2] = w.z; cw[q * 4 + 3] = w.w;
                     }
-                    float *const tp = tlane + i * kTileRowFloats;
+                    __syncwarp();
+                    int co[4 * kP];
 #pragma unroll
-                    for (int ph = 0; ph < 2; ph++) {              // bins {0,2,4,6}, then {1,3,5}: distinct columns inside a batch
-                        float tv[16];
+                    for (int q = 0; q < kP; q++) {
+                        const int4 o = *reinterpret_cast<const int4 *>(cot + q * 4);
+                        co[q * 4 + 0] = o.x; co[q * 4 + 1] = o.y; co[q * 4 + 2] = o.z; co[q * 4 + 3] = o.w;
+                    }
+                    refill();
+                    unsigned m = rowmask;
+                    while (m) {
+                        const int i = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float4 wa = *reinterpret_cast<const float4 *>(wyt + i * 8), wb = *reinterpret_cast<const float4 *>(wyt + i * 8 + 4);
+                        const float wy[kP] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
+                        float V[kP];
 #pragma unroll
-                        for (int q = ph; q < kP; q += 2)
+                        for (int q = 0; q < kP; q++) {
+                            V[q] = wy[0] * d[q];
 #pragma unroll
-                            for (int s = 0; s < 4; s++) tv[(q >> 1) * 4 + s] = tp[co[q * 4 + s]];
+                            for (int p = 1; p < kP; p++) V[q] = fma_(wy[p], d[p * kP + q], V[q]);
+                        }
+                        float *const tp = tlane + i * kTileRowFloats;
 #pragma unroll
-                        for (int q = ph; q < kP; q += 2)
+                        for (int ph = 0; ph < 2; ph++) {              // bins {0,2,4,6}, then {1,3,5}: distinct columns inside a batch
+                            float tv[16];
 #pragma unroll
-                            for (int s = 0; s < 4; s++) tv[(q >> 1) * 4 + s] = fma_(cw[q * 4 + s], V[q], tv[(q >> 1) * 4 + s]);
+                            for (int q = ph; q < kP; q += 2)
 #pragma unroll
-                        for (int q = ph; q < kP; q += 2)
+                                for (int s = 0; s < 4; s++) tv[(q >> 1) * 4 + s] = tp[co[q * 4 + s]];
 #pragma unroll
-                            for (int s = 0; s < 4; s++) tp[co[q * 4 + s]] = tv[(q >> 1) * 4 + s];
+                            for (int q = ph; q < kP; q += 2)
+#pragma unroll
+                                for (int s = 0; s < 4; s++) tv[(q >> 1) * 4 + s] = fma_(cw[q * 4 + s], V[q], tv[(q >> 1) * 4 + s]);
+#pragma unroll
+                            for (int q = ph; q < kP; q += 2)
+#pragma unroll
+                                for (int s = 0; s < 4; s++) tp[co[q * 4 + s]] = tv[(q >> 1) * 4 + s];
+                        }
                     }
                 }
+                __syncwarp();                                    // wyt / cot are rewritten by the next visit
             }
-            __syncwarp();                                    // wyt / cot are rewritten by the next visit
-        }
 
-        // ---- read-out: lane = column, 128-byte rows of streaming stores
-        for (int c = 0; c < kTC; c++) {
-            const float *src = tile_s + c * kTilePitch + lane;
-            float *dst = gbase + (int64_t)c * H * W + lane;
-#pragma unroll
-            for (int i = 0; i < kTH; i++) {
-                if (i < nrow && lane < ncol) {
-                    float val = src[i * kTileRowFloats];
-                    if (ACC) val += __ldcs(dst + i * W);
-                    __stcs(dst + i * W, val);
-                }
-            }
+            // ---- read-out.  A tile whose list was cut into several items was zero-filled by tile_sort_kernel (unless the
+            // call accumulates anyway) and every item adds its partial sums with vector reductions at L2; other tiles are
+            // stored once.
+            if (cur.nchunk > 1) tile_readout<2>(tile_s, gbase, H, W, nrow, ncol, vec, lane);
+            else if (ACC) tile_readout<1>(tile_s, gbase, H, W, nrow, ncol, vec, lane);
+            else tile_readout<0>(tile_s, gbase, H, W, nrow, ncol, vec, lane);
+            __syncwarp();
         }
-        __syncwarp();
+        cur = nxt; c0 = c0n;
+        tk_cur = tk_n1; tk_n1 = tk_n2;
     }
 }
 
 // ---- host -----------------------------------------------------------------------------------------------------------
 static size_t al256(size_t n) { return (n + 255) & ~(size_t)255; }
 
-struct TileLayout { size_t ctl, cnt, tiles, hdr, plans, lists, total; int T, cap; };
+struct TileLayout { size_t ctl, cnt, zero_end, tiles, hdr, plans, lists, items, total; int T, cap, item_cap; };
 static TileLayout tile_layout(const FeatSet &fs, int R)
 {
     Grid g;
@@ -409,10 +531,13 @@ static TileLayout tile_layout(const FeatSet &fs, int R)
     size_t off = 0;
     o.ctl = off; off += 256;                                 // cursor, ticket
     o.cnt = off; off += al256((size_t)o.T * sizeof(int));
-    o.tiles = off; off += al256((size_t)o.T * sizeof(int2));
+    o.zero_end = off;                                        // [ctl, zero_end) is cleared at the top of every call
+    o.tiles = off; off += al256((size_t)o.T * sizeof(int4));
     o.hdr = off; off += al256((size_t)R * sizeof(Hdr));
     o.plans = off; off += al256((size_t)R * sizeof(Plan));
     o.lists = off; off += al256((size_t)o.cap * sizeof(int));
+    o.item_cap = o.T + o.cap + 1;
+    o.items = off; off += al256((size_t)o.item_cap * sizeof(Item));
     o.total = off;
     return o;
 }
@@ -446,35 +571,38 @@ cudaError_t launch_roialign_bwd_tile(const FeatSet &fs, const RoiFeat &f, const 
         if ((e = cudaFuncSetAttribute(tile_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem)) != cudaSuccess) return e;
         sms[dev] = n;
     }
-    const char *dbg_env = getenv("MD_TILE_DEBUG");
-    const int dbg = dbg_env ? atoi(dbg_env) : 0;
     const TileLayout lo = tile_layout(fs, R);
     unsigned char *w = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tile_ws) + 255) & ~(uintptr_t)255);
     TileArgs a{};
     make_grid(a.g, fs.L, fs.B, fs.H, fs.W);
-    a.C = fs.C; a.R = R; a.ncg = fs.C / kTC; a.nitems = lo.T * a.ncg;
+    a.C = fs.C; a.R = R; a.ncg = fs.C / kTC; a.item_cap = lo.item_cap;
     for (int l = 0; l < fs.L; l++) a.feat[l] = fs.feat[l];
     a.dout = dout;
     a.plans = reinterpret_cast<const Plan *>(w + lo.plans);
-    a.tiles = reinterpret_cast<const int2 *>(w + lo.tiles);
+    a.tiles = reinterpret_cast<const int4 *>(w + lo.tiles);
     a.lists = reinterpret_cast<const int *>(w + lo.lists);
+    a.items = reinterpret_cast<const Item *>(w + lo.items);
     int *ctl = reinterpret_cast<int *>(w + lo.ctl);
+    a.counters = ctl;
     a.ticket = ctl + 1;
-    for (int l = 0; l < fs.L; l++) a.feat_elems[l] = (long long)fs.B * fs.C * fs.H[l] * fs.W[l];
-    a.lists_cap = lo.cap;
-    a.dbg = dbg;
-    if ((e = cudaMemsetAsync(w + lo.ctl, 0, lo.cnt + al256((size_t)lo.T * sizeof(int)) - lo.ctl, s)) != cudaSuccess) return e;
-    tile_plan_kernel<<<(R + 127) / 128, 128, 0, s>>>(f, a.g, rois5, R, reinterpret_cast<Plan *>(w + lo.plans),
-                                                      reinterpret_cast<Hdr *>(w + lo.hdr), reinterpret_cast<int *>(w + lo.cnt), flags);
+    {
+        const char *ce = getenv("MD_TILE_CHUNK");
+        a.chunk = ce && atoi(ce) > 0 ? atoi(ce) : kChunk;
+        if (a.chunk > 32767) a.chunk = 32767;
+    }
+    if ((e = cudaMemsetAsync(w + lo.ctl, 0, lo.zero_end - lo.ctl, s)) != cudaSuccess) return e;
+    tile_plan_kernel<<<(R + kPlanThreads - 1) / kPlanThreads, kPlanThreads, 0, s>>>(f, a.g, rois5, R, reinterpret_cast<Plan *>(w + lo.plans),
+                                                                                   reinterpret_cast<Hdr *>(w + lo.hdr),
+                                                                                   reinterpret_cast<int *>(w + lo.cnt), flags);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (dbg == 1) { *launched = true; return cudaSuccess; }
-    const int fill_blocks = (lo.T + 3) / 4;
-    if ((e = launch_pdl(tile_fill_kernel, dim3(fill_blocks), dim3(128), 0, s, a.g, reinterpret_cast<const Hdr *>(w + lo.hdr), R,
-                        reinterpret_cast<const int *>(w + lo.cnt), reinterpret_cast<int2 *>(w + lo.tiles), ctl,
+    if ((e = launch_pdl(tile_offsets_kernel, dim3((lo.T + 255) / 256), dim3(256), 0, s, a, reinterpret_cast<int *>(w + lo.cnt),
+                        reinterpret_cast<int4 *>(w + lo.tiles), ctl, reinterpret_cast<Item *>(w + lo.items))) != cudaSuccess) return e;
+    if ((e = launch_pdl(tile_scatter_kernel, dim3((R + 127) / 128), dim3(128), 0, s, a.g, reinterpret_cast<const Hdr *>(w + lo.hdr), R,
+                        reinterpret_cast<int *>(w + lo.cnt), reinterpret_cast<const int4 *>(w + lo.tiles),
                         reinterpret_cast<int *>(w + lo.lists))) != cudaSuccess) return e;
-    if (dbg == 2) { *launched = true; return cudaSuccess; }
-    const int grid = a.nitems < sms[dev] * 5 ? a.nitems : sms[dev] * 5;
-    if (getenv("MD_VERBOSE")) fprintf(stderr, "[mdregion] tile bwd: T %d items %d grid %d smem %d R %d\n", lo.T, a.nitems, grid, kTileSmem, R);
+    if ((e = launch_pdl(tile_sort_kernel, dim3(lo.T), dim3(kSortThreads), 0, s, a, reinterpret_cast<int *>(w + lo.lists),
+                        reinterpret_cast<Item *>(w + lo.items), accumulate ? 0 : 1)) != cudaSuccess) return e;
+    const int grid = lo.T * a.ncg < sms[dev] * kTileCtasPerSm ? lo.T * a.ncg : sms[dev] * kTileCtasPerSm;
     if (accumulate) e = launch_pdl(tile_bwd_kernel<true>, dim3(grid), dim3(32), (size_t)kTileSmem, s, a);
     else e = launch_pdl(tile_bwd_kernel<false>, dim3(grid), dim3(32), (size_t)kTileSmem, s, a);
     if (e != cudaSuccess) return e;
