@@ -36,7 +36,11 @@ METRIC = "Faster R-CNN RPN+RoI region path throughput"
 UNIT = "img/s"
 BATCH = 8            # images per GPU (weak scaling); --global-batch overrides it
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels (ncu --set full, profiles/README.md)
-NCU_TRAFFIC = {"roialign_fwd": 849e6, "roialign_bwd": 1260e6, "yolo_decode": None}
+NCU_TRAFFIC = {"roialign_fwd": 849e6, "roialign_bwd": 1260e6, "roialign_bwd_tile": 897e6, "yolo_decode": None}
+# RoIAlign backward of the step: "tile" = MdRoiAlignBwd (tile-stationary kernel: every dX byte written once, nothing to zero-fill),
+# "acc" = round 1's form (zero-fill of dX on a side stream + the scatter-add kernel through MdRoiAlignBwdAcc)
+BWD_MODE = os.environ.get("MD_BENCH_BWD", "tile")
+TILE_BWD = BWD_MODE == "tile" and os.environ.get("MD_ROI_TILE", "1") != "0"
 WORKLOADS = {
     2: ("configs[1]: Faster R-CNN R50-FPN region path, batch 8/GPU, 800x1344, 5 levels (268569 anchors), "
         "2000 pre-NMS/level, NMS 0.7, max_num 2000, G<=128 gts, 512 sampled RoIs, 256-ch 7x7 RoIAlign fwd+bwd"),
@@ -596,10 +600,10 @@ def run_b200(args):
             return z_
 
         zeroed = None
-        if overlap and ZERO_AT == "top":
+        if overlap and ZERO_AT == "top" and not TILE_BWD:
             zeroed = start_zero_fill()
         props, pmask = rp.proposal(inp["cls_scores"], inp["bbox_preds"])
-        if overlap and ZERO_AT != "top":
+        if overlap and ZERO_AT != "top" and not TILE_BWD:
             # started after Proposal: the Proposal kernels share the SMs badly with work that wants every SM's store bandwidth
             zeroed = start_zero_fill()
         mark("proposal")
@@ -918,8 +922,9 @@ def run_b200(args):
     alg = {
         # RoI tensor written + exact union of the bilinear footprints read
         "roialign_fwd": out_bytes + fp,
-        # dY read + union footprint updated + zero-init of every dX byte
-        "roialign_bwd": out_bytes + fp + dx_bytes,
+        # scatter form: dY read + union footprint updated + zero-init of every dX byte;
+        # tile-stationary form: dY read + every dX byte written once
+        "roialign_bwd": out_bytes + dx_bytes if TILE_BWD else out_bytes + fp + dx_bytes,
         # scores read + (deltas gathered, boxes written, NMS in/out, proposals out) per image
         "proposal": batch * (n_anchor * 4 + 8819 * (16 + 16 + 8 + 25) + 2000 * 21),
         # anchors + valid read, assigned written and re-read by the samplers
@@ -929,9 +934,12 @@ def run_b200(args):
                      "algorithmic_bytes_per_launch": alg[k], "ms": live_ms[k]} for k in alg}
     dominant = max(("roialign_fwd", "roialign_bwd"), key=lambda k: live_ms[k])
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": rooflines[dominant]["achieved"], "peak": peak, "unit": "GB/s",
-                "frac": rooflines[dominant]["frac"], "traffic": NCU_TRAFFIC.get(dominant),
+                "frac": rooflines[dominant]["frac"],
+                "traffic": NCU_TRAFFIC.get(dominant + "_tile" if dominant == "roialign_bwd" and TILE_BWD else dominant),
                 "algorithmic_bytes_per_launch": alg[dominant], "kernel_ms": live_ms[dominant], "peak_source": peak_src,
-                "note": "stage = the stream kernel + gather kernel for declined RoIs (+ the 4 dX memsets for bwd), timed as six "
+                "bwd_form": "tile-stationary (plan + lists + tile kernel, dX written once)" if TILE_BWD else "scatter-add + dX memsets",
+                "note": "stage = the stream kernel + gather kernel for declined RoIs (+ the 4 dX memsets for the scatter-add bwd; the "
+                        "tile-stationary bwd = its plan / list / sort kernels + the tile kernel, algorithmic bytes dY + dX once), timed as six "
                         "calls back to back with CUDA events on the launching stream (kernel time; the eager per-stage pass "
                         "of stage_ms also holds the host's launch gaps); "
                         "algorithmic bytes = RoI tensor (R*C*49*4) + exact union of bilinear footprints of this step's RoIs "
@@ -948,8 +956,11 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config_dict(args, world, batch),
             "run": {"cuda_graph": graph is not None, "same_seed": bool(args.same_seed), "diag_skip": sorted(DIAG_SKIP), "rpn_at": RPN_AT,
-                    "streams": ("rpn target assignment and the RoIAlign-gradient zero-fill on their own streams (backward accumulates: "
-                                "MdRoiAlignBwdAcc)" if not args.no_overlap else "rpn targets in line, MdRoiAlignBwd zero-fills in line"),
+                    "streams": (("rpn target assignment on its own stream; MdRoiAlignBwd = tile-stationary backward (nothing to zero-fill)"
+                                 if TILE_BWD else
+                                 "rpn target assignment and the RoIAlign-gradient zero-fill on their own streams (backward accumulates: "
+                                 "MdRoiAlignBwdAcc)") if not args.no_overlap else "rpn targets in line, MdRoiAlignBwd in line"),
+                    "roialign_bwd": "tile" if TILE_BWD else "acc",
                     "numa": numa},
             "per_rank_ms": {"min": min(per_rank), "median": float(np.median(per_rank)), "max": max(per_rank), "all": per_rank},
             "clocks": sampler.summary(),

@@ -90,9 +90,10 @@ roialign_fwd_gather_kernel(const RoiFeat f, const float *__restrict__ rois5, int
 
 __global__ void __launch_bounds__(kRoiThreads)
 roialign_bwd_gather_kernel(const RoiFeat f, const float *__restrict__ rois5, int R, int P, int csplit,
-                           const float *__restrict__ dout, const int32_t *__restrict__ only_flagged)
+                           const float *__restrict__ dout, const int32_t *__restrict__ only_flagged, const int32_t *__restrict__ nflagged)
 {
     pdl_entry();
+    if (nflagged && *nflagged == 0) return;                // the tile-stationary kernel counted the RoIs it left to this one
     __shared__ Tap taps[kRoiMaxTaps];
     for (int r = blockIdx.x; r < R; r += gridDim.x) {      // see roialign_fwd_gather_kernel
         if (only_flagged && !only_flagged[r]) continue;
@@ -187,7 +188,7 @@ cudaError_t launch_roialign_bwd_ch(const FeatSet &fs, const RoiFeat &f, const fl
 size_t roialign_ch_workspace_bytes(int R);
 // roialign_tile.cu: tile-stationary backward (7x7, S = 2, C % 32 == 0): every dX byte written once, no zero-fill
 cudaError_t launch_roialign_bwd_tile(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, const float *dout,
-                                     int32_t *flags, void *tile_ws, bool accumulate, cudaStream_t s, bool *launched);
+                                     int32_t *flags, void *tile_ws, bool accumulate, cudaStream_t s, bool *launched, const int32_t **ndecl);
 size_t roialign_tile_workspace_bytes(const FeatSet &fs, int R);
 
 // flags (R ints, padded) + the channel-lane kernels' per-RoI plans
@@ -229,12 +230,13 @@ cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, in
         const RoiFeat f = to_roifeat(fs, cfg);
         int32_t *flags = reinterpret_cast<int32_t *>(ws);
         bool tile = false;
+        const int32_t *ndecl = nullptr;
         cudaError_t e = launch_roialign_bwd_tile(fs, f, rois5, R, P, dout, flags, reinterpret_cast<unsigned char *>(ws) + roialign_workspace_bytes(R),
-                                                 accumulate, s, &tile);
+                                                 accumulate, s, &tile, &ndecl);
         if (e != cudaSuccess) return e;
         if (tile)
             return launch_pdl(roialign_bwd_gather_kernel, dim3(R < 148 ? R : 148, csplit), dim3(kRoiThreads), 0, s, f, rois5, R, P, csplit, dout,
-                              (const int32_t *)flags);
+                              (const int32_t *)flags, (const int32_t *)ndecl);
     }
     for (int l = 0; l < fs.L && !accumulate; l++) {
         cudaError_t e = cudaMemsetAsync(fs.feat[l], 0, (size_t)fs.B * fs.C * fs.H[l] * fs.W[l] * sizeof(float), s);
@@ -252,7 +254,7 @@ cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, in
         if (e != cudaSuccess) return e;
     }
     return launch_pdl(roialign_bwd_gather_kernel, dim3(tma ? (R < 148 ? R : 148) : R, csplit), dim3(kRoiThreads), 0, s, f, rois5, R, P, csplit, dout,
-                      tma ? (const int32_t *)flags : (const int32_t *)nullptr);
+                      tma ? (const int32_t *)flags : (const int32_t *)nullptr, (const int32_t *)nullptr);
 }
 
 }  // namespace md

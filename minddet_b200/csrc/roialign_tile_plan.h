@@ -26,7 +26,7 @@ namespace tile {
 
 constexpr int kP = 7, kS = 2, kNS = kP * kS;
 #ifndef MD_TILE_TH
-#define MD_TILE_TH 8
+#define MD_TILE_TH 4
 #endif
 constexpr int kTH = MD_TILE_TH, kTW = 32, kTC = 32;   // dX tile: rows x columns, channels per warp
 constexpr int kMaxRows = 2 * kNS;                 // every sample row touches <= 2 feature rows
