@@ -59,7 +59,7 @@ static_assert(sizeof(Item) == 32, "item layout");
 
 struct TileArgs {
     Grid g;
-    int C, R, ncg, chunk, item_cap;
+    int C, R, ncg, chunk, item_cap, list_cap;
     float *feat[kMaxLv];
     const float *dout;
     const Plan *plans;
@@ -163,71 +163,81 @@ tile_scatter_kernel(const __grid_constant__ Grid g, const Hdr *__restrict__ hdr,
                     int *__restrict__ cnt, const int4 *__restrict__ tiles, int *__restrict__ lists)
 {
     pdl_entry();
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per RoI, one lane per overlapped tile (a chain of dependent L2 round trips per tile: lanes run them side by side)
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (r >= R) return;
     const int4 h = __ldg(reinterpret_cast<const int4 *>(hdr) + r);
     if ((h.x & 0xff) != ST_OK) return;
     const int l = (h.x >> 8) & 0xff, b = h.x >> 16;
-    const int ty_lo = (h.z & 0xffff) / kTH;
+    const int ty_lo = (h.z & 0xffff) / kTH, nty = (h.z >> 16) / kTH - ty_lo + 1;
+    const int tx_lo = (h.y & 0xffff) / kTW, ntx = (h.y >> 16) / kTW - tx_lo + 1;
     const unsigned long long rmask = __ldg(rowmask + r);
-    for (int ty = ty_lo; ty <= (h.z >> 16) / kTH; ty++) {
-        if (ty - ty_lo < 64 && !((rmask >> (ty - ty_lo)) & 1ull)) continue;      // same rule as the count in tile_plan_kernel
-        for (int tx = (h.y & 0xffff) / kTW; tx <= (h.y >> 16) / kTW; tx++) {
-            const int t = tile_id(g, l, b, ty, tx);
-            lists[tiles[t].x + atomicAdd(cnt + t, 1)] = r;                   // any order: tile_sort_kernel puts it into RoI order
-        }
+    for (int j = lane; j < nty * ntx; j += 32) {
+        const int dy = j / ntx, dx = j - dy * ntx;
+        if (dy < 64 && !((rmask >> dy) & 1ull)) continue;                    // same rule as the count in tile_plan_kernel
+        const int t = tile_id(g, l, b, ty_lo + dy, tx_lo + dx);
+        lists[tiles[t].x + atomicAdd(cnt + t, 1)] = r;                       // any order: tile_sort_kernel puts it into RoI order
     }
 }
 
-// one block per tile: its list into ascending RoI order (rank = number of smaller entries; entries are distinct)
-constexpr int kSortThreads = 256, kSortSmem = 2048;
+// One warp per tile: its list into ascending RoI order (rank = number of smaller entries; entries are distinct) and the first
+// RoI of every chunk into the item records.
+constexpr int kSortThreads = 256;
 __global__ void __launch_bounds__(kSortThreads)
-tile_sort_kernel(const __grid_constant__ TileArgs a, int *__restrict__ lists, Item *__restrict__ items, const int zero_chunked)
+tile_sort_kernel(const __grid_constant__ TileArgs a, int *__restrict__ lists, Item *__restrict__ items)
 {
     pdl_entry();
-    __shared__ int sh[kSortSmem];
-    const int4 rec = a.tiles[blockIdx.x];
-    if (rec.y == 1 && threadIdx.x == 0) items[rec.z].first = lists[rec.x];
-    if (zero_chunked && rec.y > a.chunk) {                                   // several items will add into this tile: zeros first
-        int l, b, ty, tx;
-        decode_tile(a.g, blockIdx.x, l, b, ty, tx);
-        const int H = a.g.H[l], W = a.g.W[l], ty0 = ty * kTH, tx0 = tx * kTW;
-        const int nrow = min(kTH, H - ty0), ncol = min(kTW, W - tx0);
-        float *const base = a.feat[l] + ((int64_t)b * a.C * H + ty0) * W + tx0;
-        const int lane = threadIdx.x & 31;
-        for (int c = threadIdx.x >> 5; c < a.C; c += kSortThreads / 32)                  // one 128-byte row per warp and step
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= a.g.base[a.g.L]) return;
+    const int4 rec = a.tiles[t];
+    if (rec.y == 0) return;
+    int *list = lists + rec.x;
+    if (rec.y <= 32) {
+        const int e = lane < rec.y ? list[lane] : 0x7fffffff;
+        int rank = 0;
+        for (int j = 0; j < rec.y; j++) rank += __shfl_sync(0xffffffffu, e, j) < e;
+        __syncwarp();
+        if (lane < rec.y) list[rank] = e;
+    } else {
+        // longer lists: every lane ranks its entries against the whole list (read through L1); ranks first, writes after
+        int *const scratch = lists + a.list_cap + rec.x;                     // second half of the list buffer: the sorted copy
+        for (int i = lane; i < rec.y; i += 32) {
+            const int e = list[i];
+            int rank = 0;
+            for (int j = 0; j < rec.y; j++) rank += list[j] < e;
+            scratch[rank] = e;
+        }
+        __syncwarp();
+        for (int i = lane; i < rec.y; i += 32) list[i] = scratch[i];
+    }
+    __syncwarp();
+    for (int k = lane; k < rec.w; k += 32) items[rec.z + k].first = list[k * a.chunk];
+}
+
+// One block per tile that was cut into several items (their partial sums are added at L2): zeros first.  Other blocks exit.
+__global__ void __launch_bounds__(256)
+tile_zero_kernel(const __grid_constant__ TileArgs a)
+{
+    pdl_entry();
+    const int t = blockIdx.x;
+    if (a.tiles[t].w <= 1) return;
+    int l, b, ty, tx;
+    decode_tile(a.g, t, l, b, ty, tx);
+    const int H = a.g.H[l], W = a.g.W[l], ty0 = ty * kTH, tx0 = tx * kTW;
+    const int nrow = min(kTH, H - ty0), ncol = min(kTW, W - tx0);
+    float *const base = a.feat[l] + ((int64_t)b * a.C * H + ty0) * W + tx0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (ncol == kTW && (W & 3) == 0) {                                       // lane = (row of 4, 16-byte piece)
+        for (int c = warp; c < a.C; c += 8) {
+            float4 *p = reinterpret_cast<float4 *>(base + ((int64_t)c * H + (lane >> 3)) * W) + (lane & 7);
+            for (int r4 = 0; r4 < kTH; r4 += 4)
+                if ((lane >> 3) + r4 < nrow) p[(int64_t)r4 * W / 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+        for (int c = warp; c < a.C; c += 8)
             for (int row = 0; row < nrow; row++)
                 if (lane < ncol) base[((int64_t)c * H + row) * W + lane] = 0.0f;
     }
-    if (rec.y < 2) return;
-    int *list = lists + rec.x;
-    if (rec.y <= kSortSmem) {
-        for (int i = threadIdx.x; i < rec.y; i += kSortThreads) sh[i] = list[i];
-        __syncthreads();
-        for (int i = threadIdx.x; i < rec.y; i += kSortThreads) {
-            const int e = sh[i];
-            int rank = 0;
-            for (int j = 0; j < rec.y; j++) rank += sh[j] < e;
-            list[rank] = e;
-        }
-    } else {                                                                 // a list too long for shared memory: selection in place
-        for (int i = 0; i < rec.y; i++) {                                    // (slow; only a degenerate input gets here)
-            __syncthreads();
-            int best = 0x7fffffff, bj = -1;
-            for (int j = i + threadIdx.x; j < rec.y; j += kSortThreads)
-                if (list[j] < best) { best = list[j]; bj = j; }
-            __shared__ int sb[kSortThreads], sj[kSortThreads];
-            sb[threadIdx.x] = best; sj[threadIdx.x] = bj;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                for (int k = 1; k < kSortThreads; k++)
-                    if (sb[k] < best) { best = sb[k]; bj = sj[k]; }
-                const int tmp = list[i]; list[i] = best; list[bj] = tmp;
-            }
-        }
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < rec.w; k += kSortThreads) items[rec.z + k].first = list[k * a.chunk];
 }
 
 // ---- main -----------------------------------------------------------------------------------------------------------
@@ -552,7 +562,7 @@ static TileLayout tile_layout(const FeatSet &fs, int R)
     o.hdr = off; off += al256((size_t)R * sizeof(Hdr));
     o.rmask = off; off += al256((size_t)R * sizeof(unsigned long long));
     o.plans = off; off += al256((size_t)R * sizeof(Plan));
-    o.lists = off; off += al256((size_t)o.cap * sizeof(int));
+    o.lists = off; off += al256((size_t)o.cap * 2 * sizeof(int));   // lists + the sort's scratch copy
     o.item_cap = o.T + o.cap + 1;
     o.items = off; off += al256((size_t)o.item_cap * sizeof(Item));
     o.total = off;
@@ -593,7 +603,7 @@ cudaError_t launch_roialign_bwd_tile(const FeatSet &fs, const RoiFeat &f, const 
     unsigned char *w = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tile_ws) + 255) & ~(uintptr_t)255);
     TileArgs a{};
     make_grid(a.g, fs.L, fs.B, fs.H, fs.W);
-    a.C = fs.C; a.R = R; a.ncg = fs.C / kTC; a.item_cap = lo.item_cap;
+    a.C = fs.C; a.R = R; a.ncg = fs.C / kTC; a.item_cap = lo.item_cap; a.list_cap = lo.cap;
     for (int l = 0; l < fs.L; l++) a.feat[l] = fs.feat[l];
     a.dout = dout;
     a.plans = reinterpret_cast<const Plan *>(w + lo.plans);
@@ -616,11 +626,12 @@ cudaError_t launch_roialign_bwd_tile(const FeatSet &fs, const RoiFeat &f, const 
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = launch_pdl(tile_offsets_kernel, dim3((lo.T + 255) / 256), dim3(256), 0, s, a, reinterpret_cast<int *>(w + lo.cnt),
                         reinterpret_cast<int4 *>(w + lo.tiles), ctl, reinterpret_cast<Item *>(w + lo.items))) != cudaSuccess) return e;
-    if ((e = launch_pdl(tile_scatter_kernel, dim3((R + 127) / 128), dim3(128), 0, s, a.g, reinterpret_cast<const Hdr *>(w + lo.hdr),
+    if ((e = launch_pdl(tile_scatter_kernel, dim3((R + 3) / 4), dim3(128), 0, s, a.g, reinterpret_cast<const Hdr *>(w + lo.hdr),
                         reinterpret_cast<const unsigned long long *>(w + lo.rmask), R, reinterpret_cast<int *>(w + lo.cnt), reinterpret_cast<const int4 *>(w + lo.tiles),
                         reinterpret_cast<int *>(w + lo.lists))) != cudaSuccess) return e;
-    if ((e = launch_pdl(tile_sort_kernel, dim3(lo.T), dim3(kSortThreads), 0, s, a, reinterpret_cast<int *>(w + lo.lists),
-                        reinterpret_cast<Item *>(w + lo.items), accumulate ? 0 : 1)) != cudaSuccess) return e;
+    if ((e = launch_pdl(tile_sort_kernel, dim3((lo.T + kSortThreads / 32 - 1) / (kSortThreads / 32)), dim3(kSortThreads), 0, s, a, reinterpret_cast<int *>(w + lo.lists),
+                        reinterpret_cast<Item *>(w + lo.items))) != cudaSuccess) return e;
+    if (!accumulate && (e = launch_pdl(tile_zero_kernel, dim3(lo.T), dim3(256), 0, s, a)) != cudaSuccess) return e;
     const int grid = lo.T * a.ncg < sms[dev] * kTileCtasPerSm ? lo.T * a.ncg : sms[dev] * kTileCtasPerSm;
     if (accumulate) e = launch_pdl(tile_bwd_kernel<true>, dim3(grid), dim3(32), (size_t)kTileSmem, s, a);
     else e = launch_pdl(tile_bwd_kernel<false>, dim3(grid), dim3(32), (size_t)kTileSmem, s, a);
