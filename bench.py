@@ -951,7 +951,7 @@ def run_b200(args):
         restore_affinity()                                         # the CPU arm may use every host core again
         v, cores, busy, sample = cpu_region_throughput(10.0)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "threads_busy": busy, "kind": "port", "sample": sample}
-    nk = launches if launches is not None else (23 + (6 if mask_branch else 0))
+    nk = launches if launches is not None else (pipeline.KERNELS_PER_STEP + (6 if mask_branch else 0))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config_dict(args, world, batch),

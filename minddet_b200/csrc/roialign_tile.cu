@@ -180,13 +180,37 @@ tile_scatter_kernel(const __grid_constant__ Grid g, const Hdr *__restrict__ hdr,
     }
 }
 
+// One block per tile that was cut into several items (their partial sums are added at L2): zeros first.  Other blocks exit.
+MD_DEVINL void tile_zero_block(const TileArgs &a, const int t)
+{
+    if (a.tiles[t].w <= 1) return;
+    int l, b, ty, tx;
+    decode_tile(a.g, t, l, b, ty, tx);
+    const int H = a.g.H[l], W = a.g.W[l], ty0 = ty * kTH, tx0 = tx * kTW;
+    const int nrow = min(kTH, H - ty0), ncol = min(kTW, W - tx0);
+    float *const base = a.feat[l] + ((int64_t)b * a.C * H + ty0) * W + tx0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (ncol == kTW && (W & 3) == 0) {                                       // lane = (row of 4, 16-byte piece)
+        for (int c = warp; c < a.C; c += 8) {
+            float4 *p = reinterpret_cast<float4 *>(base + ((int64_t)c * H + (lane >> 3)) * W) + (lane & 7);
+            for (int r4 = 0; r4 < kTH; r4 += 4)
+                if ((lane >> 3) + r4 < nrow) p[(int64_t)r4 * W / 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+        for (int c = warp; c < a.C; c += 8)
+            for (int row = 0; row < nrow; row++)
+                if (lane < ncol) base[((int64_t)c * H + row) * W + lane] = 0.0f;
+    }
+}
+
 // One warp per tile: its list into ascending RoI order (rank = number of smaller entries; entries are distinct) and the first
 // RoI of every chunk into the item records.
 constexpr int kSortThreads = 256;
 __global__ void __launch_bounds__(kSortThreads)
-tile_sort_kernel(const __grid_constant__ TileArgs a, int *__restrict__ lists, Item *__restrict__ items)
+tile_sort_kernel(const __grid_constant__ TileArgs a, int *__restrict__ lists, Item *__restrict__ items, const int nsort)
 {
     pdl_entry();
+    if ((int)blockIdx.x >= nsort) { tile_zero_block(a, blockIdx.x - nsort); return; }   // the zero-fill blocks ride in the same launch
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (t >= a.g.base[a.g.L]) return;
     const int4 rec = a.tiles[t];
@@ -212,32 +236,6 @@ tile_sort_kernel(const __grid_constant__ TileArgs a, int *__restrict__ lists, It
     }
     __syncwarp();
     for (int k = lane; k < rec.w; k += 32) items[rec.z + k].first = list[k * a.chunk];
-}
-
-// One block per tile that was cut into several items (their partial sums are added at L2): zeros first.  Other blocks exit.
-__global__ void __launch_bounds__(256)
-tile_zero_kernel(const __grid_constant__ TileArgs a)
-{
-    pdl_entry();
-    const int t = blockIdx.x;
-    if (a.tiles[t].w <= 1) return;
-    int l, b, ty, tx;
-    decode_tile(a.g, t, l, b, ty, tx);
-    const int H = a.g.H[l], W = a.g.W[l], ty0 = ty * kTH, tx0 = tx * kTW;
-    const int nrow = min(kTH, H - ty0), ncol = min(kTW, W - tx0);
-    float *const base = a.feat[l] + ((int64_t)b * a.C * H + ty0) * W + tx0;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (ncol == kTW && (W & 3) == 0) {                                       // lane = (row of 4, 16-byte piece)
-        for (int c = warp; c < a.C; c += 8) {
-            float4 *p = reinterpret_cast<float4 *>(base + ((int64_t)c * H + (lane >> 3)) * W) + (lane & 7);
-            for (int r4 = 0; r4 < kTH; r4 += 4)
-                if ((lane >> 3) + r4 < nrow) p[(int64_t)r4 * W / 4] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    } else {
-        for (int c = warp; c < a.C; c += 8)
-            for (int row = 0; row < nrow; row++)
-                if (lane < ncol) base[((int64_t)c * H + row) * W + lane] = 0.0f;
-    }
 }
 
 // ---- main -----------------------------------------------------------------------------------------------------------
@@ -629,9 +627,11 @@ cudaError_t launch_roialign_bwd_tile(const FeatSet &fs, const RoiFeat &f, const 
     if ((e = launch_pdl(tile_scatter_kernel, dim3((R + 3) / 4), dim3(128), 0, s, a.g, reinterpret_cast<const Hdr *>(w + lo.hdr),
                         reinterpret_cast<const unsigned long long *>(w + lo.rmask), R, reinterpret_cast<int *>(w + lo.cnt), reinterpret_cast<const int4 *>(w + lo.tiles),
                         reinterpret_cast<int *>(w + lo.lists))) != cudaSuccess) return e;
-    if ((e = launch_pdl(tile_sort_kernel, dim3((lo.T + kSortThreads / 32 - 1) / (kSortThreads / 32)), dim3(kSortThreads), 0, s, a, reinterpret_cast<int *>(w + lo.lists),
-                        reinterpret_cast<Item *>(w + lo.items))) != cudaSuccess) return e;
-    if (!accumulate && (e = launch_pdl(tile_zero_kernel, dim3(lo.T), dim3(256), 0, s, a)) != cudaSuccess) return e;
+    {
+        const int nsort = (lo.T + kSortThreads / 32 - 1) / (kSortThreads / 32);
+        if ((e = launch_pdl(tile_sort_kernel, dim3(nsort + (accumulate ? 0 : lo.T)), dim3(kSortThreads), 0, s, a, reinterpret_cast<int *>(w + lo.lists),
+                            reinterpret_cast<Item *>(w + lo.items), nsort)) != cudaSuccess) return e;
+    }
     const int grid = lo.T * a.ncg < sms[dev] * kTileCtasPerSm ? lo.T * a.ncg : sms[dev] * kTileCtasPerSm;
     if (accumulate) e = launch_pdl(tile_bwd_kernel<true>, dim3(grid), dim3(32), (size_t)kTileSmem, s, a);
     else e = launch_pdl(tile_bwd_kernel<false>, dim3(grid), dim3(32), (size_t)kTileSmem, s, a);

@@ -8,10 +8,11 @@ import torch
 from . import synth
 from .ops import (AnchorGenerator, BboxAssignSample, BboxAssignSampleForRcnn, Proposal, SingleRoIExtractor)
 
-KERNELS_PER_STEP = 23   # 2 lanes x (select, nms_mask, nms_sweep), merge | gtmax, label, prefilter, select(list), select(full scan,
+KERNELS_PER_STEP = 28   # 2 lanes x (select, nms_mask, nms_sweep), merge | gtmax, label, prefilter, select(list), select(full scan,
                         # returns at once), finalize | gtmax (+ gt head), label, prefilter, select x2, finalize |
-                        # roialign fwd (stream + gather for declined RoIs) | roialign bwd (stream + gather);
-                        # the cudaMemsetAsync nodes of a step (dX zero-fill, small counters) are not counted
+                        # roialign fwd (stream + gather for declined RoIs) | roialign bwd (tile-stationary: plan, offsets, scatter,
+                        # sort / zero, tile kernel, gather); memset nodes (small counters) are not counted.  bench.py counts the
+                        # kernel nodes of the captured graph itself.
 
 
 class RegionPath:
