@@ -135,7 +135,9 @@ MD_API int MdRoiLevels(MD_AOT_ARGS);
  *   Default path: TMA-staged tiles + separable bilinear operators (rtol 1e-5 / atol 1e-6 vs the oracle). */
 MD_API int MdRoiAlignFwd(MD_AOT_ARGS);
 
-/* a11  ROIAlignGrad (bprop of MdRoiAlignFwd); outputs are zero-filled then accumulated
+/* a11  ROIAlignGrad (bprop of MdRoiAlignFwd); every output byte is written (nothing has to be initialised by the caller).
+ * 7x7 / 2 samples / C % 32 == 0: the tile-stationary kernel of roialign_tile.cu writes every dX byte exactly once (no
+ * zero-fill; RoIs it declines are added by the gather kernel afterwards); otherwise zero-fill + scatter-add.
  *   in : rois (R,5) f32 | dout (R,C,P,P) f32 | cfg f32[4+L]
  *   out: dfeat_0..dfeat_{L-1} (B,C,H_l,W_l) f32     (nparam = 3+L) */
 MD_API int MdRoiAlignBwd(MD_AOT_ARGS);
@@ -143,7 +145,8 @@ MD_API int MdRoiAlignBwd(MD_AOT_ARGS);
 /* a11, accumulating form: dfeat_l += ROIAlignGrad(dout) into tensors the caller owns and has initialised (zeros for a
  * plain bprop; an existing gradient for gradient accumulation).  The zero-fill is 731 MB of pure DRAM writes per step
  * at config 2; as its own node it has no producer, so a graph executor can run it beside the latency-bound Proposal
- * chain instead of in front of the RoIAlign backward (bench.py does; --no-overlap uses MdRoiAlignBwd).
+ * chain instead of in front of the RoIAlign backward (bench.py with MD_BENCH_BWD=acc does; since the tile-stationary
+ * MdRoiAlignBwd needs no zero-fill at all, the default step uses that one).
  *   in : rois (R,5) f32 | dout (R,C,P,P) f32 | cfg f32[4+L] | acc_0..acc_{L-1} (B,C,H_l,W_l) f32 (read-modify-write)
  *   out: done (1) int32 = 0      (nparam = 3+L+1) */
 MD_API int MdRoiAlignBwdAcc(MD_AOT_ARGS);
