@@ -37,10 +37,13 @@ UNIT = "img/s"
 BATCH = 8            # images per GPU (weak scaling); --global-batch overrides it
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels (ncu --set full, profiles/README.md)
 NCU_TRAFFIC = {"roialign_fwd": 849e6, "roialign_bwd": 1260e6, "roialign_bwd_tile": 897e6, "yolo_decode": None}
-# RoIAlign backward of the step: "tile" = MdRoiAlignBwd (tile-stationary kernel: every dX byte written once, nothing to zero-fill),
-# "acc" = round 1's form (zero-fill of dX on a side stream + the scatter-add kernel through MdRoiAlignBwdAcc)
-BWD_MODE = os.environ.get("MD_BENCH_BWD", "tile")
-TILE_BWD = BWD_MODE == "tile" and os.environ.get("MD_ROI_TILE", "1") != "0"
+# RoIAlign backward of the step: "plan" (default) / "tile" = the tile-stationary kernel (every dX byte written once, nothing to
+# zero-fill) as two ops / as the one-call MdRoiAlignBwd; "acc" = round 1's form (zero-fill of dX on a side stream + the scatter-add kernel through MdRoiAlignBwdAcc)
+BWD_MODE = os.environ.get("MD_BENCH_BWD", "plan")
+TILE_BWD = BWD_MODE in ("tile", "plan") and os.environ.get("MD_ROI_TILE", "1") != "0"
+# "plan": the two-op form -- MdRoiAlignBwdPrepare (plans / lists: needs the RoIs only) on its own stream beside the RoIAlign forward,
+# MdRoiAlignBwdPlanned behind it
+PLAN_BESIDE = TILE_BWD and BWD_MODE == "plan"
 WORKLOADS = {
     2: ("configs[1]: Faster R-CNN R50-FPN region path, batch 8/GPU, 800x1344, 5 levels (268569 anchors), "
         "2000 pre-NMS/level, NMS 0.7, max_num 2000, G<=128 gts, 512 sampled RoIs, 256-ch 7x7 RoIAlign fwd+bwd"),
@@ -542,6 +545,7 @@ def run_b200(args):
     side = torch.cuda.Stream(priority=-2)
     aux = torch.cuda.Stream(priority=-1)
     zstream, zjoin, zfork = torch.cuda.Stream(), torch.cuda.Event(), torch.cuda.Event()
+    pstream, pjoin, pfork = torch.cuda.Stream(priority=-1), torch.cuda.Event(), torch.cuda.Event()
     fork, join = torch.cuda.Event(), torch.cuda.Event()
     from minddet_b200 import shard
 
@@ -615,6 +619,14 @@ def run_b200(args):
         rois = rcnn["rois"].reshape(-1, 5)
         if overlap and RPN_AT == "fwd":
             rpn = fork_rpn_targets()
+        plan = None
+        if overlap and PLAN_BESIDE:
+            pfork.record(torch.cuda.current_stream())
+            pstream.wait_event(pfork)
+            with torch.cuda.stream(pstream):
+                plan = rp.extractor.prepare_backward(rois, feats_h)
+                pjoin.record(pstream)
+            plan.record_stream(torch.cuda.current_stream())
         roi_feats = rp.extractor._forward(rois, feats_h)
         mark("roialign_fwd")
         if overlap and RPN_AT == "bwd":
@@ -623,6 +635,9 @@ def run_b200(args):
             if step.zero_forked:
                 torch.cuda.current_stream().wait_event(zjoin)
             dfe = rp.extractor._backward_into(rois, inp["dout"], zeroed)
+        elif plan is not None:
+            torch.cuda.current_stream().wait_event(pjoin)
+            dfe = rp.extractor._backward_planned(rois, inp["dout"], [tuple(f.shape) for f in feats_h], plan)
         else:
             dfe = rp.extractor._backward(rois, inp["dout"], [tuple(f.shape) for f in feats_h])
         mark("roialign_bwd")
@@ -960,7 +975,8 @@ def run_b200(args):
                                  if TILE_BWD else
                                  "rpn target assignment and the RoIAlign-gradient zero-fill on their own streams (backward accumulates: "
                                  "MdRoiAlignBwdAcc)") if not args.no_overlap else "rpn targets in line, MdRoiAlignBwd in line"),
-                    "roialign_bwd": "tile" if TILE_BWD else "acc",
+                    "roialign_bwd": ("plan beside the forward + planned backward (MdRoiAlignBwdPrepare / MdRoiAlignBwdPlanned)" if PLAN_BESIDE
+                                     else "tile") if TILE_BWD else "acc",
                     "numa": numa},
             "per_rank_ms": {"min": min(per_rank), "median": float(np.median(per_rank)), "max": max(per_rank), "all": per_rank},
             "clocks": sampler.summary(),

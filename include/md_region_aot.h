@@ -151,6 +151,20 @@ MD_API int MdRoiAlignBwd(MD_AOT_ARGS);
  *   out: done (1) int32 = 0      (nparam = 3+L+1) */
 MD_API int MdRoiAlignBwdAcc(MD_AOT_ARGS);
 
+/* a11, two-op form (7x7, 2 samples, C % 32 == 0 only; anything else returns 4): everything the tile-stationary backward
+ * derives from the RoIs -- per-RoI separable plans, per-tile RoI lists, work items -- goes into a tensor the framework owns, so
+ * that a graph can run MdRoiAlignBwdPrepare beside the forward (it needs the RoIs and the level shapes only) and the backward
+ * proper starts with its tile kernel.  Plays the role of a "saved for backward" tensor; MdRoiAlignBwd is the same work in one call.
+ *   MdRoiAlignPlanBytes(R, B, C, L, H[L], W[L]) -> bytes of the plan tensor (host function; MD_TILE_CHUNK must not change between
+ *     the query and the calls)
+ *   MdRoiAlignBwdPrepare: in rois (R,5) f32 | feat_0..feat_{L-1} (B,C,H_l,W_l) f32 (shapes only, not read) | cfg f32[4+L]
+ *                         out plan int32[>= bytes / 4]                                       (nparam = 3+L)
+ *   MdRoiAlignBwdPlanned: in rois (R,5) f32 | dout (R,C,7,7) f32 | cfg f32[4+L] | plan int32[..]
+ *                         out dfeat_0..dfeat_{L-1} (B,C,H_l,W_l) f32, every byte written      (nparam = 4+L) */
+MD_API int MdRoiAlignBwdPrepare(MD_AOT_ARGS);
+MD_API int MdRoiAlignBwdPlanned(MD_AOT_ARGS);
+MD_API int64_t MdRoiAlignPlanBytes(int R, int B, int C, int L, const int *H, const int *W);
+
 /* Bit-exact variants: same I/O, gather kernels only (forward bit-identical to the oracle's op order;
  * used for levels/footprints the TMA path declines, and selectable by symbol because attributes cannot
  * be read on the host from a device cfg tensor). */

@@ -22,7 +22,7 @@ _DTYPE_NAMES = {
 
 SYMBOLS = ("MdAnchorGrid", "MdDecodeClip", "MdDecodeLevel", "MdTopKPerLevel", "MdNms", "MdProposal",
            "MdAssignSample", "MdAssignSampleRcnn", "MdRoiLevels", "MdRoiAlignFwd", "MdRoiAlignBwd", "MdRoiAlignBwdAcc",
-           "MdRoiAlignFwdExact", "MdRoiAlignBwdExact",
+           "MdRoiAlignFwdExact", "MdRoiAlignBwdExact", "MdRoiAlignBwdPrepare", "MdRoiAlignBwdPlanned",
            # the reference's own GPU symbols (iou3d_nms_kernel.cu:445-601) + the device twin of boxes_iou_nms_cpu
            "BoxesIouBevGpu", "BoxesOverlapBevGpu", "NmsGpu", "NmsNormalGpu", "BoxesIouNmsGpu",
            "MdYoloDecode", "MdYoloNms", "MdMaskTargets", "MdEncode", "MdRcnnPostProcess")
@@ -50,6 +50,9 @@ def load_library(path=None):
             fn.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int),
                            ctypes.POINTER(ctypes.POINTER(ctypes.c_int64)), ctypes.POINTER(ctypes.c_char_p),
                            ctypes.c_void_p, ctypes.c_void_p]
+        lib.MdRoiAlignPlanBytes.restype = ctypes.c_int64
+        lib.MdRoiAlignPlanBytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                            ctypes.POINTER(ctypes.c_int)]
         if path is not None:
             return lib
         _lib = lib

@@ -409,6 +409,43 @@ static int roialign_bwd_acc_impl(MD_AOT_ARGS)
                                            (const float *)params[1], ws, ctl, 0, (cudaStream_t)stream, true));
 }
 
+// two-op form of the backward: rois | feat_0..L-1 (level shapes only, not read) | cfg -> plan (int32, MdRoiAlignPlanBytes / 4)
+static int roialign_bwd_prepare_impl(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam < 4) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    const int L = nparam - 3;
+    md::FeatSet fs{};
+    int rc = parse_feats(L, 1, params, ndims, shapes, dtypes, &fs);
+    if (rc) return rc;
+    const int ic = 1 + L, io = 2 + L;
+    REQ(is_f32(dtypes[0]) && ndims[0] == 2 && shapes[0][1] == 5);
+    REQ(is_f32(dtypes[ic]) && numel(ndims[ic], shapes[ic]) >= MD_ROI_STRIDE0 + L);
+    const int R = (int)shapes[0][0];
+    REQ(is_i32(dtypes[io]) && (size_t)numel(ndims[io], shapes[io]) * 4 >= md::roialign_plan_bytes(fs, R));
+    return cuda_rc(md::launch_roialign_bwd_prepare(fs, (const float *)params[0], R, 7, (const float *)params[ic], params[io],
+                                                   (cudaStream_t)stream));
+}
+// rois | dout | cfg | plan -> dfeat_0..L-1
+static int roialign_bwd_planned_impl(MD_AOT_ARGS)
+{
+    (void)extra;
+    if (nparam < 5) return MD_ERR_NPARAM;
+    NEED_ARGS();
+    const int L = nparam - 4;
+    md::FeatSet fs{};
+    int rc = parse_feats(L, 4, params, ndims, shapes, dtypes, &fs);
+    if (rc) return rc;
+    REQ(is_f32(dtypes[0]) && ndims[0] == 2 && shapes[0][1] == 5);
+    const int R = (int)shapes[0][0];
+    REQ(is_f32(dtypes[1]) && ndims[1] == 4 && shapes[1][0] == R && shapes[1][1] == fs.C && shapes[1][2] == 7 && shapes[1][3] == 7);
+    REQ(is_f32(dtypes[2]) && numel(ndims[2], shapes[2]) >= MD_ROI_STRIDE0 + L);
+    REQ(is_i32(dtypes[3]) && (size_t)numel(ndims[3], shapes[3]) * 4 >= md::roialign_plan_bytes(fs, R));
+    return cuda_rc(md::launch_roialign_bwd_planned(fs, (const float *)params[0], R, 7, (const float *)params[2], (const float *)params[1],
+                                                   params[3], (cudaStream_t)stream));
+}
+
 // ---- the reference's own GPU symbols (iou3d_nms_kernel.cu:445-601), same parameter lists ------------------------
 static int bev_pairs_impl(int want_iou, MD_AOT_ARGS)
 {
@@ -534,6 +571,16 @@ int MdYoloNms(MD_AOT_ARGS)
 int MdRoiAlignFwd(MD_AOT_ARGS) { return roialign_fwd_impl(0, nparam, params, ndims, shapes, dtypes, stream, extra); }
 int MdRoiAlignBwd(MD_AOT_ARGS) { return roialign_bwd_impl(0, nparam, params, ndims, shapes, dtypes, stream, extra); }
 int MdRoiAlignBwdAcc(MD_AOT_ARGS) { return roialign_bwd_acc_impl(nparam, params, ndims, shapes, dtypes, stream, extra); }
+int MdRoiAlignBwdPrepare(MD_AOT_ARGS) { return roialign_bwd_prepare_impl(nparam, params, ndims, shapes, dtypes, stream, extra); }
+int MdRoiAlignBwdPlanned(MD_AOT_ARGS) { return roialign_bwd_planned_impl(nparam, params, ndims, shapes, dtypes, stream, extra); }
+int64_t MdRoiAlignPlanBytes(int R, int B, int C, int L, const int *H, const int *W)
+{
+    if (R < 0 || L < 1 || L > md::kMaxLv || !H || !W) return -1;
+    md::FeatSet fs{};
+    fs.L = L; fs.B = B; fs.C = C;
+    for (int l = 0; l < L; l++) { fs.H[l] = H[l]; fs.W[l] = W[l]; }
+    return (int64_t)md::roialign_plan_bytes(fs, R);
+}
 int MdRoiAlignFwdExact(MD_AOT_ARGS) { return roialign_fwd_impl(1, nparam, params, ndims, shapes, dtypes, stream, extra); }
 int MdRoiAlignBwdExact(MD_AOT_ARGS) { return roialign_bwd_impl(1, nparam, params, ndims, shapes, dtypes, stream, extra); }
 

@@ -96,4 +96,11 @@ cudaError_t launch_roialign_fwd(const FeatSet &fs, const float *rois5, int R, in
 cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg,
                                 const float *dout, void *ws, int *ctl, int mode, cudaStream_t s, bool accumulate = false);
 
+// two-op form of the tile-stationary backward (7x7, 2 samples, C % 32 == 0): `plan` = roialign_plan_bytes() bytes owned by the caller;
+// prepare reads the RoIs only (fs: level shapes), planned = the backward proper (every dX byte written once)
+size_t roialign_plan_bytes(const FeatSet &fs, int R);
+cudaError_t launch_roialign_bwd_prepare(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg, void *plan, cudaStream_t s);
+cudaError_t launch_roialign_bwd_planned(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg, const float *dout, void *plan,
+                                        cudaStream_t s);
+
 }  // namespace md

@@ -188,7 +188,12 @@ cudaError_t launch_roialign_bwd_ch(const FeatSet &fs, const RoiFeat &f, const fl
 size_t roialign_ch_workspace_bytes(int R);
 // roialign_tile.cu: tile-stationary backward (7x7, S = 2, C % 32 == 0): every dX byte written once, no zero-fill
 cudaError_t launch_roialign_bwd_tile(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, const float *dout,
-                                     int32_t *flags, void *tile_ws, bool accumulate, cudaStream_t s, bool *launched, const int32_t **ndecl);
+                                     void *tile_ws, bool accumulate, cudaStream_t s, bool *launched, const int32_t **flags,
+                                     const int32_t **ndecl);
+cudaError_t roialign_tile_prepare(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, void *buf, cudaStream_t s);
+cudaError_t roialign_tile_run(const FeatSet &fs, int R, const float *dout, void *buf, bool accumulate, bool rearm, cudaStream_t s,
+                              const int32_t **flags, const int32_t **ndecl);
+bool roialign_tile_supports(const FeatSet &fs, int R, int P);
 size_t roialign_tile_workspace_bytes(const FeatSet &fs, int R);
 
 // flags (R ints, padded) + the channel-lane kernels' per-RoI plans
@@ -228,15 +233,14 @@ cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, in
     const bool tile_acc = tile_acc_env && atoi(tile_acc_env) != 0;
     if (R > 0 && mode == 0 && ws && (!accumulate || tile_acc)) {
         const RoiFeat f = to_roifeat(fs, cfg);
-        int32_t *flags = reinterpret_cast<int32_t *>(ws);
         bool tile = false;
-        const int32_t *ndecl = nullptr;
-        cudaError_t e = launch_roialign_bwd_tile(fs, f, rois5, R, P, dout, flags, reinterpret_cast<unsigned char *>(ws) + roialign_workspace_bytes(R),
-                                                 accumulate, s, &tile, &ndecl);
+        const int32_t *flags = nullptr, *ndecl = nullptr;
+        cudaError_t e = launch_roialign_bwd_tile(fs, f, rois5, R, P, dout, reinterpret_cast<unsigned char *>(ws) + roialign_workspace_bytes(R),
+                                                 accumulate, s, &tile, &flags, &ndecl);
         if (e != cudaSuccess) return e;
         if (tile)
             return launch_pdl(roialign_bwd_gather_kernel, dim3(R < 148 ? R : 148, csplit), dim3(kRoiThreads), 0, s, f, rois5, R, P, csplit, dout,
-                              (const int32_t *)flags, (const int32_t *)ndecl);
+                              flags, ndecl);
     }
     for (int l = 0; l < fs.L && !accumulate; l++) {
         cudaError_t e = cudaMemsetAsync(fs.feat[l], 0, (size_t)fs.B * fs.C * fs.H[l] * fs.W[l] * sizeof(float), s);
@@ -255,6 +259,30 @@ cudaError_t launch_roialign_bwd(const FeatSet &fs, const float *rois5, int R, in
     }
     return launch_pdl(roialign_bwd_gather_kernel, dim3(tma ? (R < 148 ? R : 148) : R, csplit), dim3(kRoiThreads), 0, s, f, rois5, R, P, csplit, dout,
                       tma ? (const int32_t *)flags : (const int32_t *)nullptr, (const int32_t *)nullptr);
+}
+
+
+// ---- two-op form of the tile-stationary backward: the plan depends on the RoIs only, so a graph can run it beside the forward --------
+size_t roialign_plan_bytes(const FeatSet &fs, int R) { return roialign_tile_workspace_bytes(fs, R); }
+
+cudaError_t launch_roialign_bwd_prepare(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg, void *plan, cudaStream_t s)
+{
+    if (!roialign_tile_supports(fs, R, P)) return cudaErrorInvalidValue;
+    const RoiFeat f = to_roifeat(fs, cfg);
+    return roialign_tile_prepare(fs, f, rois5, R, plan, s);
+}
+
+cudaError_t launch_roialign_bwd_planned(const FeatSet &fs, const float *rois5, int R, int P, const float *cfg, const float *dout, void *plan,
+                                        cudaStream_t s)
+{
+    if (!roialign_tile_supports(fs, R, P) || (reinterpret_cast<uintptr_t>(dout) & 15) != 0) return cudaErrorInvalidValue;
+    const RoiFeat f = to_roifeat(fs, cfg);
+    const int32_t *flags = nullptr, *ndecl = nullptr;
+    cudaError_t e = roialign_tile_run(fs, R, dout, plan, false, true, s, &flags, &ndecl);
+    if (e != cudaSuccess) return e;
+    const int csplit = fs.C >= 64 ? 4 : 1;
+    return launch_pdl(roialign_bwd_gather_kernel, dim3(R < 148 ? R : 148, csplit), dim3(kRoiThreads), 0, s, f, rois5, R, P, csplit, dout, flags,
+                      ndecl);
 }
 
 }  // namespace md

@@ -70,6 +70,7 @@ struct TileArgs {
     const int *counters;        // [0] list cursor, [1] ticket, [2] items at the front, [3] items at the back
     int *ticket;
 };
+constexpr int kMaxTilesPerRoi = 128;   // RoIs overlapping more tiles are left to the gather kernel (bounds the list buffer)
 constexpr int kChunk = 16;      // default visits per work item: bounds the longest item (a crowd puts > 100 RoIs on one tile)
 
 // ---- plan + count ---------------------------------------------------------------------------------------------------
@@ -90,9 +91,10 @@ tile_plan_kernel(const __grid_constant__ RoiFeat f, const __grid_constant__ Grid
     int b, l;
     Plan pl;
     plan_roi(roi, f.B, f.L, f.H, f.W, f.cfg, pl, b, l);
-    hdr[r] = make_hdr(pl, b, l);
+    if (pl.status == ST_OK && (pl.y1 / kTH - pl.y0 / kTH + 1) * (pl.x1 / kTW - pl.x0 / kTW + 1) > kMaxTilesPerRoi) pl.status = ST_DECLINE;
     flag[r] = pl.status == ST_DECLINE;
     if (pl.status == ST_DECLINE) atomicAdd(ndecl, 1);
+    hdr[r] = make_hdr(pl, b, l);
     if (pl.status != ST_OK) return;
     {
         const int4 *src = reinterpret_cast<const int4 *>(&pl);
@@ -181,8 +183,12 @@ tile_scatter_kernel(const __grid_constant__ Grid g, const Hdr *__restrict__ hdr,
 }
 
 // One block per tile that was cut into several items (their partial sums are added at L2): zeros first.  Other blocks exit.
-MD_DEVINL void tile_zero_block(const TileArgs &a, const int t)
+// Part of the backward proper (it writes dX), not of the preparation.
+__global__ void __launch_bounds__(256)
+tile_zero_kernel(const __grid_constant__ TileArgs a)
 {
+    pdl_entry();
+    const int t = blockIdx.x;
     if (a.tiles[t].w <= 1) return;
     int l, b, ty, tx;
     decode_tile(a.g, t, l, b, ty, tx);
@@ -207,10 +213,9 @@ MD_DEVINL void tile_zero_block(const TileArgs &a, const int t)
 // RoI of every chunk into the item records.
 constexpr int kSortThreads = 256;
 __global__ void __launch_bounds__(kSortThreads)
-tile_sort_kernel(const __grid_constant__ TileArgs a, int *__restrict__ lists, Item *__restrict__ items, const int nsort)
+tile_sort_kernel(const __grid_constant__ TileArgs a, int *__restrict__ lists, Item *__restrict__ items)
 {
     pdl_entry();
-    if ((int)blockIdx.x >= nsort) { tile_zero_block(a, blockIdx.x - nsort); return; }   // the zero-fill blocks ride in the same launch
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (t >= a.g.base[a.g.L]) return;
     const int4 rec = a.tiles[t];
@@ -542,7 +547,16 @@ tile_bwd_kernel(const __grid_constant__ TileArgs a)
 // ---- host -----------------------------------------------------------------------------------------------------------
 static size_t al256(size_t n) { return (n + 255) & ~(size_t)255; }
 
-struct TileLayout { size_t ctl, cnt, zero_end, tiles, hdr, rmask, plans, lists, items, total; int T, cap, item_cap; };
+static int tile_chunk()
+{
+    const char *ce = getenv("MD_TILE_CHUNK");
+    int c = ce && atoi(ce) > 0 ? atoi(ce) : kChunk;
+    return c > 32767 ? 32767 : c;
+}
+
+// One buffer holds everything the backward needs besides dY: in the one-call form it lives in the (device, stream) workspace,
+// in the two-op form (MdRoiAlignBwdPrepare -> MdRoiAlignBwdPlanned) it is a tensor the framework owns.
+struct TileLayout { size_t ctl, cnt, zero_end, tiles, hdr, rmask, flags, plans, lists, items, total; int T, cap, item_cap; };
 static TileLayout tile_layout(const FeatSet &fs, int R)
 {
     Grid g;
@@ -551,17 +565,19 @@ static TileLayout tile_layout(const FeatSet &fs, int R)
     o.T = g.base[fs.L];
     int per_img_max = 1;
     for (int l = 0; l < fs.L; l++) per_img_max = per_img_max > g.nty[l] * g.ntx[l] ? per_img_max : g.nty[l] * g.ntx[l];
-    o.cap = R * per_img_max;                                 // a RoI lies on one (image, level): it overlaps at most every tile of it
+    // a RoI lies on one (image, level) and the plan leaves RoIs that overlap more than kMaxTilesPerRoi tiles to the gather kernel
+    o.cap = R * (per_img_max < kMaxTilesPerRoi ? per_img_max : kMaxTilesPerRoi);
     size_t off = 0;
-    o.ctl = off; off += 256;                                 // cursor, ticket
+    o.ctl = off; off += 256;                                 // counters (TileArgs::counters), ticket
     o.cnt = off; off += al256((size_t)o.T * sizeof(int));
-    o.zero_end = off;                                        // [ctl, zero_end) is cleared at the top of every call
+    o.zero_end = off;                                        // [ctl, zero_end) is cleared at the top of every prepare
     o.tiles = off; off += al256((size_t)o.T * sizeof(int4));
     o.hdr = off; off += al256((size_t)R * sizeof(Hdr));
     o.rmask = off; off += al256((size_t)R * sizeof(unsigned long long));
+    o.flags = off; off += al256((size_t)R * sizeof(int32_t));
     o.plans = off; off += al256((size_t)R * sizeof(Plan));
     o.lists = off; off += al256((size_t)o.cap * 2 * sizeof(int));   // lists + the sort's scratch copy
-    o.item_cap = o.T + o.cap + 1;
+    o.item_cap = o.T + o.cap / tile_chunk() + 1;
     o.items = off; off += al256((size_t)o.item_cap * sizeof(Item));
     o.total = off;
     return o;
@@ -574,22 +590,66 @@ bool roialign_tile_enabled()
     return !e || atoi(e) != 0;
 }
 
-// dX written once (accumulate = false) or dX += (true).  `flags` (R ints) receives 1 for the RoIs left to the gather kernel.
-cudaError_t launch_roialign_bwd_tile(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, const float *dout,
-                                     int32_t *flags, void *tile_ws, bool accumulate, cudaStream_t s, bool *launched, const int32_t **ndecl)
+bool roialign_tile_supports(const FeatSet &fs, int R, int P)
 {
-    *launched = false;
-    *ndecl = nullptr;
-    if (!roialign_tile_enabled() || P != kP || fs.C % kTC != 0 || fs.L > kMaxLv || R <= 0 || !tile_ws) return cudaSuccess;
-    if ((reinterpret_cast<uintptr_t>(dout) & 15) != 0) return cudaSuccess;
+    if (P != kP || fs.C % kTC != 0 || fs.L > kMaxLv || fs.L < 1 || R <= 0 || fs.B >= 32768) return false;
     for (int l = 0; l < fs.L; l++)
-        if (fs.W[l] >= 65536 || fs.H[l] >= 65536) return cudaSuccess;
-    if (fs.B >= 32768) return cudaSuccess;
+        if (fs.W[l] >= 65536 || fs.H[l] >= 65536) return false;
+    return true;
+}
+
+static unsigned char *tile_base(void *buf) { return reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(buf) + 255) & ~(uintptr_t)255); }
+
+static void tile_args(const FeatSet &fs, int R, unsigned char *w, const TileLayout &lo, TileArgs &a)
+{
+    make_grid(a.g, fs.L, fs.B, fs.H, fs.W);
+    a.C = fs.C; a.R = R; a.ncg = fs.C / kTC; a.item_cap = lo.item_cap; a.list_cap = lo.cap;
+    for (int l = 0; l < fs.L; l++) a.feat[l] = fs.feat[l];
+    a.plans = reinterpret_cast<const Plan *>(w + lo.plans);
+    a.tiles = reinterpret_cast<const int4 *>(w + lo.tiles);
+    a.lists = reinterpret_cast<const int *>(w + lo.lists);
+    a.items = reinterpret_cast<const Item *>(w + lo.items);
+    a.counters = reinterpret_cast<int *>(w + lo.ctl);
+    a.ticket = reinterpret_cast<int *>(w + lo.ctl) + 1;
+    a.chunk = tile_chunk();
+}
+
+// plans, lists, work items: everything that depends on the RoIs only (fs supplies the level shapes; its pointers are not used)
+cudaError_t roialign_tile_prepare(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, void *buf, cudaStream_t s)
+{
+    const TileLayout lo = tile_layout(fs, R);
+    unsigned char *w = tile_base(buf);
+    TileArgs a{};
+    tile_args(fs, R, w, lo, a);
+    int *ctl = reinterpret_cast<int *>(w + lo.ctl);
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(w + lo.ctl, 0, lo.zero_end - lo.ctl, s)) != cudaSuccess) return e;
+    tile_plan_kernel<<<(R + kPlanThreads - 1) / kPlanThreads, kPlanThreads, 0, s>>>(f, a.g, rois5, R, reinterpret_cast<Plan *>(w + lo.plans),
+                                                                                   reinterpret_cast<Hdr *>(w + lo.hdr),
+                                                                                   reinterpret_cast<unsigned long long *>(w + lo.rmask),
+                                                                                   reinterpret_cast<int *>(w + lo.cnt),
+                                                                                   reinterpret_cast<int32_t *>(w + lo.flags), ctl + 4);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = launch_pdl(tile_offsets_kernel, dim3((lo.T + 255) / 256), dim3(256), 0, s, a, reinterpret_cast<int *>(w + lo.cnt),
+                        reinterpret_cast<int4 *>(w + lo.tiles), ctl, reinterpret_cast<Item *>(w + lo.items))) != cudaSuccess) return e;
+    if ((e = launch_pdl(tile_scatter_kernel, dim3((R + 3) / 4), dim3(128), 0, s, a.g, reinterpret_cast<const Hdr *>(w + lo.hdr),
+                        reinterpret_cast<const unsigned long long *>(w + lo.rmask), R, reinterpret_cast<int *>(w + lo.cnt),
+                        reinterpret_cast<const int4 *>(w + lo.tiles), reinterpret_cast<int *>(w + lo.lists))) != cudaSuccess) return e;
+    const int nsort = (lo.T + kSortThreads / 32 - 1) / (kSortThreads / 32);
+    return launch_pdl(tile_sort_kernel, dim3(nsort), dim3(kSortThreads), 0, s, a, reinterpret_cast<int *>(w + lo.lists),
+                      reinterpret_cast<Item *>(w + lo.items));
+}
+
+// the backward proper on a prepared buffer: zeros for the crowded tiles, the tile kernel; *flags / *ndecl: the RoIs left to the
+// gather kernel (which the caller launches next).  rearm: the buffer may have been consumed before (ticket back to zero).
+cudaError_t roialign_tile_run(const FeatSet &fs, int R, const float *dout, void *buf, bool accumulate, bool rearm, cudaStream_t s,
+                              const int32_t **flags, const int32_t **ndecl)
+{
     static int sms[64] = {0};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev >= 64) return cudaSuccess;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidValue;
     if (!sms[dev]) {
         int n = 0;
         if ((e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
@@ -598,46 +658,35 @@ cudaError_t launch_roialign_bwd_tile(const FeatSet &fs, const RoiFeat &f, const 
         sms[dev] = n;
     }
     const TileLayout lo = tile_layout(fs, R);
-    unsigned char *w = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tile_ws) + 255) & ~(uintptr_t)255);
+    unsigned char *w = tile_base(buf);
     TileArgs a{};
-    make_grid(a.g, fs.L, fs.B, fs.H, fs.W);
-    a.C = fs.C; a.R = R; a.ncg = fs.C / kTC; a.item_cap = lo.item_cap; a.list_cap = lo.cap;
-    for (int l = 0; l < fs.L; l++) a.feat[l] = fs.feat[l];
+    tile_args(fs, R, w, lo, a);
     a.dout = dout;
-    a.plans = reinterpret_cast<const Plan *>(w + lo.plans);
-    a.tiles = reinterpret_cast<const int4 *>(w + lo.tiles);
-    a.lists = reinterpret_cast<const int *>(w + lo.lists);
-    a.items = reinterpret_cast<const Item *>(w + lo.items);
-    int *ctl = reinterpret_cast<int *>(w + lo.ctl);
-    a.counters = ctl;
-    a.ticket = ctl + 1;
-    {
-        const char *ce = getenv("MD_TILE_CHUNK");
-        a.chunk = ce && atoi(ce) > 0 ? atoi(ce) : kChunk;
-        if (a.chunk > 32767) a.chunk = 32767;
-    }
-    if ((e = cudaMemsetAsync(w + lo.ctl, 0, lo.zero_end - lo.ctl, s)) != cudaSuccess) return e;
-    tile_plan_kernel<<<(R + kPlanThreads - 1) / kPlanThreads, kPlanThreads, 0, s>>>(f, a.g, rois5, R, reinterpret_cast<Plan *>(w + lo.plans),
-                                                                                   reinterpret_cast<Hdr *>(w + lo.hdr),
-                                                                                   reinterpret_cast<unsigned long long *>(w + lo.rmask),
-                                                                                   reinterpret_cast<int *>(w + lo.cnt), flags, ctl + 4);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if ((e = launch_pdl(tile_offsets_kernel, dim3((lo.T + 255) / 256), dim3(256), 0, s, a, reinterpret_cast<int *>(w + lo.cnt),
-                        reinterpret_cast<int4 *>(w + lo.tiles), ctl, reinterpret_cast<Item *>(w + lo.items))) != cudaSuccess) return e;
-    if ((e = launch_pdl(tile_scatter_kernel, dim3((R + 3) / 4), dim3(128), 0, s, a.g, reinterpret_cast<const Hdr *>(w + lo.hdr),
-                        reinterpret_cast<const unsigned long long *>(w + lo.rmask), R, reinterpret_cast<int *>(w + lo.cnt), reinterpret_cast<const int4 *>(w + lo.tiles),
-                        reinterpret_cast<int *>(w + lo.lists))) != cudaSuccess) return e;
-    {
-        const int nsort = (lo.T + kSortThreads / 32 - 1) / (kSortThreads / 32);
-        if ((e = launch_pdl(tile_sort_kernel, dim3(nsort + (accumulate ? 0 : lo.T)), dim3(kSortThreads), 0, s, a, reinterpret_cast<int *>(w + lo.lists),
-                            reinterpret_cast<Item *>(w + lo.items), nsort)) != cudaSuccess) return e;
-    }
+    if (rearm && (e = cudaMemsetAsync(a.ticket, 0, sizeof(int), s)) != cudaSuccess) return e;
+    if (!accumulate && (e = launch_pdl(tile_zero_kernel, dim3(lo.T), dim3(256), 0, s, a)) != cudaSuccess) return e;
     const int grid = lo.T * a.ncg < sms[dev] * kTileCtasPerSm ? lo.T * a.ncg : sms[dev] * kTileCtasPerSm;
     if (accumulate) e = launch_pdl(tile_bwd_kernel<true>, dim3(grid), dim3(32), (size_t)kTileSmem, s, a);
     else e = launch_pdl(tile_bwd_kernel<false>, dim3(grid), dim3(32), (size_t)kTileSmem, s, a);
     if (e != cudaSuccess) return e;
+    *flags = reinterpret_cast<const int32_t *>(w + lo.flags);
+    *ndecl = reinterpret_cast<const int32_t *>(w + lo.ctl) + 4;
+    return cudaSuccess;
+}
+
+// one-call form: dX written once (accumulate = false) or dX += (true)
+cudaError_t launch_roialign_bwd_tile(const FeatSet &fs, const RoiFeat &f, const float *rois5, int R, int P, const float *dout,
+                                     void *tile_ws, bool accumulate, cudaStream_t s, bool *launched, const int32_t **flags,
+                                     const int32_t **ndecl)
+{
+    *launched = false;
+    *ndecl = nullptr;
+    *flags = nullptr;
+    if (!roialign_tile_enabled() || !roialign_tile_supports(fs, R, P) || !tile_ws) return cudaSuccess;
+    if ((reinterpret_cast<uintptr_t>(dout) & 15) != 0) return cudaSuccess;
+    cudaError_t e = roialign_tile_prepare(fs, f, rois5, R, tile_ws, s);
+    if (e != cudaSuccess) return e;
+    if ((e = roialign_tile_run(fs, R, dout, tile_ws, accumulate, false, s, flags, ndecl)) != cudaSuccess) return e;
     *launched = true;
-    *ndecl = ctl + 4;
     return cudaSuccess;
 }
 

@@ -277,6 +277,8 @@ class SingleRoIExtractor(_Cell):
         self._bwd = Custom(_so("MdRoiAlignBwdExact" if exact else "MdRoiAlignBwd"), None, torch.float32)
         self._bwd_acc = None if exact else Custom(_so("MdRoiAlignBwdAcc"), lambda *s: (1,), torch.int32)
         self._lvl = Custom(_so("MdRoiLevels"), lambda r, c: (r[0],), torch.int32)
+        self._prep = None if exact else Custom(_so("MdRoiAlignBwdPrepare"), None, torch.int32)
+        self._planned = None if exact else Custom(_so("MdRoiAlignBwdPlanned"), None, torch.float32)
 
     def map_roi_levels(self, rois):
         return self._lvl(rois, self._cfg([self.cfg_values[0], float(len(self.strides))], rois.device))
@@ -289,6 +291,33 @@ class SingleRoIExtractor(_Cell):
     def _backward(self, rois, dout, feat_shapes):
         self._bwd.out_shape = lambda *s: tuple(feat_shapes)
         out = self._bwd(rois, dout, self._cfg(self.cfg_values, rois.device))
+        return out if isinstance(out, tuple) else (out,)
+
+    def plan_words(self, R, feat_shapes):
+        """int32 words of the plan tensor of the two-op backward (``MdRoiAlignPlanBytes``)."""
+        import ctypes
+        from ._aot import load_library
+        L = len(feat_shapes)
+        H = (ctypes.c_int * L)(*[int(s[2]) for s in feat_shapes])
+        W = (ctypes.c_int * L)(*[int(s[3]) for s in feat_shapes])
+        n = load_library().MdRoiAlignPlanBytes(int(R), int(feat_shapes[0][0]), int(feat_shapes[0][1]), L, H, W)
+        if n < 0:
+            raise ValueError("MdRoiAlignPlanBytes: bad arguments")
+        return (int(n) + 3) // 4
+
+    def prepare_backward(self, rois, feats):
+        """Two-op bprop, first half (``MdRoiAlignBwdPrepare``): everything the tile-stationary backward derives from the RoIs, into a
+        tensor the caller owns.  Needs the RoIs and the level shapes only, so it can run beside the forward on another stream."""
+        if self._prep is None:
+            raise RuntimeError("the exact RoIAlign variant has no two-op backward")
+        n = self.plan_words(rois.shape[0], [tuple(f.shape) for f in feats])
+        self._prep.out_shape = lambda *s: (n,)
+        return self._prep(rois, *feats, self._cfg(self.cfg_values, rois.device))
+
+    def _backward_planned(self, rois, dout, feat_shapes, plan):
+        """Two-op bprop, second half (``MdRoiAlignBwdPlanned``): the backward proper on a prepared plan; every dX byte written."""
+        self._planned.out_shape = lambda *s: tuple(feat_shapes)
+        out = self._planned(rois, dout, self._cfg(self.cfg_values, rois.device), plan)
         return out if isinstance(out, tuple) else (out,)
 
     def _backward_into(self, rois, dout, grads):

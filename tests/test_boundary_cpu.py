@@ -19,7 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "md_region_aot.h")).read()
     declared = re.findall(r"MD_API\s+int\s+(\w+)\(MD_AOT_ARGS\)", hdr)
-    assert sorted(declared) == sorted(_aot.SYMBOLS) and len(declared) == 24
+    assert sorted(declared) == sorted(_aot.SYMBOLS) and len(declared) == 26
+    assert "MdRoiAlignPlanBytes" in hdr and hasattr(M.load_library(), "MdRoiAlignPlanBytes")
     lib = M.load_library()
     for s in declared:
         assert hasattr(lib, s), s

@@ -481,6 +481,38 @@ def test_roialign_tile_backward_repeats(chunk, monkeypatch):
             np.testing.assert_allclose(host(y), host(x), rtol=1e-5, atol=tol)
 
 
+def test_roialign_two_op_backward_vs_oracle():
+    """MdRoiAlignBwdPrepare (on another stream, beside other work) + MdRoiAlignBwdPlanned == the oracle; the plan tensor is
+    owned by the caller and can be consumed twice (the backward re-arms its ticket)."""
+    rng = np.random.default_rng(49)
+    B, C = 2, 64
+    shapes = synth.level_shapes()[:4]
+    strides = synth.STRIDES[:4]
+    rois_h = _rois(rng, 1500, B)
+    rois_h[0, 1:] = [5, 100, 1300, 130]
+    rois_h[1, 0] = -1
+    rois_h[2:200, 1:] = rois_h[2:200, 1:] * 0.03 + np.array([500, 300, 500, 300], np.float32)     # a crowd on a few tiles
+    dout_h = rng.uniform(-1, 1, (1500, C, 7, 7)).astype(np.float32)
+    dref = O.roialign_bwd([(B, C, h, w) for h, w in shapes], strides, rois_h, dout_h)
+    ext = SingleRoIExtractor()
+    rois, dout = dev(rois_h), dev(dout_h)
+    feats = [torch.empty(B, C, h, w, device="cuda") for h, w in shapes]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        plan = ext.prepare_backward(rois, feats)
+    torch.cuda.current_stream().wait_stream(side)
+    fshapes = [(B, C, h, w) for h, w in shapes]
+    for _ in range(2):
+        got = ext._backward_planned(rois, dout, fshapes, plan)
+        for l in range(4):
+            np.testing.assert_allclose(host(got[l]), dref[l], rtol=1e-5, atol=1e-5 * max(1.0, np.abs(dref[l]).max()))
+    # shapes the tile kernel does not take are refused (return code 4), never silently mis-handled
+    ext14 = SingleRoIExtractor(14, 2, strides, 56)
+    with pytest.raises(Exception):
+        ext14._backward_planned(rois, dev(rng.uniform(-1, 1, (1500, C, 14, 14)).astype(np.float32)), fshapes, plan)
+
+
 def test_roialign_bwd_accumulates_into_caller_tensors():
     """MdRoiAlignBwdAcc: acc_l += ROIAlignGrad(dout).  Starting from zeros it is the plain bprop (oracle), starting
     from an existing gradient it adds to it; the self-contained MdRoiAlignBwd stays the zero-filling form."""
