@@ -174,7 +174,7 @@ MD_API int MdRoiAlignBwdExact(MD_AOT_ARGS);
 /* ---- "next" row 3: the reference's OWN GPU symbols, same names and parameter lists
  * (minddet/models/centerpoint/det3d_ms/ops/test_custom_pytorch/iou3d_nms_kernel.cu:445, :470, :493, :548; python side
  * iou_gpu.py:14-80), so `ops.Custom("<this .so>:NmsGpu", ...)` replaces `iou_nms.so:NmsGpu` without touching the cell.
- * Boxes are (N,7) f32 [x, y, z, dx, dy, dz, heading]; N <= 2048 for the NMS symbols.
+ * Boxes are (N,7) f32 [x, y, z, dx, dy, dz, heading]; N <= 4096 for the NMS symbols.
  *   BoxesIouBevGpu / BoxesOverlapBevGpu : in boxes_a (N,7) | boxes_b (M,7)        out ans (N,M) f32
  *   NmsGpu (rotated) / NmsNormalGpu (axis-aligned): in boxes (N,7) score-sorted | thresh f32[1]
  *                                          out keep (N) int64 zero padded | num_to_keep int32[1]    (IoU > thresh suppresses)

@@ -182,30 +182,34 @@ tile_scatter_kernel(const __grid_constant__ Grid g, const Hdr *__restrict__ hdr,
     }
 }
 
-// One block per tile that was cut into several items (their partial sums are added at L2): zeros first.  Other blocks exit.
-// Part of the backward proper (it writes dX), not of the preparation.
+// Tiles that were cut into several items (their partial sums are added at L2) get zeros first: the blocks walk the front of the
+// item array (the crowded tiles' items) and take the tiles whose first chunk they meet.  Part of the backward proper (it writes
+// dX), not of the preparation.
 __global__ void __launch_bounds__(256)
 tile_zero_kernel(const __grid_constant__ TileArgs a)
 {
     pdl_entry();
-    const int t = blockIdx.x;
-    if (a.tiles[t].w <= 1) return;
-    int l, b, ty, tx;
-    decode_tile(a.g, t, l, b, ty, tx);
-    const int H = a.g.H[l], W = a.g.W[l], ty0 = ty * kTH, tx0 = tx * kTW;
-    const int nrow = min(kTH, H - ty0), ncol = min(kTW, W - tx0);
-    float *const base = a.feat[l] + ((int64_t)b * a.C * H + ty0) * W + tx0;
+    const int nfront = __ldg(a.counters + 2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (ncol == kTW && (W & 3) == 0) {                                       // lane = (row of 4, 16-byte piece)
-        for (int c = warp; c < a.C; c += 8) {
-            float4 *p = reinterpret_cast<float4 *>(base + ((int64_t)c * H + (lane >> 3)) * W) + (lane & 7);
-            for (int r4 = 0; r4 < kTH; r4 += 4)
-                if ((lane >> 3) + r4 < nrow) p[(int64_t)r4 * W / 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = blockIdx.x; i < nfront; i += gridDim.x) {
+        const int4 u = __ldg(reinterpret_cast<const int4 *>(a.items + i));      // t, chunk, nchunk, nv
+        if (u.y != 0) continue;
+        int l, b, ty, tx;
+        decode_tile(a.g, u.x, l, b, ty, tx);
+        const int H = a.g.H[l], W = a.g.W[l], ty0 = ty * kTH, tx0 = tx * kTW;
+        const int nrow = min(kTH, H - ty0), ncol = min(kTW, W - tx0);
+        float *const base = a.feat[l] + ((int64_t)b * a.C * H + ty0) * W + tx0;
+        if (ncol == kTW && (W & 3) == 0) {                                   // lane = (row of 4, 16-byte piece)
+            for (int c = warp; c < a.C; c += 8) {
+                float4 *p = reinterpret_cast<float4 *>(base + ((int64_t)c * H + (lane >> 3)) * W) + (lane & 7);
+                for (int r4 = 0; r4 < kTH; r4 += 4)
+                    if ((lane >> 3) + r4 < nrow) p[(int64_t)r4 * W / 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (int c = warp; c < a.C; c += 8)
+                for (int row = 0; row < nrow; row++)
+                    if (lane < ncol) base[((int64_t)c * H + row) * W + lane] = 0.0f;
         }
-    } else {
-        for (int c = warp; c < a.C; c += 8)
-            for (int row = 0; row < nrow; row++)
-                if (lane < ncol) base[((int64_t)c * H + row) * W + lane] = 0.0f;
     }
 }
 
@@ -663,7 +667,7 @@ cudaError_t roialign_tile_run(const FeatSet &fs, int R, const float *dout, void 
     tile_args(fs, R, w, lo, a);
     a.dout = dout;
     if (rearm && (e = cudaMemsetAsync(a.ticket, 0, sizeof(int), s)) != cudaSuccess) return e;
-    if (!accumulate && (e = launch_pdl(tile_zero_kernel, dim3(lo.T), dim3(256), 0, s, a)) != cudaSuccess) return e;
+    if (!accumulate && (e = launch_pdl(tile_zero_kernel, dim3(lo.T < 592 ? lo.T : 592), dim3(256), 0, s, a)) != cudaSuccess) return e;
     const int grid = lo.T * a.ncg < sms[dev] * kTileCtasPerSm ? lo.T * a.ncg : sms[dev] * kTileCtasPerSm;
     if (accumulate) e = launch_pdl(tile_bwd_kernel<true>, dim3(grid), dim3(32), (size_t)kTileSmem, s, a);
     else e = launch_pdl(tile_bwd_kernel<false>, dim3(grid), dim3(32), (size_t)kTileSmem, s, a);
