@@ -513,6 +513,29 @@ def test_roialign_two_op_backward_vs_oracle():
         ext14._backward_planned(rois, dev(rng.uniform(-1, 1, (1500, C, 14, 14)).astype(np.float32)), fshapes, plan)
 
 
+@pytest.mark.parametrize("shapes,strides", [([(7, 45), (3, 9)], (4, 16)), ([(5, 30)], (8,)), ([(64, 64), (33, 31), (17, 16), (8, 8), (4, 4)], (4, 8, 16, 32, 64))])
+def test_roialign_tile_backward_odd_pyramids(shapes, strides):
+    """Tile kernel on pyramids that are nothing like config 2: maps smaller than one tile, widths that are not multiples of 4
+    (scalar read-out), one level, five levels, one image, RoIs hanging over every border."""
+    rng = np.random.default_rng(50)
+    B, C, n = 1, 32, 300
+    img_w, img_h = shapes[0][1] * strides[0], shapes[0][0] * strides[0]
+    b = synth.rand_boxes(rng, n, img_w=float(img_w), img_h=float(img_h), smin=2, smax=float(max(img_w, img_h)))
+    b += rng.uniform(-20, 20, b.shape).astype(np.float32)                      # some of them outside the image
+    rois = np.concatenate([np.zeros((n, 1), np.float32), b], 1).astype(np.float32)
+    ext = SingleRoIExtractor(7, 2, strides, 56)
+    dout = rng.uniform(-1, 1, (n, C, 7, 7)).astype(np.float32)
+    fshapes = [(B, C, h, w) for h, w in shapes]
+    dref = O.roialign_bwd(fshapes, strides, rois, dout)
+    got = ext._backward(dev(rois), dev(dout), fshapes)
+    plan = ext.prepare_backward(dev(rois), [torch.empty(s, device="cuda") for s in fshapes])
+    got2 = ext._backward_planned(dev(rois), dev(dout), fshapes, plan)
+    for l in range(len(shapes)):
+        tol = 1e-5 * max(1.0, np.abs(dref[l]).max())
+        np.testing.assert_allclose(host(got[l]), dref[l], rtol=1e-5, atol=tol)
+        np.testing.assert_allclose(host(got2[l]), dref[l], rtol=1e-5, atol=tol)
+
+
 def test_roialign_bwd_accumulates_into_caller_tensors():
     """MdRoiAlignBwdAcc: acc_l += ROIAlignGrad(dout).  Starting from zeros it is the plain bprop (oracle), starting
     from an existing gradient it adds to it; the self-contained MdRoiAlignBwd stays the zero-filling form."""
