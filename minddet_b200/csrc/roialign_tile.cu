@@ -4,20 +4,27 @@
 // read-modify-writes every footprint at L2.  Here every dX byte is written exactly ONCE:
 //
 //   plan   tile_plan_kernel, one thread per RoI: the separable operators of the RoI (roialign_tile_plan.h: <= 28 touched
-//          feature rows x 7 bin weights; columns dense for footprints <= 16 wide, per bin otherwise), a 16-byte header, and
-//          one count per 8 x 32-pixel dX tile the footprint overlaps.
-//   lists  tile_offsets_kernel (one thread per tile: its slice of the list buffer) + tile_scatter_kernel (one thread per RoI
-//          drops its index into every tile it overlaps, in any order); the main kernel visits a tile's RoIs in increasing
-//          index order (warp-wide "smallest entry above the previous one"), so the floating-point sum is deterministic.
-//   main   tile_bwd_kernel, persistent single-warp CTAs, work item = (tile, 32 channels), LANE = CHANNEL: the 8 x 32 x 32-channel
-//          accumulator tile lives in shared memory as [row][channel][33] (odd pitch: conflict-free for lane = channel and for the
-//          lane = column read-out; slot 32 of every row is a dump slot for columns outside the tile).  Per RoI of the tile's list
-//          ("visit") the warp gets dY (32 channels x 49 = 6272 contiguous bytes) and the plan (1664 bytes) by two bulk copies
-//          on one mbarrier, issued one visit ahead; every index, weight, loop bound and branch is warp-uniform.  Per touched
-//          row: V[q] = sum_p Wy[y][p] dY[p][q] (49 FMAs on registers), then per in-tile column one shared-memory
+//          feature rows x 7 bin weights; columns dense for footprints <= 16 wide, per bin otherwise), a 16-byte header, a mask
+//          of the tile rows that hold a touched feature row, and one count per kTH x 32-pixel dX tile of the footprint (kTH = 4).
+//   lists  tile_offsets_kernel (one thread per tile: its slice of the list buffer and its work-item records),
+//          tile_scatter_kernel (one warp per RoI drops its index into every tile it overlaps, in any order), tile_sort_kernel
+//          (one warp per tile: ascending RoI order, so the floating-point sum of a tile is taken in a fixed order).
+//   items  a work item = (tile, <= kChunk consecutive visits of its list) x (32 channels).  A crowd puts > 100 RoIs on one
+//          tile; such a tile is cut into several items, zero-filled by tile_zero_kernel and every item ADDS its partial tile
+//          with vector reductions at L2 (the only place where the order of a sum is not fixed).  Crowded tiles' items get the
+//          early tickets.
+//   main   tile_bwd_kernel, persistent single-warp CTAs (8 per SM), LANE = CHANNEL: the kTH x 32 x 32-channel accumulator tile
+//          lives in shared memory as [row][channel][33] (odd pitch: conflict-free for lane = channel and for the 16-byte
+//          read-out; slot 32 of every row is a dump slot for columns outside the tile).  Per RoI of the item ("visit") the warp
+//          gets dY (32 channels x 49 = 6272 contiguous bytes) and the plan (1664 bytes) by two bulk copies on one mbarrier,
+//          issued one visit ahead -- at the last visit of an item for the first visit of the NEXT item (tickets are taken two
+//          items ahead, item records one item ahead); every index, weight, loop bound and branch is warp-uniform.  Per
+//          touched row: V[q] = sum_p Wy[y][p] dY[p][q] (49 FMAs on registers), then per in-tile column one shared-memory
 //          read-modify-write with 7 FMAs (dense plans: column weights in registers), or per bin 4 read-modify-writes (wide
 //          plans; bins {0,2,4,6} then {1,3,5} as two batches of independent updates).  After the last visit the tile leaves
 //          as 128-byte rows of streaming stores; tiles no RoI touches are written as zeros without going through shared memory.
+//   forms  one call (MdRoiAlignBwd: prepare + run on the (device, stream) workspace) or two ops (MdRoiAlignBwdPrepare ->
+//          plan tensor owned by the framework -> MdRoiAlignBwdPlanned), so that a graph can prepare beside the forward.
 //
 // RoIs the plan declines (S != 2, ...) are flagged for the gather kernel (roialign.cu), which runs after this kernel and
 // adds onto the finished dX.  Algorithmic bytes: dY (R*C*49*4) + dX written once; nothing is zero-filled, nothing is re-read.
