@@ -545,7 +545,7 @@ def run_b200(args):
     side = torch.cuda.Stream(priority=-2)
     aux = torch.cuda.Stream(priority=-1)
     zstream, zjoin, zfork = torch.cuda.Stream(), torch.cuda.Event(), torch.cuda.Event()
-    pstream, pjoin, pfork = torch.cuda.Stream(priority=-1), torch.cuda.Event(), torch.cuda.Event()
+    pstream, pjoin, pfork = torch.cuda.Stream(priority=int(os.environ.get("MD_BENCH_PLAN_PRIO", "-3"))), torch.cuda.Event(), torch.cuda.Event()
     fork, join = torch.cuda.Event(), torch.cuda.Event()
     from minddet_b200 import shard
 
