@@ -1,6 +1,7 @@
 """The operator surface over REAL ``mindspore.ops.Custom(func_type="aot")`` -- what a minddet maintainer drops into the
 graph: ``AnchorGenerator``, ``BoundingBoxDecode``, ``BoundingBoxEncode``, ``TopKPerLevel``, ``NMSWithMask``, ``Proposal``,
-``BboxAssignSample``, ``BboxAssignSampleForRcnn``, ``SingleRoIExtractor`` (+ bprop), ``MaskTargets``,
+``BboxAssignSample``, ``BboxAssignSampleForRcnn``, ``SingleRoIExtractor`` (+ bprop), ``RoIAlignGradPlan`` /
+``RoIAlignGradPlanned`` (the two-op bprop), ``MaskTargets``,
 ``YoloV8PostProcess``, ``RcnnPostProcess``.  Every cell is ``nn.Cell``-shaped and its ``construct`` is one or two aot calls
 with static output shapes computed from the input shapes -- the call convention the reference already uses
 (centerpoint/det3d_ms/ops/test_custom_pytorch/iou_gpu.py:46-80, ops/nms_cpu.py:10-27).
@@ -214,6 +215,47 @@ if HAVE_MINDSPORE:
 
         def construct(self, rois, *feats):
             return self.op(rois, *feats, self.cfg)
+
+    class RoIAlignGradPlan(nn.Cell):
+        """a11, two-op form, first half (``MdRoiAlignBwdPrepare``).  ``construct(rois (R,5), feat1..featL)`` -> plan (int32): the
+        per-RoI plans and per-tile RoI lists of the tile-stationary backward, in a tensor the graph owns.  Reads the RoIs and the
+        SHAPES of the feature maps only, so the executor can place it beside the forward.  7x7 / 2 samples / C % 32 == 0."""
+
+        def __init__(self, featmap_strides=(4, 8, 16, 32), finest_scale=56, roi_end_mode=0):
+            super().__init__()
+            self.cfg = _f32([finest_scale, 2, roi_end_mode, 0.0, *[float(s) for s in featmap_strides]])
+
+        @staticmethod
+        def plan_words(R, feat_shapes):
+            import ctypes
+            lib = ctypes.CDLL(LIB_PATH)
+            lib.MdRoiAlignPlanBytes.restype = ctypes.c_int64
+            L = len(feat_shapes)
+            n = lib.MdRoiAlignPlanBytes(int(R), int(feat_shapes[0][0]), int(feat_shapes[0][1]), L,
+                                        (ctypes.c_int * L)(*[int(s[2]) for s in feat_shapes]), (ctypes.c_int * L)(*[int(s[3]) for s in feat_shapes]))
+            if n < 0:
+                raise ValueError("MdRoiAlignPlanBytes: bad arguments")
+            return (int(n) + 3) // 4
+
+        def construct(self, rois, *feats):
+            n = self.plan_words(rois.shape[0], [tuple(f.shape) for f in feats])
+            op = ops.Custom(_so("MdRoiAlignBwdPrepare"), out_shape=lambda *s: (n,), out_dtype=mstype.int32, func_type="aot")
+            return op(rois, *feats, self.cfg)
+
+    class RoIAlignGradPlanned(nn.Cell):
+        """a11, two-op form, second half (``MdRoiAlignBwdPlanned``).  ``construct(rois, dout (R,C,7,7), plan)`` -> per-level
+        gradients, every byte written; ``feat_shapes`` are the (B,C,H_l,W_l) of the forward's inputs."""
+
+        def __init__(self, feat_shapes, featmap_strides=(4, 8, 16, 32), finest_scale=56, roi_end_mode=0):
+            super().__init__()
+            self.cfg = _f32([finest_scale, 2, roi_end_mode, 0.0, *[float(s) for s in featmap_strides]])
+            shapes = tuple(tuple(int(v) for v in s) for s in feat_shapes)
+            self.op = ops.Custom(_so("MdRoiAlignBwdPlanned"), out_shape=lambda *s: shapes,
+                                 out_dtype=tuple(mstype.float32 for _ in shapes), func_type="aot")
+
+        def construct(self, rois, dout, plan):
+            grads = self.op(rois, dout, self.cfg, plan)
+            return grads if isinstance(grads, tuple) else (grads,)
 
     class MaskTargets(nn.Cell):
         """a13.  ``construct(gt_masks (B,G,H,W) bool, rois (R,5), gt_idx (R) int32)`` -> (R,M,M) bool."""

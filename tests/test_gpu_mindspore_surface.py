@@ -93,6 +93,11 @@ def test_proposal_assign_extract(M):
     dref = O.roialign_bwd([f.shape for f in feats], strides[:4], rois_np, dout)
     for l in range(4):
         np.testing.assert_allclose(host(ft[l].grad), dref[l], rtol=1e-5, atol=1e-5 * max(1.0, np.abs(dref[l]).max()))
+    # the two-op bprop: plan from the RoIs (+ feature shapes), then the planned backward
+    plan = M.RoIAlignGradPlan(strides[:4], 56)(rois, *[dev(f) for f in feats])
+    grads = M.RoIAlignGradPlanned([f.shape for f in feats], strides[:4], 56)(rois, dev(dout), plan)
+    for l in range(4):
+        np.testing.assert_allclose(host(grads[l]), dref[l], rtol=1e-5, atol=1e-5 * max(1.0, np.abs(dref[l]).max()))
 
 
 def test_next_row_cells(M):
