@@ -36,7 +36,7 @@ METRIC = "Faster R-CNN RPN+RoI region path throughput"
 UNIT = "img/s"
 BATCH = 8            # images per GPU (weak scaling); --global-batch overrides it
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels (ncu --set full, profiles/README.md)
-NCU_TRAFFIC = {"roialign_fwd": 849e6, "roialign_bwd": 1260e6, "roialign_bwd_tile": 962e6, "yolo_decode": None}
+NCU_TRAFFIC = {"roialign_fwd": 849e6, "roialign_bwd": 1260e6, "roialign_bwd_tile": 970e6, "yolo_decode": None}
 # RoIAlign backward of the step: "plan" (default) / "tile" = the tile-stationary kernel (every dX byte written once, nothing to
 # zero-fill) as two ops / as the one-call MdRoiAlignBwd; "acc" = round 1's form (zero-fill of dX on a side stream + the scatter-add kernel through MdRoiAlignBwdAcc)
 BWD_MODE = os.environ.get("MD_BENCH_BWD", "plan")
