@@ -16,6 +16,11 @@ Prints ONE JSON line (rank 0).  `value` is device-resident throughput (CUDA even
 pinned-host -> device copy of every input and a device -> host read of a token sample of the results every step.
 After the timed region every rank compares what it just computed with the CPU oracle on its own inputs
 (`parity_checked`); a mismatch is a non-zero exit.
+
+Diagnosis switches (environment; the line records them under `run`): MD_BENCH_BWD=plan|tile|acc (RoIAlign backward of the step:
+two-op tile-stationary form with its plan kernels beside the forward (default) | one-call MdRoiAlignBwd | round 1's zero-fill +
+scatter-add through MdRoiAlignBwdAcc), MD_BENCH_PLAN_PRIO (stream priority of the plan branch), MD_BENCH_SKIP=rpn,zero,
+MD_BENCH_RPN_AT=top|fwd|bwd, MD_BENCH_NO_GATHER=1, MD_BENCH_FREEZE_SAMPLES=1.
 """
 import argparse
 import ctypes
