@@ -66,7 +66,7 @@ static_assert(sizeof(Item) == 32, "item layout");
 
 struct TileArgs {
     Grid g;
-    int C, R, ncg, chunk, item_cap, list_cap;
+    int C, R, ncg, chunk, item_cap, list_cap, sig;   // sig: what the buffer was prepared for (counters[5] must match)
     float *feat[kMaxLv];
     const float *dout;
     const Plan *plans;
@@ -74,7 +74,8 @@ struct TileArgs {
     const int *lists;           // per tile: RoI indices, ascending
     const Item *items;          // crowded tiles (more than one chunk) from the front, the others from the back: the long items
                                 // get the early tickets
-    const int *counters;        // [0] list cursor, [1] ticket, [2] items at the front, [3] items at the back
+    const int *counters;        // [0] list cursor, [1] ticket, [2] items at the front, [3] items at the back, [4] declined RoIs,
+                                // [5] signature of the preparation
     int *ticket;
 };
 constexpr int kMaxTilesPerRoi = 128;   // RoIs overlapping more tiles are left to the gather kernel (bounds the list buffer)
@@ -146,6 +147,7 @@ tile_offsets_kernel(const __grid_constant__ TileArgs a, int *__restrict__ cnt, i
     pdl_entry();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.g.base[a.g.L]) return;
+    if (t == 0) counters[5] = a.sig;                                         // the buffer now belongs to this (shapes, R, chunk)
     const int c = cnt[t];
     cnt[t] = 0;                                                              // re-used as the tile's fill cursor
     const int off = c ? atomicAdd(counters + 0, c) : 0;
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(256)
 tile_zero_kernel(const __grid_constant__ TileArgs a)
 {
     pdl_entry();
+    if (__ldg(a.counters + 5) != a.sig) return;                              // not a plan made for these shapes: touch nothing
     const int nfront = __ldg(a.counters + 2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = blockIdx.x; i < nfront; i += gridDim.x) {
@@ -383,6 +386,9 @@ tile_bwd_kernel(const __grid_constant__ TileArgs a)
     __syncwarp();
     uint32_t parity = 0;
     float *const tlane = tile_s + lane * kTilePitch;
+    // a plan tensor that was not prepared for these shapes / RoI count / chunk length (two-op form: it comes from the caller) is
+    // refused as a whole: nothing is read through it, dX stays unwritten
+    if (__ldg(a.counters + 5) != a.sig) return;
     const int nfront = __ldg(a.counters + 2), nback = __ldg(a.counters + 3);
     const int ntickets = (nfront + nback) * a.ncg;
 
@@ -623,6 +629,11 @@ static void tile_args(const FeatSet &fs, int R, unsigned char *w, const TileLayo
     a.counters = reinterpret_cast<int *>(w + lo.ctl);
     a.ticket = reinterpret_cast<int *>(w + lo.ctl) + 1;
     a.chunk = tile_chunk();
+    unsigned h = 2166136261u;                                                // FNV-1a over everything the layout depends on
+    auto mix = [&h](int v) { h = (h ^ (unsigned)v) * 16777619u; };
+    mix(R); mix(fs.B); mix(fs.C); mix(fs.L); mix(a.chunk); mix(kTH);
+    for (int l = 0; l < fs.L; l++) { mix(fs.H[l]); mix(fs.W[l]); }
+    a.sig = (int)(h | 1u);                                                   // never 0 (a cleared buffer is not a plan)
 }
 
 // plans, lists, work items: everything that depends on the RoIs only (fs supplies the level shapes; its pointers are not used)
@@ -656,18 +667,11 @@ cudaError_t roialign_tile_prepare(const FeatSet &fs, const RoiFeat &f, const flo
 cudaError_t roialign_tile_run(const FeatSet &fs, int R, const float *dout, void *buf, bool accumulate, bool rearm, cudaStream_t s,
                               const int32_t **flags, const int32_t **ndecl)
 {
-    static int sms[64] = {0};
-    int dev = 0;
+    static_assert(kTileSmem <= 48 * 1024, "no opt-in for large dynamic shared memory needed");
+    int dev = 0, nsm = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64) return cudaErrorInvalidValue;
-    if (!sms[dev]) {
-        int n = 0;
-        if ((e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(tile_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(tile_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem)) != cudaSuccess) return e;
-        sms[dev] = n;
-    }
+    if ((e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     const TileLayout lo = tile_layout(fs, R);
     unsigned char *w = tile_base(buf);
     TileArgs a{};
@@ -675,7 +679,7 @@ cudaError_t roialign_tile_run(const FeatSet &fs, int R, const float *dout, void 
     a.dout = dout;
     if (rearm && (e = cudaMemsetAsync(a.ticket, 0, sizeof(int), s)) != cudaSuccess) return e;
     if (!accumulate && (e = launch_pdl(tile_zero_kernel, dim3(lo.T < 592 ? lo.T : 592), dim3(256), 0, s, a)) != cudaSuccess) return e;
-    const int grid = lo.T * a.ncg < sms[dev] * kTileCtasPerSm ? lo.T * a.ncg : sms[dev] * kTileCtasPerSm;
+    const int grid = lo.T * a.ncg < nsm * kTileCtasPerSm ? lo.T * a.ncg : nsm * kTileCtasPerSm;
     if (accumulate) e = launch_pdl(tile_bwd_kernel<true>, dim3(grid), dim3(32), (size_t)kTileSmem, s, a);
     else e = launch_pdl(tile_bwd_kernel<false>, dim3(grid), dim3(32), (size_t)kTileSmem, s, a);
     if (e != cudaSuccess) return e;

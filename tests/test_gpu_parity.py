@@ -507,6 +507,9 @@ def test_roialign_two_op_backward_vs_oracle():
         got = ext._backward_planned(rois, dout, fshapes, plan)
         for l in range(4):
             np.testing.assert_allclose(host(got[l]), dref[l], rtol=1e-5, atol=1e-5 * max(1.0, np.abs(dref[l]).max()))
+    # a plan that was prepared for another RoI count is refused on the device (signature mismatch): nothing is read through it
+    ext._backward_planned(rois[:1400].contiguous(), dout[:1400].contiguous(), fshapes, plan)
+    torch.cuda.synchronize()
     # shapes the tile kernel does not take are refused (return code 4), never silently mis-handled
     ext14 = SingleRoIExtractor(14, 2, strides, 56)
     with pytest.raises(Exception):
