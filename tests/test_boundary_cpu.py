@@ -97,3 +97,17 @@ def test_harness_speaks_the_reference_aot_abi(golden):
     assert lib.boxes_iou_nms_cpu(4, params, ndims, None, None, None, None) == 0
     assert cnt[0] == golden["rotnms_count"][0] and np.array_equal(keep, golden["rotnms_keep"])
     assert lib.boxes_iou_nms_cpu(3, params, ndims, None, None, None, None) == 1
+
+
+def test_plan_bytes_is_a_host_function():
+    """MdRoiAlignPlanBytes (size of the two-op backward's plan tensor) needs no GPU: positive, grows with R, -1 on bad arguments."""
+    import ctypes
+    lib = M.load_library()
+    H = (ctypes.c_int * 4)(200, 100, 50, 25)
+    W = (ctypes.c_int * 4)(336, 168, 84, 42)
+    a = lib.MdRoiAlignPlanBytes(512, 1, 256, 4, H, W)
+    b = lib.MdRoiAlignPlanBytes(4096, 8, 256, 4, H, W)
+    assert 0 < a < b < (64 << 20)
+    assert lib.MdRoiAlignPlanBytes(4096, 8, 256, 0, H, W) == -1
+    assert lib.MdRoiAlignPlanBytes(-1, 8, 256, 4, H, W) == -1
+    assert lib.MdRoiAlignPlanBytes(4096, 8, 256, 4, None, W) == -1
