@@ -10,6 +10,9 @@ What is executed (all paths relative to /root/reference/minddet/models):
   * pointpillars/src/core/box_np_ops.py:639-679   iou_jit(boxes, query, eps=1.0)
   * pointpillars/src/core/target_assigner.py:29-166  create_target_np(..., positive_fraction=None)
   * pointpillars/src/core/box_np_ops.py:453-523   create_anchors_3d_stride (grid order)
+  * pointpillars/src/core/box_np_ops.py:639-679   iou_jit(boxes, query, eps=0.0)  (offset-0 IoU)
+  * pointpillars/src/core/eval_utils.py:118-165   image_box_overlap(boxes, query, criterion=-1)
+  * centerpoint/det3d_ms/core/utils/center_utils.py:97-131  bilinear_interpolate_torch (4-tap weights)
   * centerpoint/det3d_ms/ops/iou-bev-nms-org.cpp:237-283  boxes_iou_nms_cpu, compiled by
     oracle/Makefile into oracle/_ref/nms_fast_ref.so and called through the 7-argument aot ABI.
 `mindspore` is not installed, so a stub module is injected; none of the functions above touch it
@@ -44,6 +47,10 @@ def _stub_mindspore():
     sys.modules["mindspore"] = ms
     sys.modules["mindspore.ops"] = ms.ops
     sys.modules["mindspore.nn"] = ms.nn
+    ms.common = types.ModuleType("mindspore.common")           # imported (never called) by circle_nms_jit.py
+    ms.common.dtype = types.ModuleType("mindspore.common.dtype")
+    sys.modules["mindspore.common"] = ms.common
+    sys.modules["mindspore.common.dtype"] = ms.common.dtype
 
 
 class _AsNumpy:
@@ -166,6 +173,44 @@ def main():
     out["rotnms_thr"] = thr
     out["rotnms_keep"] = keep
     out["rotnms_count"] = cnt
+
+    # ---- added in round 2: independent generator, so every array above keeps its bytes -------------
+    rng2 = np.random.default_rng(20261019)
+
+    # iou_jit(eps=0) and eval_utils.image_box_overlap(criterion=-1): the offset-0 IoU (no +1)
+    from src.core import eval_utils
+    a0 = rand_boxes(rng2, 400)
+    g0 = rand_boxes(rng2, 31, smin=16, smax=512)
+    a0[7] = g0[3]                                  # identical pair (IoU 1)
+    a0[8] = g0[4] + np.float32(2000.0)             # disjoint
+    a0[9, 0] = g0[5, 2]; a0[9, 2] = a0[9, 0] + 40  # touching edge: iw == 0 -> 0
+    out["iou0_boxes"] = a0
+    out["iou0_gts"] = g0
+    out["iou0_mat_iou_jit"] = box_np_ops.iou_jit(a0, g0, eps=0.0)
+    out["iou0_mat_image_box_overlap"] = eval_utils.image_box_overlap(a0, g0, criterion=-1)
+
+    # bilinear_interpolate_torch (centerpoint/det3d_ms/core/utils/center_utils.py:97-131): the 4-tap
+    # weights on interior points.  The file is executed from where it lies through a synthetic package
+    # (its own package __init__ imports MindSpore), so its relative import of circle_nms_jit resolves.
+    import importlib
+    import torch
+    pkg = types.ModuleType("_ref_center_utils_pkg")
+    pkg.__path__ = [os.path.join(REF, "centerpoint", "det3d_ms", "core", "utils")]
+    sys.modules["_ref_center_utils_pkg"] = pkg
+    cu = importlib.import_module("_ref_center_utils_pkg.center_utils")
+    Hh, Ww, Cc = 19, 27, 5
+    im = rng2.uniform(-1, 1, (Hh, Ww, Cc)).astype(np.float32)
+    n = 600
+    x = rng2.uniform(0.0, Ww - 1.0, n).astype(np.float32)
+    y = rng2.uniform(0.0, Hh - 1.0, n).astype(np.float32)
+    x[:8] = np.arange(8, dtype=np.float32)          # exactly on lattice columns
+    y[4:12] = np.arange(8, dtype=np.float32) + 2     # exactly on lattice rows
+    x = np.minimum(x, np.float32(Ww - 1.001)); y = np.minimum(y, np.float32(Hh - 1.001))
+    val = cu.bilinear_interpolate_torch(torch.from_numpy(im), torch.from_numpy(x), torch.from_numpy(y)).numpy()
+    out["bilinear_im"] = im
+    out["bilinear_x"] = x
+    out["bilinear_y"] = y
+    out["bilinear_val"] = val.astype(np.float32)
 
     path = os.path.join(HERE, "reference_golden.npz")
     np.savez_compressed(path, **out)

@@ -352,6 +352,21 @@ def test_roialign_fwd_bwd_vs_oracle(P, S, C, exact):
         np.testing.assert_allclose(host(ft[l].grad), dref[l], rtol=1e-5, atol=1e-5 * max(1.0, np.abs(dref[l]).max()))
 
 
+@pytest.mark.parametrize("exact", [False, True])
+def test_roialign_taps_vs_reference_bilinear_golden(golden, exact):
+    """The CUDA path against outputs of the REFERENCE's own bilinear_interpolate_torch
+    (centerpoint/det3d_ms/core/utils/center_utils.py:97-131; fixture made by tests/golden/make_golden.py):
+    a 1x1-bin, 1-sample RoIAlign of a stride-1 map is one bilinear read at the RoI centre."""
+    im, x, y, ref = golden["bilinear_im"], golden["bilinear_x"], golden["bilinear_y"], golden["bilinear_val"]
+    feat = np.ascontiguousarray(im.transpose(2, 0, 1)[None])
+    h = np.float32(0.5)
+    rois = np.stack([np.zeros_like(x), x - h, y - h, x + h, y + h], 1).astype(np.float32)
+    ext = SingleRoIExtractor(1, 1, (1,), 56, exact=exact)
+    got = host(ext(dev(rois), dev(feat))).reshape(len(x), -1)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=2e-5)
+    assert np.array_equal(got, O.roialign_fwd([feat], (1,), rois, P=1, S=1).reshape(len(x), -1)) or not exact
+
+
 def test_roialign_full_size_vs_oracle():
     """config-2 shapes (C=256, 4 levels), 128 RoIs against the oracle."""
     rng = np.random.default_rng(44)

@@ -68,3 +68,31 @@ def test_anchor_grid_order_matches_reference_generator(golden):
     # per-cell variants are the innermost axis in both
     assert np.array_equal(ref[0, 2, 3, 0, :, 6], np.array([0.0, 1.0], np.float32))
     assert np.array_equal(mine[2, 3, :, 2] - mine[2, 3, :, 0], np.array([2.0, 4.0], np.float32))
+
+
+def test_iou_offset0_matches_iou_jit_and_image_box_overlap(golden):
+    # pointpillars/src/core/box_np_ops.py:639-679 with eps=0.0 and eval_utils.py:118-165 (criterion -1):
+    # the no-offset IoU the NMS modes and the YOLO / RCNN post-process use.
+    got = O.iou_matrix(golden["iou0_boxes"], golden["iou0_gts"], off=0.0)
+    for name in ("iou0_mat_iou_jit", "iou0_mat_image_box_overlap"):
+        ref = golden[name]
+        assert np.array_equal(got == 0, ref == 0), name          # same pairs overlap (strict iw > 0, ih > 0)
+        np.testing.assert_allclose(got, ref, rtol=2e-6, atol=1e-7, err_msg=name)
+    assert got[7, 3] == 1.0 and got[8, 4] == 0.0 and got[9, 5] == 0.0
+
+
+def bilinear_rois(x, y):
+    """One-bin, one-sample RoIs whose single sample point is (x, y) on a stride-1 map."""
+    h = np.float32(0.5)
+    return np.stack([np.zeros_like(x), x - h, y - h, x + h, y + h], 1).astype(np.float32)
+
+
+def test_roialign_taps_match_bilinear_interpolate_torch(golden):
+    # centerpoint/det3d_ms/core/utils/center_utils.py:97-131 on interior points: a 1x1-bin, 1-sample RoIAlign
+    # of a stride-1 map is exactly one bilinear read.  (At x >= W-1 that function's clamped x1 makes its weights
+    # negative; the RoIAlign edge rules of CONVENTIONS #16 differ there by design, so the fixture stays interior.)
+    im, x, y, ref = golden["bilinear_im"], golden["bilinear_x"], golden["bilinear_y"], golden["bilinear_val"]
+    feat = np.ascontiguousarray(im.transpose(2, 0, 1)[None])
+    rois = bilinear_rois(x, y)
+    got = O.roialign_fwd([feat], (1,), rois, P=1, S=1, lvl=np.zeros(len(x), np.int32))
+    np.testing.assert_allclose(got.reshape(len(x), -1), ref, rtol=0, atol=2e-5)
