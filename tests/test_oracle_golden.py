@@ -96,3 +96,38 @@ def test_roialign_taps_match_bilinear_interpolate_torch(golden):
     rois = bilinear_rois(x, y)
     got = O.roialign_fwd([feat], (1,), rois, P=1, S=1, lvl=np.zeros(len(x), np.int32))
     np.testing.assert_allclose(got.reshape(len(x), -1), ref, rtol=0, atol=2e-5)
+
+
+def test_assign_mode0_differs_from_the_pinned_mode1_only_where_the_rules_say(golden):
+    """Mode 0 (the benchmarked, unpinned rule order) against mode 1 (bit-exact to the reference's create_target_np,
+    target_assigner.py:84-134) on the reference-run fixtures.  With F(a) = the gts whose best IoU anchor a ties
+    (max > 0): mode 1 gives such an anchor its OWN argmax gt, mode 0 the last gt of F(a) (CONVENTIONS #11 / #12).
+    Everywhere else -- positives by threshold, negatives, ignored -- the two modes must be identical, so the
+    reference pins mode 0 on every anchor outside that set."""
+    total = differing = 0
+    # a hand-made case that exercises the differing set: anchor 0 equals gt 0 and is also the only anchor touching gt 1
+    crafted = (np.array([[0, 0, 99, 99], [300, 300, 340, 340], [0, 0, 99, 49]], np.float32),
+               np.array([[0, 0, 99, 99], [90, 90, 109, 109]], np.float32), np.float32(0.6), np.float32(0.3))
+    cases = [(t, golden[f"assign_{t}_anchors"], golden[f"assign_{t}_gts"], *golden[f"assign_{t}_thr"]) for t in "abc"]
+    for tag, anchors, gts, pos, neg in cases + [("crafted",) + crafted]:
+        a1, _, am = O.assign(anchors, gts, pos, neg, 0.0, off=1.0, mode=1)
+        a0, _, _ = O.assign(anchors, gts, pos, neg, 1e-30, off=1.0, mode=0)   # min_pos_iou: "max > 0", as mode 1
+        iou = O.iou_matrix(anchors, gts, off=1.0)
+        gmax = iou.max(0)
+        ties = (iou == gmax[None, :]) & (gmax[None, :] > 0)
+        forced = ties.any(1)
+        last = np.where(forced, ties.shape[1] - 1 - np.argmax(ties[:, ::-1], 1), -1)
+        differ = forced & (last != am)
+        assert np.array_equal(a0[~differ], a1[~differ]), tag
+        assert np.array_equal(a0[differ], last[differ] + 1) and np.array_equal(a1[differ], am[differ] + 1), tag
+        if tag == "crafted":
+            assert differ.tolist() == [True, False, False] and a0.tolist() == [2, 0, -1] and a1.tolist() == [1, 0, -1]
+            continue
+        # on the reference-run fixtures themselves mode 0 reproduces the reference's labels and matched gt ids
+        labels, gtids = golden[f"assign_{tag}_labels"], golden[f"assign_{tag}_gtids"]
+        fg = (labels > 0) & ~differ
+        assert np.array_equal(a0 > 0, labels > 0) and np.array_equal(a0 == 0, labels == 0), tag
+        assert np.array_equal(a0[fg] - 1, gtids[fg]), tag
+        total += len(a0)
+        differing += int(differ.sum())
+    assert total > 1000 and differing < total // 20
