@@ -4,7 +4,9 @@
   (minddet/models/centerpoint/det3d_ms/ops/iou-bev-nms-org.cpp) is compiled from where it lies into
   oracle/_ref/nms_fast_ref.so by oracle/Makefile and called here (kind: "reference", parity PINNED).
 * axis-aligned IoU on 7-float boxes (`iou_normal`, .../test_custom_pytorch/iou3d_nms_kernel.cu:347-358) needs a GPU +
-  libtorch to run in the reference, so it is restated in numpy fp32 with the same operation order (parity unpinned).
+  libtorch to run in the reference as a whole, so it is restated in numpy fp32 with the same operation order; the
+  restatement is pinned bit-exact (lattice boxes, tests/test_oracle_golden.py) to that one function cut out of the
+  reference file and compiled for the host (oracle/ref_iou_normal_harness.cpp -> oracle/_ref/iou_normal_ref.so).
 """
 import ctypes
 import os

@@ -9,13 +9,21 @@
  * PARITY STATUS: the reference checkout (/root/reference) contains no Faster R-CNN code, so
  *   - o_nms           is pinned (bit-exact, tests/golden) to pointpillars/src/core/nms.py:85-112
  *                     (nms_jit, mode offset=0/inclusive) and nms.py:7-41 (apply_nms, offset=1/strict);
- *                     the default mode follows iou_normal/nms_normal_kernel
- *                     centerpoint/det3d_ms/ops/test_custom_pytorch/iou3d_nms_kernel.cu:347-405.
- *   - o_iou_pair_p1   is pinned (<=1e-6) to pointpillars/src/core/box_np_ops.py:639-679 (iou_jit, eps=1).
- *   - o_assign mode 1 is pinned (bit-exact) to pointpillars/src/core/target_assigner.py:84-134.
+ *                     the default mode (offset 0, strict >, union guard) is pinned bit-exact on lattice
+ *                     boxes to iou_normal, centerpoint/det3d_ms/ops/test_custom_pytorch/
+ *                     iou3d_nms_kernel.cu:347-358, cut out of that file and run on the host
+ *                     (oracle/ref_iou_normal_harness.cpp; sweep restated from :361-405, :526-536).
+ *   - o_iou_pair_p1   is pinned (<=1e-6) to pointpillars/src/core/box_np_ops.py:639-679 (iou_jit, eps=1);
+ *                     with offset 0 (<=2e-6) to iou_jit(eps=0) and eval_utils.py:118-165 (image_box_overlap).
+ *   - o_assign mode 1 is pinned (bit-exact) to pointpillars/src/core/target_assigner.py:84-134; mode 0
+ *                     reproduces the same reference-run fixtures and may differ from mode 1 only on
+ *                     anchors that tie one gt's best IoU while their argmax is another gt (tested).
  *   - anchors grid order is pinned to pointpillars/src/core/box_np_ops.py:453-523.
- *   - decode, top-k ties, assign mode 0, sampling, RoI level map, RoIAlign fwd/bwd: PARITY UNPINNED
- *     (no reference code exists; cross-checked against torchvision where conventions coincide).
+ *   - RoIAlign 4-tap bilinear weights (interior points) are pinned (2e-5) to bilinear_interpolate_torch,
+ *                     centerpoint/det3d_ms/core/utils/center_utils.py:97-131.
+ *   - decode, top-k ties, sampling, RoI level map, RoIAlign bin geometry / edge rules / backward:
+ *     PARITY UNPINNED (no reference code exists; cross-checked against torchvision where conventions
+ *     coincide).
  */
 #include <math.h>
 #include <pthread.h>

@@ -13,6 +13,10 @@ What is executed (all paths relative to /root/reference/minddet/models):
   * pointpillars/src/core/box_np_ops.py:639-679   iou_jit(boxes, query, eps=0.0)  (offset-0 IoU)
   * pointpillars/src/core/eval_utils.py:118-165   image_box_overlap(boxes, query, criterion=-1)
   * centerpoint/det3d_ms/core/utils/center_utils.py:97-131  bilinear_interpolate_torch (4-tap weights)
+  * centerpoint/det3d_ms/ops/test_custom_pytorch/iou3d_nms_kernel.cu:42,347-358  EPS and iou_normal, cut out of the
+    file where it lies by oracle/Makefile and compiled for the host (oracle/ref_iou_normal_harness.cpp ->
+    oracle/_ref/iou_normal_ref.so); the pair loop / greedy sweep around it restate nms_normal_kernel :361-405 and
+    the host reduce :526-536
   * centerpoint/det3d_ms/ops/iou-bev-nms-org.cpp:237-283  boxes_iou_nms_cpu, compiled by
     oracle/Makefile into oracle/_ref/nms_fast_ref.so and called through the 7-argument aot ABI.
 `mindspore` is not installed, so a stub module is injected; none of the functions above touch it
@@ -211,6 +215,62 @@ def main():
     out["bilinear_x"] = x
     out["bilinear_y"] = y
     out["bilinear_val"] = val.astype(np.float32)
+
+    # ---- iou_normal (iou3d_nms_kernel.cu:347-358), cut out of the reference's CUDA file by oracle/Makefile and run on
+    # the host (oracle/ref_iou_normal_harness.cpp): the arithmetic of the DEFAULT NMS mode (offset 0, strict >, union
+    # guard EPS).  Boxes on a 0.25-px lattice: xyxy <-> (centre, size) converts without rounding, so the fixture pins
+    # bits, not tolerances; one off-lattice case with a threshold margin checks the general behaviour.
+    nl = ctypes.CDLL(os.path.join(REPO, "oracle", "_ref", "iou_normal_ref.so"))
+    nl.ref_iou_normal_eps.restype = ctypes.c_float
+    vp = ctypes.c_void_p
+    nl.ref_iou_normal_matrix.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, vp]
+    nl.ref_nms_normal.argtypes = [vp, ctypes.c_int, ctypes.c_float, vp, ctypes.POINTER(ctypes.c_int)]
+    out["ioun_eps"] = np.array([nl.ref_iou_normal_eps()], np.float32)
+
+    def to7(xyxy):
+        b7 = np.zeros((len(xyxy), 7), np.float32)
+        b7[:, 0] = (xyxy[:, 0] + xyxy[:, 2]) / np.float32(2)
+        b7[:, 1] = (xyxy[:, 1] + xyxy[:, 3]) / np.float32(2)
+        b7[:, 3] = xyxy[:, 2] - xyxy[:, 0]
+        b7[:, 4] = xyxy[:, 3] - xyxy[:, 1]
+        b7[:, 5] = 1.0
+        return b7
+
+    def ref_matrix(a7, b7):
+        m = np.zeros((len(a7), len(b7)), np.float32)
+        nl.ref_iou_normal_matrix(a7.ctypes.data, len(a7), b7.ctypes.data, len(b7), m.ctypes.data)
+        return m
+
+    def ref_keep(b7, thr):
+        keep = np.zeros(len(b7), np.int64)
+        cnt = ctypes.c_int(0)
+        nl.ref_nms_normal(b7.ctypes.data, len(b7), thr, keep.ctypes.data, ctypes.byref(cnt))
+        return keep[:cnt.value].copy()
+
+    for tag, n, cl, lattice in (("a", 600, None, True), ("b", 900, 25, True), ("c", 64, 4, True), ("d", 700, 20, False)):
+        xy = rand_boxes(rng2, n, cluster=cl)
+        if lattice:
+            xy = (np.round(xy * 4) / 4).astype(np.float32)
+            xy[:, 2] = np.maximum(xy[:, 2], xy[:, 0] + 0.25)
+            xy[:, 3] = np.maximum(xy[:, 3], xy[:, 1] + 0.25)
+            if tag == "c":
+                xy[10] = xy[3]                       # exact duplicate
+                xy[20, 2] = xy[20, 0]                # zero-width box: area 0, union guard
+                xy[21] = xy[20]
+            b7 = to7(xy)
+            assert np.array_equal(b7[:, 0] - b7[:, 3] / 2, xy[:, 0]) and np.array_equal(b7[:, 0] + b7[:, 3] / 2, xy[:, 2])
+            assert np.array_equal(b7[:, 1] - b7[:, 4] / 2, xy[:, 1]) and np.array_equal(b7[:, 1] + b7[:, 4] / 2, xy[:, 3])
+        else:
+            b7 = to7(xy)
+        out[f"ioun_{tag}_xyxy"] = xy                 # rows are already in score order (row 0 = best)
+        out[f"ioun_{tag}_box7"] = b7
+        m = ref_matrix(b7, b7)
+        out[f"ioun_{tag}_iou"] = m[:96].copy()       # first 96 rows against all boxes (keeps the fixture small)
+        for thr in (0.3, 0.7):
+            t = float(np.float32(thr))
+            if not lattice:
+                assert np.abs(m[np.triu_indices(n, 1)] - t).min() > 1e-5   # no pair on the threshold
+            out[f"ioun_{tag}_{thr}_keep"] = ref_keep(b7, t)
 
     path = os.path.join(HERE, "reference_golden.npz")
     np.savez_compressed(path, **out)

@@ -1,0 +1,41 @@
+"""The CUDA path against fixtures made by running the REFERENCE's own `iou_normal` (iou3d_nms_kernel.cu:347-358, cut out of
+the file where it lies and compiled for the host: oracle/ref_iou_normal_harness.cpp, tests/golden/make_golden.py).
+
+The CPU side of this pin (oracle == fixture, bit for bit) is tests/test_oracle_golden.py; CUDA == oracle in the default NMS
+mode is tests/test_gpu_parity.py / tests/test_gpu_bev.py.  This file closes the triangle directly.  It was written after the
+round's GPU minutes were spent, so it is named to sort after every other `-m gpu` file: under `pytest -x` it cannot hide a
+test that has been seen green on a B200 (profiles/r2_gpu_tests_head.log)."""
+import numpy as np
+import pytest
+import torch
+
+from minddet_b200 import NMSWithMask
+from minddet_b200.bev_ops import NmsNormalGpu
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_default_nms_mode_vs_reference_iou_normal_golden(golden, tag):
+    # NMSWithMask default mode = offset 0, strict >, union guard 1e-8 (CONVENTIONS #1-2); rows are in score order
+    xy = golden[f"ioun_{tag}_xyxy"]
+    for thr in (0.3, 0.7):
+        ref_keep = golden[f"ioun_{tag}_{thr}_keep"]
+        _, mask, _ = NMSWithMask(float(np.float32(thr)), 0.0, False, 1e-8)(dev(xy))
+        assert np.array_equal(np.nonzero(mask.cpu().numpy())[0], ref_keep), (tag, thr)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_nms_normal_gpu_vs_reference_iou_normal_golden(golden, tag):
+    # the reference's own symbol (NmsNormalGpu, iou3d_nms_kernel.cu:548-601) on the 7-float boxes
+    b7 = golden[f"ioun_{tag}_box7"]
+    for thr in (0.3, 0.7):
+        ref_keep = golden[f"ioun_{tag}_{thr}_keep"]
+        keep, num = NmsNormalGpu()(dev(b7), dev(np.array([thr], np.float32)))
+        got = keep.cpu().numpy()
+        assert int(num) == len(ref_keep), (tag, thr)
+        assert np.array_equal(got[:len(ref_keep)], ref_keep) and not got[len(ref_keep):].any(), (tag, thr)

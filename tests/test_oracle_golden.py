@@ -131,3 +131,26 @@ def test_assign_mode0_differs_from_the_pinned_mode1_only_where_the_rules_say(gol
         total += len(a0)
         differing += int(differ.sum())
     assert total > 1000 and differing < total // 20
+
+
+def test_default_nms_mode_matches_the_references_iou_normal(golden):
+    """The DEFAULT NMS mode (offset 0, strict >, union guard: what `Proposal`, the YOLO / RCNN post-process and
+    `NmsNormalGpu` run) against the reference's own `iou_normal` (iou3d_nms_kernel.cu:347-358) executed on the host
+    (oracle/ref_iou_normal_harness.cpp).  Lattice cases a-c: keep lists AND IoU values bit-identical; the off-lattice
+    case d (centre/size <-> corner conversion rounds) keeps the same boxes and agrees to 1e-6."""
+    from oracle import bev
+    eps = float(golden["ioun_eps"][0])
+    assert eps == float(np.float32(1e-8))
+    for tag in "abcd":
+        xy, b7, ref_iou = golden[f"ioun_{tag}_xyxy"], golden[f"ioun_{tag}_box7"], golden[f"ioun_{tag}_iou"]
+        got = bev.iou_normal(b7[:96], b7)
+        if tag != "d":
+            assert np.array_equal(got, ref_iou), tag                       # numpy restatement used by the BEV tests
+        else:
+            np.testing.assert_allclose(got, ref_iou, rtol=1e-6, atol=1e-7)
+        for thr in (0.3, 0.7):
+            ref_keep = golden[f"ioun_{tag}_{thr}_keep"]
+            mask = O.nms(xy, np.float32(thr), off=0.0, inclusive=False, union_eps=eps)
+            assert np.array_equal(_keep_from_mask(mask), ref_keep), (tag, thr)
+            # the numpy oracle the NmsNormalGpu tests use (tests/test_gpu_bev.py)
+            assert np.array_equal(bev.greedy_from_iou(bev.iou_normal(b7, b7), np.float32(thr)), ref_keep), (tag, thr)
