@@ -6,7 +6,7 @@
 //    host reduce of NmsNormalGpu :526-536),
 // which needs libtorch and a GPU to run as a whole.  `iou_normal` itself is plain C float arithmetic, so
 // oracle/Makefile cuts that one function and the EPS constant out of the file WHERE IT LIES into
-// oracle/_ref/iou_normal_extract.inc (git-ignored, never committed) and this harness compiles them for the host with
+// oracle/_ref/iou_normal_extract.inc (git-ignored, never committed, deleted again once the .so is linked) and this harness compiles them for the host with
 // `__device__` defined away.  What runs below is therefore the reference's own expression tree; only the pair loop and
 // the greedy sweep around it (the kernel's bit mask + the host reduce: box j is removed iff a kept i < j has
 // iou_normal(i, j) > thr, strict) are restated here, because a __global__ kernel cannot run on the host.
