@@ -5,6 +5,7 @@ mangled C++ name).  Run once in the build container:  python tests/golden/make_b
 """
 import ctypes
 import os
+import sys
 
 import numpy as np
 
@@ -72,7 +73,7 @@ def main():
         out[f"nms_{tag}_keep_gt"], out[f"nms_{tag}_count_gt"] = k64, np.array([len(kept)], np.int32)
         out[f"nms_{tag}_margin"] = np.array([margin], np.float32)
         print(tag, "kept(cpu >=)", int(cnt[0]), "kept(>)", len(kept), "margin", margin, "attempts", attempt + 1)
-    path = os.path.join(HERE, "bev_golden.npz")
+    path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "bev_golden.npz")   # argv[1]: tests/test_golden_regenerates.py
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 

@@ -272,7 +272,7 @@ def main():
                 assert np.abs(m[np.triu_indices(n, 1)] - t).min() > 1e-5   # no pair on the threshold
             out[f"ioun_{tag}_{thr}_keep"] = ref_keep(b7, t)
 
-    path = os.path.join(HERE, "reference_golden.npz")
+    path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "reference_golden.npz")   # argv[1]: tests/test_golden_regenerates.py
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")
 
