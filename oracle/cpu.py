@@ -22,7 +22,7 @@ def build(force=False):
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "_build/liboracle.so"], stdout=subprocess.DEVNULL)
     ref_so = os.path.join(_HERE, "_ref", "nms_fast_ref.so")
-    ref_so2 = os.path.join(_HERE, "_ref", "iou_normal_ref.so")     # the reference's iou_normal on the host (golden generator only)
+    ref_so2 = os.path.join(_HERE, "_ref", "iou3d_device_ref.so")   # the reference's __device__ functions on the host (golden generators only)
     if os.path.isdir("/root/reference") and (force or not os.path.exists(ref_so) or not os.path.exists(ref_so2)):
         subprocess.call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 

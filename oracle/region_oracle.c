@@ -12,7 +12,7 @@
  *                     the default mode (offset 0, strict >, union guard) is pinned bit-exact on lattice
  *                     boxes to iou_normal, centerpoint/det3d_ms/ops/test_custom_pytorch/
  *                     iou3d_nms_kernel.cu:347-358, cut out of that file and run on the host
- *                     (oracle/ref_iou_normal_harness.cpp; sweep restated from :361-405, :526-536).
+ *                     (oracle/ref_cu_device_harness.cpp; sweep restated from :361-405, :526-536).
  *   - o_iou_pair_p1   is pinned (<=1e-6) to pointpillars/src/core/box_np_ops.py:639-679 (iou_jit, eps=1);
  *                     with offset 0 (<=2e-6) to iou_jit(eps=0) and eval_utils.py:118-165 (image_box_overlap).
  *   - o_assign mode 1 is pinned (bit-exact) to pointpillars/src/core/target_assigner.py:84-134; mode 0

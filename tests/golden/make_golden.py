@@ -14,8 +14,8 @@ What is executed (all paths relative to /root/reference/minddet/models):
   * pointpillars/src/core/eval_utils.py:118-165   image_box_overlap(boxes, query, criterion=-1)
   * centerpoint/det3d_ms/core/utils/center_utils.py:97-131  bilinear_interpolate_torch (4-tap weights)
   * centerpoint/det3d_ms/ops/test_custom_pytorch/iou3d_nms_kernel.cu:42,347-358  EPS and iou_normal, cut out of the
-    file where it lies by oracle/Makefile and compiled for the host (oracle/ref_iou_normal_harness.cpp ->
-    oracle/_ref/iou_normal_ref.so); the pair loop / greedy sweep around it restate nms_normal_kernel :361-405 and
+    file where it lies by oracle/Makefile and compiled for the host (oracle/ref_cu_device_harness.cpp ->
+    oracle/_ref/iou3d_device_ref.so); the pair loop / greedy sweep around it restate nms_normal_kernel :361-405 and
     the host reduce :526-536
   * centerpoint/det3d_ms/ops/iou-bev-nms-org.cpp:237-283  boxes_iou_nms_cpu, compiled by
     oracle/Makefile into oracle/_ref/nms_fast_ref.so and called through the 7-argument aot ABI.
@@ -217,15 +217,15 @@ def main():
     out["bilinear_val"] = val.astype(np.float32)
 
     # ---- iou_normal (iou3d_nms_kernel.cu:347-358), cut out of the reference's CUDA file by oracle/Makefile and run on
-    # the host (oracle/ref_iou_normal_harness.cpp): the arithmetic of the DEFAULT NMS mode (offset 0, strict >, union
+    # the host (oracle/ref_cu_device_harness.cpp): the arithmetic of the DEFAULT NMS mode (offset 0, strict >, union
     # guard EPS).  Boxes on a 0.25-px lattice: xyxy <-> (centre, size) converts without rounding, so the fixture pins
     # bits, not tolerances; one off-lattice case with a threshold margin checks the general behaviour.
-    nl = ctypes.CDLL(os.path.join(REPO, "oracle", "_ref", "iou_normal_ref.so"))
-    nl.ref_iou_normal_eps.restype = ctypes.c_float
+    nl = ctypes.CDLL(os.path.join(REPO, "oracle", "_ref", "iou3d_device_ref.so"))
+    nl.ref_cu_eps.restype = ctypes.c_float
     vp = ctypes.c_void_p
-    nl.ref_iou_normal_matrix.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, vp]
-    nl.ref_nms_normal.argtypes = [vp, ctypes.c_int, ctypes.c_float, vp, ctypes.POINTER(ctypes.c_int)]
-    out["ioun_eps"] = np.array([nl.ref_iou_normal_eps()], np.float32)
+    nl.ref_cu_pair_matrix.argtypes = [ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, vp]
+    nl.ref_cu_nms.argtypes = [ctypes.c_int, vp, ctypes.c_int, ctypes.c_float, vp, ctypes.POINTER(ctypes.c_int)]
+    out["ioun_eps"] = np.array([nl.ref_cu_eps()], np.float32)
 
     def to7(xyxy):
         b7 = np.zeros((len(xyxy), 7), np.float32)
@@ -238,13 +238,13 @@ def main():
 
     def ref_matrix(a7, b7):
         m = np.zeros((len(a7), len(b7)), np.float32)
-        nl.ref_iou_normal_matrix(a7.ctypes.data, len(a7), b7.ctypes.data, len(b7), m.ctypes.data)
+        nl.ref_cu_pair_matrix(0, a7.ctypes.data, len(a7), b7.ctypes.data, len(b7), m.ctypes.data)
         return m
 
     def ref_keep(b7, thr):
         keep = np.zeros(len(b7), np.int64)
         cnt = ctypes.c_int(0)
-        nl.ref_nms_normal(b7.ctypes.data, len(b7), thr, keep.ctypes.data, ctypes.byref(cnt))
+        nl.ref_cu_nms(0, b7.ctypes.data, len(b7), thr, keep.ctypes.data, ctypes.byref(cnt))
         return keep[:cnt.value].copy()
 
     for tag, n, cl, lattice in (("a", 600, None, True), ("b", 900, 25, True), ("c", 64, 4, True), ("d", 700, 20, False)):

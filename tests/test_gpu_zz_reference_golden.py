@@ -1,5 +1,5 @@
 """The CUDA path against fixtures made by running the REFERENCE's own `iou_normal` (iou3d_nms_kernel.cu:347-358, cut out of
-the file where it lies and compiled for the host: oracle/ref_iou_normal_harness.cpp, tests/golden/make_golden.py).
+the file where it lies and compiled for the host: oracle/ref_cu_device_harness.cpp, tests/golden/make_golden.py).
 
 The CPU side of this pin (oracle == fixture, bit for bit) is tests/test_oracle_golden.py; CUDA == oracle in the default NMS
 mode is tests/test_gpu_parity.py / tests/test_gpu_bev.py.  This file closes the triangle directly.  It was written after the

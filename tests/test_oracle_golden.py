@@ -136,7 +136,7 @@ def test_assign_mode0_differs_from_the_pinned_mode1_only_where_the_rules_say(gol
 def test_default_nms_mode_matches_the_references_iou_normal(golden):
     """The DEFAULT NMS mode (offset 0, strict >, union guard: what `Proposal`, the YOLO / RCNN post-process and
     `NmsNormalGpu` run) against the reference's own `iou_normal` (iou3d_nms_kernel.cu:347-358) executed on the host
-    (oracle/ref_iou_normal_harness.cpp).  Lattice cases a-c: keep lists AND IoU values bit-identical; the off-lattice
+    (oracle/ref_cu_device_harness.cpp).  Lattice cases a-c: keep lists AND IoU values bit-identical; the off-lattice
     case d (centre/size <-> corner conversion rounds) keeps the same boxes and agrees to 1e-6."""
     from oracle import bev
     eps = float(golden["ioun_eps"][0])
@@ -154,3 +154,26 @@ def test_default_nms_mode_matches_the_references_iou_normal(golden):
             assert np.array_equal(_keep_from_mask(mask), ref_keep), (tag, thr)
             # the numpy oracle the NmsNormalGpu tests use (tests/test_gpu_bev.py)
             assert np.array_equal(bev.greedy_from_iou(bev.iou_normal(b7, b7), np.float32(thr)), ref_keep), (tag, thr)
+
+
+def test_reference_gpu_file_and_cpu_file_agree_bit_for_bit():
+    """The rotated-BEV symbols are pinned to the reference's CPU file (iou-bev-nms-org.cpp, compiled as it lies).  The symbols
+    they replace live in the GPU file (iou3d_nms_kernel.cu): its __device__ functions, cut out and run on the host, give the
+    same IoU bits and the keep lists the fixtures hold for the strict '>' symbols -- one arithmetic, two files."""
+    import os
+    import pytest
+    from oracle import bev
+    if not (bev.have_ref() and bev.have_ref_cu()):
+        pytest.skip("oracle/_ref not built (needs /root/reference once)")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bev_golden.npz"))
+    a, b = g["iou_a"], g["iou_b"]
+    iou_cu = bev.ref_cu_pairs("iou_bev", a, b)
+    assert np.array_equal(iou_cu, g["iou_ref"]) and np.array_equal(iou_cu, bev.ref_iou_bev(a, b))
+    assert (iou_cu > 0).sum() > 1000
+    ov = bev.ref_cu_pairs("box_overlap", a, b)
+    sa, sb = a[:, 3] * a[:, 4], b[:, 3] * b[:, 4]
+    assert np.array_equal(ov / np.maximum(sa[:, None] + sb[None] - ov, np.float32(1e-8)), iou_cu)
+    for tag in "abcd":
+        boxes, thr = g[f"nms_{tag}_boxes"], g[f"nms_{tag}_thr"][0]
+        n = int(g[f"nms_{tag}_count_gt"][0])
+        assert np.array_equal(bev.ref_cu_nms(boxes, thr, rotated=True), g[f"nms_{tag}_keep_gt"][:n]), tag
