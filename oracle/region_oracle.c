@@ -18,10 +18,12 @@
  *   - o_assign mode 1 is pinned (bit-exact) to pointpillars/src/core/target_assigner.py:84-134; mode 0
  *                     reproduces the same reference-run fixtures and may differ from mode 1 only on
  *                     anchors that tie one gt's best IoU while their argmax is another gt (tested).
+ *   - o_topk          values + indices on unique scores are pinned (bit-exact) to pointpillars/src/core/nms.py:66-83
+ *                     (topk_); the tie order is a decision.
  *   - anchors grid order is pinned to pointpillars/src/core/box_np_ops.py:453-523.
  *   - RoIAlign 4-tap bilinear weights (interior points) are pinned (2e-5) to bilinear_interpolate_torch,
  *                     centerpoint/det3d_ms/core/utils/center_utils.py:97-131.
- *   - decode, top-k ties, sampling, RoI level map, RoIAlign bin geometry / edge rules / backward:
+ *   - decode, top-k tie order, sampling, RoI level map, RoIAlign bin geometry / edge rules / backward:
  *     PARITY UNPINNED (no reference code exists; cross-checked against torchvision where conventions
  *     coincide).
  */

@@ -12,6 +12,8 @@ What is executed (all paths relative to /root/reference/minddet/models):
   * pointpillars/src/core/box_np_ops.py:453-523   create_anchors_3d_stride (grid order)
   * pointpillars/src/core/box_np_ops.py:639-679   iou_jit(boxes, query, eps=0.0)  (offset-0 IoU)
   * pointpillars/src/core/eval_utils.py:118-165   image_box_overlap(boxes, query, criterion=-1)
+  * pointpillars/src/data/kitti_common.py:10-73    iou(boxes1, boxes2, add1)
+  * pointpillars/src/core/nms.py:66-83            topk_(matrix, K, axis=0)
   * centerpoint/det3d_ms/core/utils/center_utils.py:97-131  bilinear_interpolate_torch (4-tap weights)
   * centerpoint/det3d_ms/ops/test_custom_pytorch/iou3d_nms_kernel.cu:42,347-358  EPS and iou_normal, cut out of the
     file where it lies by oracle/Makefile and compiled for the host (oracle/ref_cu_device_harness.cpp ->
@@ -271,6 +273,22 @@ def main():
             if not lattice:
                 assert np.abs(m[np.triu_indices(n, 1)] - t).min() > 1e-5   # no pair on the threshold
             out[f"ioun_{tag}_{thr}_keep"] = ref_keep(b7, t)
+
+    # ---- topk_ (pointpillars/src/core/nms.py:66-83), the reference's numpy top-k (argpartition + argsort; it returns the
+    # K-1 best: `K = K - 1` on its first line).  Unique scores, so tie order cannot matter.
+    sc = (rng2.permutation(20000).astype(np.float32) / np.float32(20000) - np.float32(0.5)) * np.float32(12)
+    assert len(np.unique(sc)) == len(sc)
+    vals, idx = ref_nms.topk_(sc[:, None], 1001, axis=0)
+    out["topk_scores"] = sc
+    out["topk_ref_vals"] = vals[:, 0].astype(np.float32)
+    out["topk_ref_idx"] = idx[:, 0].astype(np.int64)
+
+    # ---- kitti_common.iou (pointpillars/src/data/kitti_common.py:10-73): vectorised numpy IoU, with and without the +1
+    for name in ("skimage", "skimage.io"):          # imported at the top of kitti_common.py (image loading), never called here
+        sys.modules.setdefault(name, types.ModuleType(name))
+    from src.data import kitti_common
+    out["iou0_mat_kitti"] = kitti_common.iou(a0, g0, add1=False).astype(np.float32)
+    out["iou1_mat_kitti"] = kitti_common.iou(a0, g0, add1=True).astype(np.float32)
 
     path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "reference_golden.npz")   # argv[1]: tests/test_golden_regenerates.py
     np.savez_compressed(path, **out)

@@ -39,3 +39,12 @@ def test_nms_normal_gpu_vs_reference_iou_normal_golden(golden, tag):
         got = keep.cpu().numpy()
         assert int(num) == len(ref_keep), (tag, thr)
         assert np.array_equal(got[:len(ref_keep)], ref_keep) and not got[len(ref_keep):].any(), (tag, thr)
+
+
+def test_topk_vs_reference_numpy_topk_golden(golden):
+    # MdTopKPerLevel against outputs of the reference's own numpy top-k (pointpillars/src/core/nms.py:66-83), unique scores
+    from minddet_b200 import TopKPerLevel
+    sc, rv, ri = golden["topk_scores"], golden["topk_ref_vals"], golden["topk_ref_idx"]
+    vals, idx = TopKPerLevel(len(ri))(dev(sc[None]))
+    assert np.array_equal(idx[0].cpu().numpy(), ri.astype(np.int32))
+    assert np.array_equal(vals[0].cpu().numpy(), rv)

@@ -177,3 +177,20 @@ def test_reference_gpu_file_and_cpu_file_agree_bit_for_bit():
         boxes, thr = g[f"nms_{tag}_boxes"], g[f"nms_{tag}_thr"][0]
         n = int(g[f"nms_{tag}_count_gt"][0])
         assert np.array_equal(bev.ref_cu_nms(boxes, thr, rotated=True), g[f"nms_{tag}_keep_gt"][:n]), tag
+
+
+def test_topk_matches_the_references_numpy_topk(golden):
+    # pointpillars/src/core/nms.py:66-83 (`topk_`: argpartition + argsort, returns the K-1 best) on unique scores:
+    # values and indices of the sorted top-k (a3); the tie order stays a decision (CONVENTIONS #3).
+    sc, rv, ri = golden["topk_scores"], golden["topk_ref_vals"], golden["topk_ref_idx"]
+    v, i = O.topk(sc, len(ri))
+    assert len(ri) == 1000 and np.array_equal(i, ri) and np.array_equal(v, rv)
+
+
+def test_iou_both_offsets_match_kitti_common_iou(golden):
+    # pointpillars/src/data/kitti_common.py:10-73 (vectorised numpy, add1 False / True) on the iou0 fixture boxes
+    a, g = golden["iou0_boxes"], golden["iou0_gts"]
+    for off, name in ((0.0, "iou0_mat_kitti"), (1.0, "iou1_mat_kitti")):
+        got, ref = O.iou_matrix(a, g, off=off), golden[name]
+        assert np.array_equal(got == 0, ref == 0), name
+        np.testing.assert_allclose(got, ref, rtol=2e-6, atol=1e-7, err_msg=name)
