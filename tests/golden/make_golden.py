@@ -14,6 +14,7 @@ What is executed (all paths relative to /root/reference/minddet/models):
   * pointpillars/src/core/eval_utils.py:118-165   image_box_overlap(boxes, query, criterion=-1)
   * pointpillars/src/data/kitti_common.py:10-73    iou(boxes1, boxes2, add1)
   * pointpillars/src/core/nms.py:66-83            topk_(matrix, K, axis=0)
+  * pointpillars/src/predict.py:98-112            softmax(x, axis=1), sigmoid(x)
   * centerpoint/det3d_ms/core/utils/center_utils.py:97-131  bilinear_interpolate_torch (4-tap weights)
   * centerpoint/det3d_ms/ops/test_custom_pytorch/iou3d_nms_kernel.cu:42,347-358  EPS and iou_normal, cut out of the
     file where it lies by oracle/Makefile and compiled for the host (oracle/ref_cu_device_harness.cpp ->
@@ -53,6 +54,10 @@ def _stub_mindspore():
     sys.modules["mindspore"] = ms
     sys.modules["mindspore.ops"] = ms.ops
     sys.modules["mindspore.nn"] = ms.nn
+    ms.dtype = types.ModuleType("mindspore.dtype")               # imported (never touched) by pointpillars/src/predict.py
+    ms.numpy = types.ModuleType("mindspore.numpy")
+    sys.modules["mindspore.dtype"] = ms.dtype
+    sys.modules["mindspore.numpy"] = ms.numpy
     ms.common = types.ModuleType("mindspore.common")           # imported (never called) by circle_nms_jit.py
     ms.common.dtype = types.ModuleType("mindspore.common.dtype")
     sys.modules["mindspore.common"] = ms.common
@@ -289,6 +294,16 @@ def main():
     from src.data import kitti_common
     out["iou0_mat_kitti"] = kitti_common.iou(a0, g0, add1=False).astype(np.float32)
     out["iou1_mat_kitti"] = kitti_common.iou(a0, g0, add1=True).astype(np.float32)
+
+    # ---- sigmoid / softmax (pointpillars/src/predict.py:98-112): the score activations of the post-process rows
+    from src import predict
+    ax = rng2.normal(0, 3, (300, 16)).astype(np.float32)
+    ax[0, :8] = [-30, -20, -10, -1e-3, 0, 1e-3, 10, 20]
+    ax[1] = 0.0
+    ax[2] = np.linspace(-12, 12, 16, dtype=np.float32)
+    out["act_x"] = ax
+    out["act_sigmoid_ref"] = predict.sigmoid(ax).astype(np.float32)
+    out["act_softmax_ref"] = predict.softmax(ax, axis=1).astype(np.float32)
 
     path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "reference_golden.npz")   # argv[1]: tests/test_golden_regenerates.py
     np.savez_compressed(path, **out)

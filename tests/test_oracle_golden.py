@@ -194,3 +194,11 @@ def test_iou_both_offsets_match_kitti_common_iou(golden):
         got, ref = O.iou_matrix(a, g, off=off), golden[name]
         assert np.array_equal(got == 0, ref == 0), name
         np.testing.assert_allclose(got, ref, rtol=2e-6, atol=1e-7, err_msg=name)
+
+
+def test_score_activations_match_the_references_numpy_functions(golden):
+    # pointpillars/src/predict.py:98-112: sigmoid = 1 / (1 + 1 / exp(x)), softmax = exp(x) / sum exp(x) (no max shift).
+    # The oracle's own exp (CONVENTIONS #6) and its max-shifted softmax agree to a few ulp.
+    x = golden["act_x"]
+    np.testing.assert_allclose(O.sigmoid(x), golden["act_sigmoid_ref"], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(O.softmax_rows(x), golden["act_softmax_ref"], rtol=4e-6, atol=0)
