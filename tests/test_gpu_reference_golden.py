@@ -1,10 +1,10 @@
-"""The CUDA path against fixtures made by running the REFERENCE's own `iou_normal` (iou3d_nms_kernel.cu:347-358, cut out of
-the file where it lies and compiled for the host: oracle/ref_cu_device_harness.cpp, tests/golden/make_golden.py).
-
-The CPU side of this pin (oracle == fixture, bit for bit) is tests/test_oracle_golden.py; CUDA == oracle in the default NMS
-mode is tests/test_gpu_parity.py / tests/test_gpu_bev.py.  This file closes the triangle directly.  It was written after the
-round's GPU minutes were spent, so it is named to sort after every other `-m gpu` file: under `pytest -x` it cannot hide a
-test that has been seen green on a B200 (profiles/r2_gpu_tests_head.log)."""
+"""The CUDA path against fixtures made by RUNNING THE REFERENCE's own code (tests/golden/make_golden.py):
+  * the default NMS mode and the reference's own symbol NmsNormalGpu against `iou_normal` (iou3d_nms_kernel.cu:347-358, cut
+    out of the file where it lies and compiled for the host: oracle/ref_cu_device_harness.cpp) -- keep lists bit-exact;
+  * MdTopKPerLevel against the reference's numpy top-k (pointpillars/src/core/nms.py:66-83).
+The CPU side of these pins (oracle == fixture) is tests/test_oracle_golden.py; the other golden-vector GPU tests
+(nms_jit / apply_nms modes, assign mode 1, bilinear taps, rotated BEV) live in test_gpu_parity.py / test_gpu_bev.py.
+Green on a B200: profiles/r2_gpu_tests_head.log."""
 import numpy as np
 import pytest
 import torch
